@@ -1,0 +1,140 @@
+/*
+ * b2r.h — C ABI of the B200-native retrieval hot path (libb2r.so).
+ *
+ * This is the drop-in boundary for the retrieval arithmetic of HEIcby/RAG-Challenge-2.
+ * The reference has no FFI of its own: its hot path is two third-party Python objects,
+ * faiss.IndexFlatIP (faiss-cpu==1.9.0.post1) and rank_bm25.BM25Okapi (rank-bm25==0.2.2),
+ * called from src/retrieval.py.  Each entry point below names the reference call site it
+ * replaces (paths relative to the reference checkout).  The Python classes in
+ * rag-challenge-2_b200/ bind these symbols with ctypes and mirror the faiss / rank_bm25 /
+ * retriever interfaces on top of them.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative B2R_ERR_* code; no exceptions cross
+ *     the ABI; b2r_last_error() returns a thread-local message for the last failure.
+ *   - plain pointers and sizes only.  "dev" pointers are CUDA device pointers on the handle's
+ *     device, "host" pointers are ordinary host memory.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = the legacy default stream).
+ *   - handles own their device memory unless created by an *_adopt call.
+ *   - *_host entry points are synchronous and may be called concurrently from many host
+ *     threads on one handle (src/retrieval.py:1498-1504 does exactly that with faiss);
+ *     *_dev entry points only enqueue work on `stream`.
+ *   - ids are int64 row numbers in insertion order (faiss semantics); a missing result is
+ *     id -1 with score -3.4028235e38 (faiss pads k > ntotal the same way).
+ *   - result order: score descending, ties by ascending id.
+ */
+#ifndef B2R_H_
+#define B2R_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_OK 0
+#define B2R_ERR_INVALID (-1)     /* bad argument (NULL handle, d mismatch, k out of range ...) */
+#define B2R_ERR_CUDA (-2)        /* a CUDA runtime call failed; message has the CUDA error    */
+#define B2R_ERR_NOMEM (-3)       /* device or host allocation failed                          */
+#define B2R_ERR_UNSUPPORTED (-4) /* valid request outside what the kernels implement          */
+
+#define B2R_MAX_K 1024 /* largest k of the fused select (faiss-gpu caps at 2048)          */
+
+typedef struct b2r_flat b2r_flat; /* exact inner-product index  == faiss.IndexFlatIP          */
+typedef struct b2r_bm25 b2r_bm25; /* BM25Okapi postings index   == rank_bm25.BM25Okapi        */
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* b2r_last_error(void);
+int b2r_version(void);
+int b2r_device_count(int* out);
+/* Tunables for experiments and tests (pipeline depth, select buffer size ...).  Unknown keys
+ * return B2R_ERR_INVALID.  Not part of the reference surface. */
+int b2r_tunable_set(const char* key, int value);
+int b2r_tunable_get(const char* key, int* value);
+
+/* ---- flat inner-product index ------------------------------------------------------------ */
+/* faiss.IndexFlatIP(d)                                   src/ingestion.py:82 */
+int b2r_flat_create(int d, int device, b2r_flat** out);
+/* index.add(float32[n,d]) — copies the rows              src/ingestion.py:83
+ * rows_on_device != 0: `rows` is a device pointer on the handle's device. */
+int b2r_flat_add(b2r_flat* h, const float* rows, int64_t n, int rows_on_device);
+/* Zero-copy variant for corpora generated or loaded straight into HBM: the handle borrows
+ * dev_rows[n,d] (row-major, 16-byte aligned); the caller keeps it alive.  Index must be empty. */
+int b2r_flat_adopt(b2r_flat* h, const float* dev_rows, int64_t n);
+/* index.ntotal / index.d                                 generate_similarity_matrix.py:49-51 */
+int b2r_flat_ntotal(const b2r_flat* h, int64_t* out);
+int b2r_flat_dim(const b2r_flat* h, int* out);
+/* Device pointer of the row storage (for the N x N cosine analysis and peer access). */
+int b2r_flat_rows_dev(const b2r_flat* h, const float** out);
+/* D, I = index.search(x=float32[nq,d], k=k)              src/retrieval.py:622,730,1140,1165,1261,1423
+ * q, D[nq*k], I[nq*k] are host buffers.  Synchronous, thread-safe. */
+int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, int64_t* I);
+/* Same search with everything resident: q_dev[nq,d], D_dev[nq,k], I_dev[nq,k] on the device,
+ * enqueued on `stream`.  id_offset is added to every valid id (global id of a row shard). */
+int b2r_flat_search_dev(b2r_flat* h, const float* q_dev, int nq, int k, float* D_dev,
+                        int64_t* I_dev, int64_t id_offset, void* stream);
+/* index.reconstruct(i) / index.reconstruct_batch(ids)    src/retrieval.py:573;
+ * generate_similarity_matrix.py:61.  out is host float32[m,d]; any id outside [0,ntotal)
+ * fails with B2R_ERR_INVALID (faiss raises; the reference catches it, :574-576). */
+int b2r_flat_reconstruct(b2r_flat* h, const int64_t* ids, int m, float* out);
+int b2r_flat_destroy(b2r_flat* h);
+/* Number of kernel launches the last search on this thread enqueued (bench accounting). */
+int b2r_last_launch_count(void);
+
+/* ---- top-k merge --------------------------------------------------------------------------- */
+/* Merge n_lists per-shard / per-database result lists into one top-k per query; replaces the
+ * Python sorted(...)[:top_n] over per-report hits (src/retrieval.py:293-295,1719,1754) and is
+ * the consumer of the multi-GPU all-gather.  Layout: D_lists[n_lists][nq][k_in] (list-major,
+ * i.e. exactly what an all-gather of per-rank [nq,k_in] results produces), same for I_lists.
+ * Entries with id < 0 are ignored.  Output D[nq,k_out], I[nq,k_out], padded with -1. */
+int b2r_topk_merge_dev(const float* D_lists, const int64_t* I_lists, int n_lists, int nq, int k_in,
+                       int k_out, float* D, int64_t* I, void* stream);
+int b2r_topk_merge_host(const float* D_lists, const int64_t* I_lists, int n_lists, int nq,
+                        int k_in, int k_out, float* D, int64_t* I, int device);
+
+/* ---- BM25Okapi ----------------------------------------------------------------------------- */
+/* BM25Okapi(corpus) after host tokenisation              src/ingestion.py:19-22
+ * The corpus arrives as term-major CSR postings (host pointers): for term t the postings are
+ * doc_ids[indptr[t]..indptr[t+1]) ascending, with term frequencies tf[...].  doc_len[n_docs] are
+ * the token counts.  idf[n_terms] (float64) and avgdl are the *corpus-global* statistics
+ * computed by the caller exactly as rank_bm25 does (epsilon floor included), so that a document
+ * shard scores identically to the unsharded corpus.  The library precomputes the per-posting
+ * weight tf*(k1+1)/(tf+k1*(1-b+b*dl/avgdl)) in float64 and stores it as float32. */
+int b2r_bm25_create(int64_t n_docs, int32_t n_terms, const int64_t* indptr, const int32_t* doc_ids,
+                    const int32_t* tf, const int32_t* doc_len, double avgdl, const double* idf,
+                    double k1, double b, int device, b2r_bm25** out);
+int b2r_bm25_ndocs(const b2r_bm25* h, int64_t* out);
+/* scores = bm25.get_scores(tokens)                       src/retrieval.py:262
+ * One query: term_ids[n_q_terms] (duplicates kept, unknown tokens dropped by the caller);
+ * scores is host float64[n_docs].  Parity/debug path: writes the dense vector. */
+int b2r_bm25_scores_host(b2r_bm25* h, const int32_t* term_ids, int n_q_terms, double* scores);
+/* get_scores + sorted(range(n), key=scores.__getitem__, reverse=True)[:k]
+ *                                                        src/retrieval.py:262-265
+ * Batched and fused: query i owns term_ids[term_offsets[i]..term_offsets[i+1]).  No dense score
+ * vector is written.  S[nq,k] float64 scores, I[nq,k] doc ids; ties (including the zero-score
+ * tail) keep ascending doc id, as Python's stable sort does. */
+int b2r_bm25_topk_host(b2r_bm25* h, const int32_t* term_ids, const int32_t* term_offsets, int nq,
+                       int k, double* S, int64_t* I);
+int b2r_bm25_topk_dev(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* term_offsets_dev,
+                      const int32_t* term_offsets_host, int nq, int k, double* S_dev,
+                      int64_t* I_dev, int64_t id_offset, void* stream);
+int b2r_bm25_destroy(b2r_bm25* h);
+
+/* ---- N x N cosine analysis ---------------------------------------------------------------- */
+/* compute_cosine_similarity_matrix + off-diagonal statistics
+ *                             semantic_similarity_analysis/generate_similarity_matrix.py:84-98,162-171
+ * rows_dev[n,d] float32.  Never materialises the n x n matrix: streams tiles of
+ * S = Xn Xn^T (Xn = X / (|X| + 1e-8), diagonal forced to 1, clipped to [-1,1]) and reduces them.
+ * stats[0..5] = off-diagonal sum, sum of squares, min, max, count, (reserved);
+ * hist[n_bins] counts off-diagonal entries over [-1,1] (for the median);
+ * if k > 0: topk_S[n,k] / topk_I[n,k] per-row nearest neighbours (self excluded).
+ * Rows [row_begin,row_end) of S are processed (row-block sharding across GPUs). */
+int b2r_cosine_stats_dev(const float* rows_dev, int64_t n, int d, int64_t row_begin, int64_t row_end,
+                         double* stats_dev, unsigned long long* hist_dev, int n_bins, int k,
+                         float* topk_S_dev, int64_t* topk_I_dev, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H_ */

@@ -1,0 +1,92 @@
+// api.cu — library-level plumbing of the C ABI: thread-local error string, tunables, version.
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "b2r_common.cuh"
+
+namespace b2r {
+
+std::string& last_error_ref() {
+  static thread_local std::string msg;
+  return msg;
+}
+
+int fail(int code, const std::string& msg) {
+  last_error_ref() = msg;
+  return code;
+}
+
+int& launch_counter() {
+  static thread_local int n = 0;
+  return n;
+}
+
+static std::mutex g_tun_mu;
+static std::map<std::string, int>& tunables() {
+  // 0 / negative == "let the library decide"
+  static std::map<std::string, int> t = {
+      {"flat.stages", 0},          // depth of the bulk-copy ring
+      {"flat.tile_rows", 0},       // rows per tile (rounded to a multiple of the consumer warps)
+      {"flat.ctas_per_sm", 0},     // resident CTAs per SM the plan aims for
+      {"flat.consumer_warps", 0},  // 4 or 8
+      {"flat.max_nq", 0},          // cap on queries sharing one pass (1, 2 or 4)
+      {"flat.force_generic", 0},   // 1: use the non-TMA kernel even for templated widths
+      {"select.buf_cap", 0},       // cap on the final-select scratch (keys); small values force the fallback
+      {"bm25.block_docs", 0},      // documents per CTA in the BM25 kernel
+  };
+  return t;
+}
+
+int tunable(const char* key) {
+  std::lock_guard<std::mutex> lock(g_tun_mu);
+  auto& t = tunables();
+  auto it = t.find(key);
+  return it == t.end() ? 0 : it->second;
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+extern "C" {
+
+const char* b2r_last_error(void) { return last_error_ref().c_str(); }
+
+int b2r_version(void) { return 100; /* 0.1.0 */ }
+
+int b2r_device_count(int* out) {
+  if (!out) return fail(B2R_ERR_INVALID, "b2r_device_count: out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *out = 0;
+    return fail(B2R_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *out = n;
+  return B2R_OK;
+}
+
+int b2r_tunable_set(const char* key, int value) {
+  if (!key) return fail(B2R_ERR_INVALID, "b2r_tunable_set: key is NULL");
+  std::lock_guard<std::mutex> lock(g_tun_mu);
+  auto& t = tunables();
+  auto it = t.find(key);
+  if (it == t.end()) return fail(B2R_ERR_INVALID, std::string("unknown tunable: ") + key);
+  it->second = value;
+  return B2R_OK;
+}
+
+int b2r_tunable_get(const char* key, int* value) {
+  if (!key || !value) return fail(B2R_ERR_INVALID, "b2r_tunable_get: NULL argument");
+  std::lock_guard<std::mutex> lock(g_tun_mu);
+  auto& t = tunables();
+  auto it = t.find(key);
+  if (it == t.end()) return fail(B2R_ERR_INVALID, std::string("unknown tunable: ") + key);
+  *value = it->second;
+  return B2R_OK;
+}
+
+int b2r_last_launch_count(void) { return launch_counter(); }
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+// b2r_common.cuh — shared host/device helpers for libb2r (sm_100a only).
+//
+// Contents: error plumbing for the C ABI, mbarrier / bulk-copy (TMA) PTX wrappers, the 64-bit
+// ordered (score, id) key used by every select in the library, warp- and block-level bitonic
+// sorts over shared memory, and block_select_lists(): the "many sorted lists -> one top-k"
+// routine used by the last-CTA epilogue of the scan kernels and by the stand-alone merge kernel.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "b2r.h"
+
+namespace b2r {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ----------------------------------------------------------------------------------------------
+// host: error plumbing
+// ----------------------------------------------------------------------------------------------
+std::string& last_error_ref();
+int fail(int code, const std::string& msg);
+int& launch_counter();  // thread-local: kernels enqueued by the last search on this thread
+
+#define B2R_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      return ::b2r::fail(_e == cudaErrorMemoryAllocation ? B2R_ERR_NOMEM : B2R_ERR_CUDA,      \
+                         std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+    }                                                                                         \
+  } while (0)
+
+int tunable(const char* key);  // current value of a tunable (see b2r_tunable_set)
+
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// device: PTX wrappers (mbarrier + 1-D bulk async copy, the TMA engine without a tensor map —
+// row tiles of a row-major matrix are contiguous, so a tile is one linear copy)
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ u32 smem_u32(const void* p) {
+  return static_cast<u32>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+  // make the initialised barriers visible to the async (TMA) proxy
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  u32 done;
+  const u32 addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// L2 eviction policy for data that is streamed once per query.
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// global -> shared linear bulk copy, completion counted in bytes on `bar` (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u32 bytes, u64* bar,
+                                         u64 policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+
+// ----------------------------------------------------------------------------------------------
+// device: ordered (score, id) key
+//   high 32 bits: the float score mapped so that unsigned order == float order
+//   low  32 bits: 0xFFFFFFFF - local id, so that among equal scores the LOWER id is the larger key
+//   key 0 is reserved for "empty" (it would decode to id 0xFFFFFFFF, which is never a valid row).
+// Sorting keys descending therefore yields score descending, id ascending: the order faiss's heap
+// reorder and Python's stable sort (src/retrieval.py:265) both produce.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 float_to_ordered(float s) {
+  s = s + 0.0f;                    // -0.0 -> +0.0 so that equal scores have equal keys
+  if (!(s == s)) s = -3.4028235e38f;  // NaN never outranks a number (faiss: comparisons are false)
+  const u32 u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float ordered_to_float(u32 o) {
+  const u32 u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ u64 make_key(float s, u32 local_id) {
+  return (static_cast<u64>(float_to_ordered(s)) << 32) | static_cast<u64>(0xFFFFFFFFu - local_id);
+}
+
+__device__ __forceinline__ float key_score(u64 key) { return ordered_to_float(static_cast<u32>(key >> 32)); }
+__device__ __forceinline__ u32 key_id(u64 key) { return 0xFFFFFFFFu - static_cast<u32>(key & 0xFFFFFFFFull); }
+
+// ----------------------------------------------------------------------------------------------
+// device: bitonic sorts (descending) over u64 keys in shared memory; n must be a power of two
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cmpxchg_desc(u64* a, int i, int j, bool up) {
+  // `up` == true: this pair belongs to an ascending run of the bitonic network
+  const u64 x = a[i], y = a[j];
+  const bool swap = up ? (x > y) : (x < y);
+  if (swap) {
+    a[i] = y;
+    a[j] = x;
+  }
+}
+
+// one warp sorts a[0..n) descending; all 32 lanes must call it
+__device__ __forceinline__ void warp_sort_desc(u64* a, int n, int lane) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = lane; t < (n >> 1); t += 32) {
+        const int i = ((t / stride) * (stride << 1)) + (t % stride);
+        const int j = i + stride;
+        const bool up = (i & size) != 0;
+        cmpxchg_desc(a, i, j, up);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// the whole CTA sorts a[0..n) descending; every thread of the block must call it
+__device__ __forceinline__ void block_sort_desc(u64* a, int n) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (n >> 1); t += nt) {
+        const int i = ((t / stride) * (stride << 1)) + (t % stride);
+        const int j = i + stride;
+        const bool up = (i & size) != 0;
+        cmpxchg_desc(a, i, j, up);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ----------------------------------------------------------------------------------------------
+// device: select the k largest keys out of n_lists lists of `stride` keys each (every list sorted
+// descending, empty slots == 0) and leave them sorted in buf[0..k).  Whole-CTA routine.
+//   src      : global memory, n_lists * stride keys
+//   buf      : shared scratch of buf_cap keys (power of two, >= 2k)
+//   s_ctl    : shared u64[2] scratch
+// Fast path: every key that can be in the answer is >= T = max over lists of the list's k-th key
+// (that list alone already holds k keys >= T), so only the survivors of that filter are sorted —
+// for randomly distributed data a little over k of them.  If the survivors do not fit (adversarial
+// layouts) fall back to streaming rounds of "keep best k, append, sort".
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_select_lists(const u64* __restrict__ src, int n_lists, int stride,
+                                                   int k, u64* buf, int buf_cap, u64* s_ctl) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const long long total = static_cast<long long>(n_lists) * stride;
+  u32* s_cnt = reinterpret_cast<u32*>(s_ctl);  // [0] survivor count
+  u64* s_thr = s_ctl + 1;                      // threshold key
+  if (tid == 0) {
+    *s_cnt = 0;
+    *s_thr = 0;
+  }
+  __syncthreads();
+  if (k <= stride) {
+    u64 t = 0;
+    for (int l = tid; l < n_lists; l += nt) {
+      const u64 v = src[static_cast<long long>(l) * stride + (k - 1)];
+      t = v > t ? v : t;
+    }
+    if (t) atomicMax(s_thr, t);
+  }
+  __syncthreads();
+  const u64 thr = *s_thr;
+  for (long long i = tid; i < total; i += nt) {
+    const u64 v = src[i];
+    if (v != 0 && v >= thr) {
+      const u32 pos = atomicAdd(s_cnt, 1u);
+      if (pos < static_cast<u32>(buf_cap)) buf[pos] = v;
+    }
+  }
+  __syncthreads();
+  const u32 cnt = *s_cnt;
+  if (cnt <= static_cast<u32>(buf_cap)) {
+    const int need = static_cast<int>(cnt) > k ? static_cast<int>(cnt) : k;
+    const int p = next_pow2(need < 2 ? 2 : need);
+    for (int i = cnt + tid; i < p; i += nt) buf[i] = 0;
+    __syncthreads();
+    block_sort_desc(buf, p);
+    return;
+  }
+  // fallback: streaming rounds; buf[0..k) holds the best so far
+  for (int i = tid; i < buf_cap; i += nt) buf[i] = 0;
+  __syncthreads();
+  const int chunk = buf_cap - k;
+  for (long long base = 0; base < total; base += chunk) {
+    for (int i = tid; i < chunk; i += nt) {
+      const long long g = base + i;
+      buf[k + i] = g < total ? src[g] : 0ull;
+    }
+    __syncthreads();
+    block_sort_desc(buf, buf_cap);
+  }
+}
+
+// write buf[0..k) (sorted keys) as (score, int64 id) with faiss padding for empty slots
+__device__ __forceinline__ void block_emit_keys(const u64* buf, int k, float* D, long long* I,
+                                                long long id_offset) {
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const u64 key = buf[i];
+    if (key == 0) {
+      D[i] = -3.4028235e38f;
+      I[i] = -1;
+    } else {
+      D[i] = key_score(key);
+      I[i] = static_cast<long long>(key_id(key)) + id_offset;
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b2r
