@@ -104,7 +104,17 @@ int b2r_topk_merge_host(const float* D_lists, const int64_t* I_lists, int n_list
 int b2r_bm25_create(int64_t n_docs, int32_t n_terms, const int64_t* indptr, const int32_t* doc_ids,
                     const int32_t* tf, const int32_t* doc_len, double avgdl, const double* idf,
                     double k1, double b, int device, b2r_bm25** out);
+/* Extended form: inputs_on_device != 0 takes all array arguments as device pointers (corpora built
+ * in HBM; the arrays are only read during the call); weight_bits = 32 stores float32 weights
+ * (8 B / posting), 64 keeps float64 weights (12 B / posting) — scores are then bit-identical to
+ * rank_bm25's float64 arithmetic. */
+int b2r_bm25_create_ex(int64_t n_docs, int32_t n_terms, const int64_t* indptr, const int32_t* doc_ids,
+                       const int32_t* tf, const int32_t* doc_len, double avgdl, const double* idf,
+                       double k1, double b, int device, int inputs_on_device, int weight_bits,
+                       b2r_bm25** out);
 int b2r_bm25_ndocs(const b2r_bm25* h, int64_t* out);
+/* number of postings and the stored weight width (bench accounting: bytes per posting) */
+int b2r_bm25_postings(const b2r_bm25* h, int64_t* n_post, int* weight_bits);
 /* scores = bm25.get_scores(tokens)                       src/retrieval.py:262
  * One query: term_ids[n_q_terms] (duplicates kept, unknown tokens dropped by the caller);
  * scores is host float64[n_docs].  Parity/debug path: writes the dense vector. */

@@ -53,7 +53,7 @@ def flat_ip_search_ref(xb, xq, k):
     return topk_from_scores(flat_ip_scores_ref(xb, xq, np.float32), int(k))
 
 
-def assert_topk_equivalent(D, I, S_ref, k, rtol=1e-5, atol=1e-6, what="top-k"):
+def assert_topk_equivalent(D, I, S_ref, k, rtol=1e-5, atol=1e-6, what="top-k", pad_score=NEG):
     """Check a (D, I) result against full reference scores S_ref [nq, n] (fp32 or fp64).
 
     north_star's bar: identical top-k ids except ties within tolerance, scores within 1e-5 relative.
@@ -73,7 +73,7 @@ def assert_topk_equivalent(D, I, S_ref, k, rtol=1e-5, atol=1e-6, what="top-k"):
         assert np.all((ids >= 0) & (ids < n)), f"{what}: q{qi} invalid id in {ids}"
         assert len(set(ids.tolist())) == kk, f"{what}: q{qi} duplicate ids"
         assert np.all(I[qi, kk:] == -1), f"{what}: q{qi} padding ids not -1"
-        assert np.all(D[qi, kk:] == NEG), f"{what}: q{qi} padding scores not -FLT_MAX"
+        assert np.all(D[qi, kk:] == pad_score), f"{what}: q{qi} padding scores are not the pad value"
         ref_scores = S_ref[qi, ids]
         tol = atol + rtol * np.abs(ref_scores)
         assert np.all(np.abs(D[qi, :kk] - ref_scores) <= tol), (

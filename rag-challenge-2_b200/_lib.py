@@ -50,7 +50,10 @@ SIGNATURES = {
     "b2r_topk_merge_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "b2r_bm25_create": (C.c_int, [C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_double,
                                   C.c_double, C.c_int, C.POINTER(_vp)]),
+    "b2r_bm25_create_ex": (C.c_int, [C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_double,
+                                     C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "b2r_bm25_ndocs": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "b2r_bm25_postings": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "b2r_bm25_scores_host": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "b2r_bm25_topk_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b2r_bm25_topk_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp]),

@@ -1,0 +1,268 @@
+"""BM25Okapi — the rank_bm25.BM25Okapi surface the reference uses, scored on the GPU by libb2r.
+
+Reference call sites (paths relative to the reference checkout):
+  BM25Okapi([chunk.split() for chunk in chunks])          src/ingestion.py:19-22
+  pickle.dump / pickle.load of the index object           src/ingestion.py:46-47, src/retrieval.py:253-254
+  bm25_index.get_scores(query.split())                    src/retrieval.py:261-262
+  sorted(range(n), key=scores.__getitem__, reverse=True)  src/retrieval.py:265   (-> topk())
+
+Host side (this file): tokenised corpus -> vocabulary, term-major CSR postings, and the corpus
+statistics exactly as rank-bm25 0.2.2 computes them (idf with the epsilon floor, avgdl; Python
+float arithmetic in the same order).  Device side (csrc/bm25.cu): per-posting weights, scoring and
+the fused top-k.  There is no CPU scoring path.
+"""
+import ctypes as C
+import math
+import pickle
+
+import numpy as np
+
+from . import _lib
+
+
+def corpus_statistics(nd, corpus_size, epsilon=0.25):
+    """rank_bm25.BM25Okapi._calc_idf: nd maps word -> number of documents containing it (dict order
+    is preserved because the average is a running Python float sum)."""
+    idf = {}
+    idf_sum = 0
+    negative = []
+    for word, freq in nd.items():
+        v = math.log(corpus_size - freq + 0.5) - math.log(freq + 0.5)
+        idf[word] = v
+        idf_sum += v
+        if v < 0:
+            negative.append(word)
+    average_idf = idf_sum / len(idf)
+    eps = epsilon * average_idf
+    for word in negative:
+        idf[word] = eps
+    return idf, average_idf
+
+
+class BM25Okapi:
+    """Drop-in for rank_bm25.BM25Okapi; `device` selects the GPU that holds the postings."""
+
+    def __init__(self, corpus, tokenizer=None, k1=1.5, b=0.75, epsilon=0.25, device=0, weight_bits=32):
+        self.k1, self.b, self.epsilon = k1, b, epsilon
+        self.tokenizer = tokenizer
+        self.device = int(device)
+        self.weight_bits = int(weight_bits)
+        self._h = None
+        self._vocab = None
+        if tokenizer is not None:
+            corpus = [tokenizer(doc) for doc in corpus]
+        self.corpus_size = 0
+        self.doc_len = []
+        self.doc_freqs = []
+        nd = {}
+        num_tokens = 0
+        for document in corpus:
+            self.doc_len.append(len(document))
+            num_tokens += len(document)
+            freqs = {}
+            for word in document:
+                freqs[word] = freqs.get(word, 0) + 1
+            self.doc_freqs.append(freqs)
+            for word in freqs:
+                nd[word] = nd.get(word, 0) + 1
+            self.corpus_size += 1
+        self.avgdl = num_tokens / self.corpus_size  # ZeroDivisionError on an empty corpus, like rank_bm25
+        self.idf, self.average_idf = corpus_statistics(nd, self.corpus_size, epsilon)
+        self._build_from_doc_freqs()
+
+    # ---- alternative constructors ---------------------------------------------------------------
+    @classmethod
+    def from_postings(cls, indptr, doc_ids, tf, doc_len, idf, avgdl, k1=1.5, b=0.75, device=0, weight_bits=32,
+                      vocab=None):
+        """Build from term-major CSR postings (numpy arrays, or CUDA tensors for corpora generated in
+        HBM).  `idf` / `avgdl` are the corpus-global statistics, so a document shard scores exactly
+        like the unsharded corpus.  vocab: optional dict token -> term id for string queries."""
+        self = cls.__new__(cls)
+        self.k1, self.b, self.epsilon = k1, b, None
+        self.tokenizer = None
+        self.device = int(device)
+        self.weight_bits = int(weight_bits)
+        self.doc_freqs = None
+        self.idf = None
+        self.average_idf = None
+        self.avgdl = float(avgdl)
+        self._vocab = vocab
+        self._h = None
+        on_dev = hasattr(indptr, "is_cuda")
+        if on_dev:
+            import torch
+
+            args = [indptr.to(torch.int64).contiguous(), doc_ids.to(torch.int32).contiguous(),
+                    tf.to(torch.int32).contiguous(), doc_len.to(torch.int32).contiguous(),
+                    idf.to(torch.float64).contiguous()]
+            self.corpus_size = int(doc_len.shape[0])
+            n_terms = int(indptr.shape[0]) - 1
+            ptrs = [C.c_void_p(a.data_ptr()) for a in args]
+            torch.cuda.synchronize(indptr.device)
+        else:
+            args = [np.ascontiguousarray(indptr, np.int64), np.ascontiguousarray(doc_ids, np.int32),
+                    np.ascontiguousarray(tf, np.int32), np.ascontiguousarray(doc_len, np.int32),
+                    np.ascontiguousarray(idf, np.float64)]
+            self.corpus_size = int(args[3].shape[0])
+            n_terms = int(args[0].shape[0]) - 1
+            ptrs = [_lib.ptr(a) for a in args]
+        self.doc_len = None
+        self._n_terms = n_terms
+        self._create(n_terms, ptrs, 1 if on_dev else 0)
+        return self
+
+    def _create(self, n_terms, ptrs, on_dev):
+        lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(lib.b2r_bm25_create_ex(self.corpus_size, n_terms, ptrs[0], ptrs[1], ptrs[2], ptrs[3],
+                                          float(self.avgdl), ptrs[4], float(self.k1), float(self.b), self.device,
+                                          on_dev, self.weight_bits, C.byref(h)))
+        self._h = h
+        self._lib = lib
+
+    def _build_from_doc_freqs(self):
+        """doc_freqs (list of {token: tf}) -> vocabulary + CSR postings -> device index."""
+        vocab = {w: i for i, w in enumerate(self.idf)}  # first-seen order, as rank_bm25's nd dict
+        n_post = sum(len(f) for f in self.doc_freqs)
+        terms = np.empty(n_post, dtype=np.int32)
+        docs = np.empty(n_post, dtype=np.int32)
+        tfs = np.empty(n_post, dtype=np.int32)
+        p = 0
+        for doc_id, freqs in enumerate(self.doc_freqs):
+            for w, f in freqs.items():
+                terms[p] = vocab[w]
+                docs[p] = doc_id
+                tfs[p] = f
+                p += 1
+        order = np.argsort(terms, kind="stable")  # stable: doc ids stay ascending inside a term
+        n_terms = len(vocab)
+        indptr = np.zeros(n_terms + 1, dtype=np.int64)
+        np.cumsum(np.bincount(terms, minlength=n_terms), out=indptr[1:])
+        idf_arr = np.array([self.idf[w] for w in vocab], dtype=np.float64)
+        args = [indptr, np.ascontiguousarray(docs[order]), np.ascontiguousarray(tfs[order]),
+                np.asarray(self.doc_len, dtype=np.int32), idf_arr]
+        self._vocab = vocab
+        self._n_terms = n_terms
+        self._create(n_terms, [_lib.ptr(a) for a in args], 0)
+
+    # ---- queries ----------------------------------------------------------------------------------
+    def _term_ids(self, query):
+        """Tokens -> term ids; unknown tokens contribute 0 in rank_bm25 and are dropped here."""
+        if len(query) and not isinstance(query[0], str):
+            return np.ascontiguousarray(query, dtype=np.int32)
+        if self._vocab is None:
+            raise ValueError("this index was built from raw postings without a vocabulary; pass term ids")
+        v = self._vocab
+        return np.array([v[t] for t in query if t in v], dtype=np.int32)
+
+    def get_scores(self, query):
+        """float64[corpus_size] — rank_bm25.BM25Okapi.get_scores(query tokens)."""
+        self._ensure_built()
+        ids = self._term_ids(query)
+        out = np.empty(self.corpus_size, dtype=np.float64)
+        _lib.check(self._lib.b2r_bm25_scores_host(self._h, _lib.ptr(ids), int(ids.shape[0]), _lib.ptr(out)))
+        return out
+
+    def topk(self, queries, k):
+        """Fused scoring + top-k for a batch: queries is a list of token lists (or term-id arrays).
+        Returns (S float64[nq,k], I int64[nq,k]) ordered like the reference's stable descending sort
+        (src/retrieval.py:265); k > corpus_size pads with id -1."""
+        self._ensure_built()
+        ids = [self._term_ids(q) for q in queries]
+        offs = np.zeros(len(ids) + 1, dtype=np.int32)
+        np.cumsum([len(a) for a in ids], out=offs[1:])
+        flat = np.ascontiguousarray(np.concatenate(ids) if ids else np.zeros(0), dtype=np.int32)
+        nq = len(ids)
+        S = np.empty((nq, int(k)), dtype=np.float64)
+        I = np.empty((nq, int(k)), dtype=np.int64)
+        _lib.check(self._lib.b2r_bm25_topk_host(self._h, _lib.ptr(flat), _lib.ptr(offs), nq, int(k), _lib.ptr(S),
+                                                _lib.ptr(I)))
+        return S, I
+
+    def topk_dev(self, term_ids, term_offsets, k, S=None, I=None, id_offset=0, stream=None):
+        """Resident batch: term_ids / term_offsets are int32 CUDA tensors; returns CUDA tensors."""
+        import torch
+
+        nq = int(term_offsets.shape[0]) - 1
+        if S is None:
+            S = torch.empty((nq, k), dtype=torch.float64, device=term_ids.device)
+        if I is None:
+            I = torch.empty((nq, k), dtype=torch.int64, device=term_ids.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(term_ids.device).cuda_stream
+        _lib.check(self._lib.b2r_bm25_topk_dev(self._h, C.c_void_p(term_ids.data_ptr()),
+                                               C.c_void_p(term_offsets.data_ptr()), None, nq, int(k),
+                                               C.c_void_p(S.data_ptr()), C.c_void_p(I.data_ptr()), int(id_offset),
+                                               C.c_void_p(stream)))
+        return S, I
+
+    def get_top_n(self, query, documents, n=5):
+        """rank_bm25.BM25.get_top_n: the n best documents (numpy argsort order upstream; here the
+        deterministic score-descending / id-ascending order of topk)."""
+        assert self.corpus_size == len(documents), "The documents given don't match the index corpus!"
+        _, I = self.topk([query], min(n, self.corpus_size))
+        return [documents[i] for i in I[0] if i >= 0]
+
+    def n_postings(self):
+        self._ensure_built()
+        n, bits = C.c_int64(0), C.c_int(0)
+        _lib.check(self._lib.b2r_bm25_postings(self._h, C.byref(n), C.byref(bits)))
+        return int(n.value), int(bits.value)
+
+    def last_launch_count(self):
+        return int(self._lib.b2r_last_launch_count())
+
+    # ---- pickling (src/ingestion.py:46-47, src/retrieval.py:253-254) -----------------------------
+    _STATE_KEYS = ("corpus_size", "avgdl", "doc_freqs", "idf", "doc_len", "tokenizer", "k1", "b", "epsilon",
+                   "average_idf")
+
+    def __getstate__(self):
+        if self.doc_freqs is None:
+            raise pickle.PicklingError("an index built from raw postings cannot be pickled")
+        return {k: getattr(self, k) for k in self._STATE_KEYS}
+
+    def __setstate__(self, state):
+        # accepts the attribute dict of a genuine rank_bm25.BM25Okapi pickle as well as our own
+        self.__dict__.update(state)
+        self.device = getattr(self, "device", 0)
+        self.weight_bits = getattr(self, "weight_bits", 32)
+        self._h = None
+        self._vocab = None
+
+    def _ensure_built(self):
+        if self._h is None:
+            self._build_from_doc_freqs()
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.b2r_bm25_destroy(h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Rank25Unpickler(pickle.Unpickler):
+    """Loads bm25_dbs/<sha1>.pkl files written by the reference (class rank_bm25.BM25Okapi) into
+    this module's BM25Okapi without rank_bm25 being installed."""
+
+    def find_class(self, module, name):
+        if module.split(".")[0] == "rank_bm25" and name in ("BM25Okapi", "BM25"):
+            return BM25Okapi
+        return super().find_class(module, name)
+
+
+def load_bm25_pickle(fileobj_or_path, device=0):
+    if hasattr(fileobj_or_path, "read"):
+        obj = _Rank25Unpickler(fileobj_or_path).load()
+    else:
+        with open(str(fileobj_or_path), "rb") as f:
+            obj = _Rank25Unpickler(f).load()
+    if not isinstance(obj, BM25Okapi):
+        raise TypeError(f"pickle holds {type(obj)!r}, not a BM25Okapi index")
+    obj.device = device
+    return obj

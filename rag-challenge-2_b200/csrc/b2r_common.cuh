@@ -17,6 +17,7 @@ namespace b2r {
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
+typedef unsigned __int128 u128;  // (ordered float64 score << 64) | inverted id — BM25 keys
 
 // ----------------------------------------------------------------------------------------------
 // host: error plumbing
@@ -145,9 +146,10 @@ __device__ __forceinline__ u32 key_id(u64 key) { return 0xFFFFFFFFu - static_cas
 // ----------------------------------------------------------------------------------------------
 // device: bitonic sorts (descending) over u64 keys in shared memory; n must be a power of two
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cmpxchg_desc(u64* a, int i, int j, bool up) {
+template <class K>
+__device__ __forceinline__ void cmpxchg_desc(K* a, int i, int j, bool up) {
   // `up` == true: this pair belongs to an ascending run of the bitonic network
-  const u64 x = a[i], y = a[j];
+  const K x = a[i], y = a[j];
   const bool swap = up ? (x > y) : (x < y);
   if (swap) {
     a[i] = y;
@@ -156,7 +158,8 @@ __device__ __forceinline__ void cmpxchg_desc(u64* a, int i, int j, bool up) {
 }
 
 // one warp sorts a[0..n) descending; all 32 lanes must call it
-__device__ __forceinline__ void warp_sort_desc(u64* a, int n, int lane) {
+template <class K>
+__device__ __forceinline__ void warp_sort_desc(K* a, int n, int lane) {
   for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = lane; t < (n >> 1); t += 32) {
@@ -171,7 +174,8 @@ __device__ __forceinline__ void warp_sort_desc(u64* a, int n, int lane) {
 }
 
 // the whole CTA sorts a[0..n) descending; every thread of the block must call it
-__device__ __forceinline__ void block_sort_desc(u64* a, int n) {
+template <class K>
+__device__ __forceinline__ void block_sort_desc(K* a, int n) {
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int size = 2; size <= n; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -203,8 +207,14 @@ __device__ __forceinline__ int next_pow2(int v) {
 // for randomly distributed data a little over k of them.  If the survivors do not fit (adversarial
 // layouts) fall back to streaming rounds of "keep best k, append, sort".
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_select_lists(const u64* __restrict__ src, int n_lists, int stride,
-                                                   int k, u64* buf, int buf_cap, u64* s_ctl) {
+// the part of a key the prefilter compares (the score bits; for 128-bit keys ties on the score
+// survive the filter and are resolved by the sort)
+__device__ __forceinline__ u64 key_prune_part(u64 k) { return k; }
+__device__ __forceinline__ u64 key_prune_part(u128 k) { return static_cast<u64>(k >> 64); }
+
+template <class K>
+__device__ __forceinline__ void block_select_lists(const K* __restrict__ src, int n_lists, int stride,
+                                                   int k, K* buf, int buf_cap, u64* s_ctl) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const long long total = static_cast<long long>(n_lists) * stride;
   u32* s_cnt = reinterpret_cast<u32*>(s_ctl);  // [0] survivor count
@@ -217,7 +227,7 @@ __device__ __forceinline__ void block_select_lists(const u64* __restrict__ src, 
   if (k <= stride) {
     u64 t = 0;
     for (int l = tid; l < n_lists; l += nt) {
-      const u64 v = src[static_cast<long long>(l) * stride + (k - 1)];
+      const u64 v = key_prune_part(src[static_cast<long long>(l) * stride + (k - 1)]);
       t = v > t ? v : t;
     }
     if (t) atomicMax(s_thr, t);
@@ -225,8 +235,8 @@ __device__ __forceinline__ void block_select_lists(const u64* __restrict__ src, 
   __syncthreads();
   const u64 thr = *s_thr;
   for (long long i = tid; i < total; i += nt) {
-    const u64 v = src[i];
-    if (v != 0 && v >= thr) {
+    const K v = src[i];
+    if (v != 0 && key_prune_part(v) >= thr) {
       const u32 pos = atomicAdd(s_cnt, 1u);
       if (pos < static_cast<u32>(buf_cap)) buf[pos] = v;
     }
@@ -248,7 +258,7 @@ __device__ __forceinline__ void block_select_lists(const u64* __restrict__ src, 
   for (long long base = 0; base < total; base += chunk) {
     for (int i = tid; i < chunk; i += nt) {
       const long long g = base + i;
-      buf[k + i] = g < total ? src[g] : 0ull;
+      buf[k + i] = g < total ? src[g] : static_cast<K>(0);
     }
     __syncthreads();
     block_sort_desc(buf, buf_cap);

@@ -1,0 +1,242 @@
+"""GPU parity: K4 BM25 scoring + fused top-k, through the C ABI, vs the rank_bm25 restatement.
+
+float64-weight indexes must reproduce the oracle's float64 scores BIT FOR BIT and the reference's
+stable-sort order exactly; float32-weight indexes (the default layout, 8 B / posting) must agree to
+1e-6 relative with top-k ids equal up to ties within that band (north_star: 1e-5).
+"""
+import io
+import pickle
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle.bm25 import bm25_scores_csr_ref
+
+pytestmark = pytest.mark.gpu
+
+PAD = -1.7976931348623157e308
+
+
+def synth(b2r):
+    from rag_challenge_2_b200 import synth as s
+
+    return s
+
+
+def as_tokens(q):
+    return [f"t{r}" for r in q]
+
+
+KAT_CORPUS = [
+    "the cat sat on the mat".split(),
+    "the dog sat on the log".split(),
+    "the cat chased the dog".split(),
+    "birds fly".split(),
+    "the the the the".split(),
+]
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+def test_kat_small_corpus(b2r, bits):
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    ref = oracle.BM25OkapiRef(KAT_CORPUS)
+    idx = BM25Okapi(KAT_CORPUS, weight_bits=bits)
+    assert idx.corpus_size == 5 and idx.avgdl == ref.avgdl
+    assert idx.idf == ref.idf and idx.average_idf == ref.average_idf
+    assert ref.idf["the"] == 0.25 * ref.average_idf  # in 4 of 5 docs -> negative idf -> epsilon floor
+    queries = [
+        ["cat"], ["the"], ["the", "cat", "the"],      # repeated token counted twice
+        ["zebra"], [], ["zebra", "dog", "unseen"],    # unknown tokens contribute 0
+        ["birds", "fly", "the", "dog", "sat"],
+    ]
+    for q in queries:
+        got, want = idx.get_scores(q), ref.get_scores(q)
+        if bits == 64:
+            assert np.array_equal(got, want), (q, got, want)
+        else:
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-12), (q, got, want)
+    # all-zero scores: the top-n is the first n ids (stable sort, src/retrieval.py:265)
+    S, I = idx.topk([["zebra"], []], 3)
+    assert np.array_equal(I, [[0, 1, 2], [0, 1, 2]]) and np.all(S == 0.0)
+    # k > corpus size pads
+    S, I = idx.topk([["cat"]], 8)
+    assert np.array_equal(I[0, :5], oracle.bm25_topn_ref(ref.get_scores(["cat"]), 8))
+    assert np.all(I[0, 5:] == -1) and np.all(S[0, 5:] == PAD)
+
+
+def test_negative_epsilon_ranks_below_zero(b2r):
+    """average_idf < 0 makes epsilon negative: documents containing the common word score below the
+    untouched (zero-score) documents, which must still fill the top-n in ascending id order."""
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    corpus = [["a", "b"], ["a", "b"], ["a"], ["c"]]
+    ref = oracle.BM25OkapiRef(corpus)
+    assert ref.average_idf < 0
+    idx = BM25Okapi(corpus, weight_bits=64)
+    for q in (["a"], ["a", "b"], ["c", "a"]):
+        want = ref.get_scores(q)
+        assert np.array_equal(idx.get_scores(q), want)
+        S, I = idx.topk([q], 4)
+        assert np.array_equal(I[0], oracle.bm25_topn_ref(want, 4))
+        assert np.array_equal(S[0], want[I[0]])
+
+
+@pytest.mark.parametrize("n_docs", [1, 37, 3000, 20000])
+def test_synthetic_corpus_bit_exact_f64(b2r, n_docs):
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    docs = s.token_corpus_np(n_docs, vocab=5000, seed=7)
+    ref = oracle.BM25OkapiRef(docs)
+    idx = BM25Okapi(docs, weight_bits=64)
+    queries = [as_tokens(q) for q in s.token_queries_np(12, vocab=5000, seed=8)]
+    wants = [ref.get_scores(q) for q in queries]
+    for q, want in zip(queries[:4], wants[:4]):
+        assert np.array_equal(idx.get_scores(q), want)
+    for k in (1, 30, 100):
+        S, I = idx.topk(queries, k)
+        for qi, want in enumerate(wants):
+            top = oracle.bm25_topn_ref(want, k)
+            assert np.array_equal(I[qi, :len(top)], top), f"n={n_docs} k={k} q{qi}"
+            assert np.array_equal(S[qi, :len(top)], want[top])
+            assert np.all(I[qi, len(top):] == -1)
+
+
+def test_synthetic_corpus_f32_weights(b2r):
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    docs = s.token_corpus_np(20000, vocab=5000, seed=9)
+    ref = oracle.BM25OkapiRef(docs)
+    idx = BM25Okapi(docs)  # default: float32 weights
+    assert idx.n_postings()[1] == 32
+    queries = [as_tokens(q) for q in s.token_queries_np(10, vocab=5000, seed=10)]
+    want = np.stack([ref.get_scores(q) for q in queries])
+    got0 = idx.get_scores(queries[0])
+    assert np.allclose(got0, want[0], rtol=1e-6, atol=1e-9)
+    S, I = idx.topk(queries, 30)
+    oracle.assert_topk_equivalent(S, I, want, 30, rtol=1e-6, atol=1e-9, what="bm25 f32", pad_score=PAD)
+
+
+def test_long_query_many_terms(b2r):
+    """More query tokens than one term chunk (64) — e.g. a HyDE passage used as the BM25 query."""
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    docs = s.token_corpus_np(5000, vocab=2000, seed=11)
+    ref = oracle.BM25OkapiRef(docs)
+    idx = BM25Okapi(docs, weight_bits=64)
+    rng = np.random.default_rng(12)
+    q = [f"t{int(r)}" for r in rng.integers(0, 2000, 300)]
+    want = ref.get_scores(q)
+    assert np.array_equal(idx.get_scores(q), want)
+    S, I = idx.topk([q], 50)
+    assert np.array_equal(I[0], oracle.bm25_topn_ref(want, 50))
+
+
+def test_sharded_postings_match_unsharded(b2r):
+    """Document shards built with corpus-global idf / avgdl score exactly like the whole corpus, and
+    merging the per-shard top-k gives the global top-k."""
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    docs = s.token_corpus_np(6000, vocab=3000, seed=13)
+    ref = oracle.BM25OkapiRef(docs)
+    full = BM25Okapi(docs, weight_bits=64)
+    vocab = full._vocab
+    idf_arr = np.array([full.idf[w] for w in vocab], dtype=np.float64)
+    queries = [as_tokens(q) for q in s.token_queries_np(6, vocab=3000, seed=14)]
+    bounds = [0, 1500, 4100, 6000]
+    shard_results = []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        terms, dids, tfs = [], [], []
+        for di in range(lo, hi):
+            for w, f in ref.doc_freqs[di].items():
+                terms.append(vocab[w]); dids.append(di - lo); tfs.append(f)
+        terms = np.array(terms); order = np.argsort(terms, kind="stable")
+        indptr = np.zeros(len(vocab) + 1, np.int64)
+        np.cumsum(np.bincount(terms, minlength=len(vocab)), out=indptr[1:])
+        shard = BM25Okapi.from_postings(indptr, np.array(dids)[order], np.array(tfs)[order],
+                                        np.array(ref.doc_len[lo:hi]), idf_arr, ref.avgdl, weight_bits=64, vocab=vocab)
+        S, I = shard.topk(queries, 30)
+        shard_results.append((S, np.where(I >= 0, I + lo, -1)))
+        assert np.array_equal(shard.get_scores(queries[0]), ref.get_scores(queries[0])[lo:hi])
+    for qi, q in enumerate(queries):
+        want = ref.get_scores(q)
+        top = oracle.bm25_topn_ref(want, 30)
+        cand = [(-float(S[qi, j]), int(I[qi, j])) for S, I in shard_results for j in range(30) if I[qi, j] >= 0]
+        merged = [i for _, i in sorted(cand)[:30]]
+        assert merged == top
+
+
+def test_pickle_round_trip_and_rank_bm25_pickle(b2r, tmp_path):
+    from rag_challenge_2_b200.bm25 import BM25Okapi, load_bm25_pickle
+
+    docs = KAT_CORPUS
+    idx = BM25Okapi(docs, weight_bits=64)
+    blob = pickle.dumps(idx)
+    idx2 = pickle.loads(blob)
+    assert np.array_equal(idx2.get_scores(["cat", "dog"]), idx.get_scores(["cat", "dog"]))
+    # a pickle as the reference's ingestion writes it: class rank_bm25.BM25Okapi with rank_bm25's attrs
+    ref = oracle.BM25OkapiRef(docs)
+    state = {"corpus_size": ref.corpus_size, "avgdl": ref.avgdl, "doc_freqs": ref.doc_freqs, "idf": ref.idf,
+             "doc_len": ref.doc_len, "tokenizer": None, "k1": 1.5, "b": 0.75, "epsilon": 0.25,
+             "average_idf": ref.average_idf}
+    import sys
+    import types
+    fake = types.ModuleType("rank_bm25")
+
+    class BM25Okapi_(object):
+        pass
+
+    BM25Okapi_.__name__ = BM25Okapi_.__qualname__ = "BM25Okapi"
+    BM25Okapi_.__module__ = "rank_bm25"
+    fake.BM25Okapi = BM25Okapi_
+    sys.modules["rank_bm25"] = fake
+    try:
+        obj = BM25Okapi_()
+        obj.__dict__.update(state)
+        path = tmp_path / "abc.pkl"
+        with open(path, "wb") as f:
+            pickle.dump(obj, f)
+    finally:
+        del sys.modules["rank_bm25"]
+    loaded = load_bm25_pickle(path)
+    loaded.weight_bits = 64
+    assert np.array_equal(loaded.get_scores(["the", "cat"]), ref.get_scores(["the", "cat"]))
+
+
+def test_device_built_postings_vs_csr_oracle(b2r):
+    """Corpus generated in HBM (the benchmark's path) scored against the vectorised CSR oracle."""
+    import torch
+
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    n, V = 200_000, 50_000
+    post = s.token_postings_torch(0, n, V, "cuda", seed=4242)
+    idf, _ = s.bm25_idf_from_df(post["df"].cpu().numpy(), n)
+    avgdl = post["total_len"] / n
+    idx = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"],
+                                  torch.from_numpy(idf).cuda(), avgdl, weight_bits=64)
+    indptr, dids = post["indptr"].cpu().numpy(), post["doc_ids"].cpu().numpy()
+    tf, dl = post["tf"].cpu().numpy(), post["doc_len"].cpu().numpy()
+    # postings are doc-ascending inside every term
+    for t in (0, 1, 17, 4999):
+        seg = dids[indptr[t]:indptr[t + 1]]
+        assert np.all(np.diff(seg) > 0)
+    queries = s.token_queries_np(16, vocab=V, seed=4243)
+    S, I = idx.topk([np.array(q, np.int32) for q in queries], 30)
+    for qi, q in enumerate(queries):
+        want = bm25_scores_csr_ref(indptr, dids, tf, dl, avgdl, idf, q)
+        order = np.lexsort((np.arange(n), -want))[:30]
+        assert np.array_equal(I[qi], order), f"q{qi}"
+        assert np.array_equal(S[qi], want[order])
+    # float32 weights on the same corpus: tolerance comparison
+    idx32 = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"],
+                                    torch.from_numpy(idf).cuda(), avgdl, weight_bits=32)
+    S32, I32 = idx32.topk([np.array(q, np.int32) for q in queries], 30)
+    want = np.stack([bm25_scores_csr_ref(indptr, dids, tf, dl, avgdl, idf, q) for q in queries])
+    oracle.assert_topk_equivalent(S32, I32, want, 30, rtol=1e-6, atol=1e-9, what="bm25 f32 dev", pad_score=PAD)

@@ -1,0 +1,72 @@
+"""CPU: pin the oracle with hand-derived known answers (the reference ships no golden vectors)."""
+import math
+
+import numpy as np
+
+import oracle
+from oracle.bm25 import bm25_scores_csr_ref
+
+
+def test_flat_ip_kat_with_tie_and_padding():
+    xb = np.array([[1, 0, 0], [0, 1, 0], [1, 0, 0], [0.5, 0.5, 0]], dtype=np.float32)
+    xq = np.array([[1, 0, 0], [0, 2, 0], [1, 1, 0]], dtype=np.float32)
+    D, I = oracle.flat_ip_search_ref(xb, xq, 3)
+    assert I.tolist() == [[0, 2, 3], [1, 3, 0], [0, 1, 2]]   # ties: ascending id
+    assert D.tolist() == [[1.0, 1.0, 0.5], [2.0, 1.0, 0.0], [1.0, 1.0, 1.0]]
+    D, I = oracle.flat_ip_search_ref(xb, xq[:1], 6)           # k > ntotal pads like faiss
+    assert I.tolist() == [[0, 2, 3, 1, -1, -1]]
+    assert D[0, 4] == np.float32(-3.4028235e38) and D.dtype == np.float32 and I.dtype == np.int64
+    S64 = oracle.flat_ip_scores_ref(xb, xq, np.float64)
+    S32 = oracle.flat_ip_scores_ref(xb, xq, np.float32)
+    assert np.all(np.abs(S32 - S64) <= 1e-5 * np.abs(S64))
+    oracle.assert_topk_equivalent(*oracle.flat_ip_search_ref(xb, xq, 2), S64, 2)
+
+
+def test_bm25_kat_hand_computed():
+    corpus = [["a", "b", "a"], ["b", "c"], ["c", "c", "d"]]
+    bm = oracle.BM25OkapiRef(corpus)
+    assert bm.corpus_size == 3 and bm.avgdl == 8 / 3 and bm.doc_len == [3, 2, 3]
+    # idf = ln(N - n + 0.5) - ln(n + 0.5)
+    idf_a = math.log(2.5) - math.log(1.5)      # in 1 doc
+    idf_b = math.log(1.5) - math.log(2.5)      # in 2 docs -> negative
+    avg = (idf_a + idf_b + idf_b + idf_a) / 4  # order of first appearance: a, b, c, d
+    assert bm.average_idf == avg
+    assert bm.idf["a"] == idf_a and bm.idf["d"] == idf_a
+    assert bm.idf["b"] == 0.25 * avg and bm.idf["c"] == 0.25 * avg   # epsilon floor
+    # score of doc 0 for query ["a"]: tf = 2, dl = 3
+    w = 2 * 2.5 / (2 + 1.5 * (1 - 0.75 + 0.75 * 3 / (8 / 3)))
+    s = bm.get_scores(["a"])
+    assert s[0] == idf_a * w and s[1] == 0.0 and s[2] == 0.0
+    # repeated token counted twice, unknown token ignored
+    assert np.array_equal(bm.get_scores(["a", "a", "zz"]), 2 * s)
+    # stable descending sort keeps ascending ids among ties, zero-score docs eligible
+    assert oracle.bm25_topn_ref(s, 3) == [0, 1, 2]
+    assert oracle.bm25_topn_ref(np.zeros(4), 2) == [0, 1]
+
+
+def test_bm25_csr_form_matches_dict_form():
+    rng = np.random.default_rng(0)
+    docs = [[f"t{int(r)}" for r in rng.zipf(1.3, int(rng.integers(5, 40))) if r < 200] or ["t1"] for _ in range(300)]
+    bm = oracle.BM25OkapiRef(docs)
+    vocab = {w: i for i, w in enumerate(bm.idf)}
+    terms, dids, tfs = [], [], []
+    for di, f in enumerate(bm.doc_freqs):
+        for w, c in f.items():
+            terms.append(vocab[w]); dids.append(di); tfs.append(c)
+    terms = np.array(terms); order = np.argsort(terms, kind="stable")
+    indptr = np.zeros(len(vocab) + 1, np.int64)
+    np.cumsum(np.bincount(terms, minlength=len(vocab)), out=indptr[1:])
+    idf = np.array([bm.idf[w] for w in vocab])
+    for q in (["t1", "t2"], ["t7", "t7", "t3"], ["t150"]):
+        ids = [vocab[t] for t in q if t in vocab]
+        got = bm25_scores_csr_ref(indptr, np.array(dids)[order], np.array(tfs)[order], np.array(bm.doc_len), bm.avgdl, idf, ids)
+        assert np.array_equal(got, bm.get_scores(q))
+
+
+def test_cosine_matrix_kat():
+    x = np.array([[3, 4], [0, 2], [-3, -4]], dtype=np.float32)
+    s = oracle.cosine_matrix_ref(x)
+    assert np.allclose(s, [[1, 0.8, -1], [0.8, 1, -0.8], [-1, -0.8, 1]], atol=1e-6)
+    st = oracle.cosine_stats_ref(s)
+    assert abs(st["avg_similarity"] - (-1 / 3)) < 1e-6 and st["max_similarity"] == np.float32(0.8)
+    assert abs(st["min_similarity"] + 1) < 1e-6 and abs(st["median_similarity"] + 0.8) < 1e-6
