@@ -71,7 +71,7 @@ def test_negative_epsilon_ranks_below_zero(b2r):
     untouched (zero-score) documents, which must still fill the top-n in ascending id order."""
     from rag_challenge_2_b200.bm25 import BM25Okapi
 
-    corpus = [["a", "b"], ["a", "b"], ["a"], ["c"]]
+    corpus = [["a", "b"], ["a", "b"], ["a", "b"], ["c"]]
     ref = oracle.BM25OkapiRef(corpus)
     assert ref.average_idf < 0
     idx = BM25Okapi(corpus, weight_bits=64)
