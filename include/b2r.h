@@ -90,6 +90,9 @@ int b2r_last_launch_count(void);
  * Entries with id < 0 are ignored.  Output D[nq,k_out], I[nq,k_out], padded with -1. */
 int b2r_topk_merge_dev(const float* D_lists, const int64_t* I_lists, int n_lists, int nq, int k_in,
                        int k_out, float* D, int64_t* I, void* stream);
+/* float64-score variant (BM25 lists). */
+int b2r_topk_merge_f64_dev(const double* S_lists, const int64_t* I_lists, int n_lists, int nq,
+                           int k_in, int k_out, double* S, int64_t* I, void* stream);
 int b2r_topk_merge_host(const float* D_lists, const int64_t* I_lists, int n_lists, int nq,
                         int k_in, int k_out, float* D, int64_t* I, int device);
 
@@ -130,6 +133,17 @@ int b2r_bm25_topk_dev(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* t
                       const int32_t* term_offsets_host, int nq, int k, double* S_dev,
                       int64_t* I_dev, int64_t id_offset, void* stream);
 int b2r_bm25_destroy(b2r_bm25* h);
+
+/* ---- dense + BM25 fusion ------------------------------------------------------------------- */
+/* Hybrid top-k for BASELINE config 4.  The reference defines no dense+BM25 formula (PARITY
+ * UNPINNED); this applies its aggregation rule src/retrieval.py:1639-1661 with BM25
+ * as one more retrieval source: base = dense score if the chunk is a dense hit, else the BM25 score
+ * min-max normalised over the query's BM25 hits; final = base * 1.1 when both retrievers found it.
+ * D/I[nq,k_dense] dense hits, S/J[nq,k_bm25] BM25 hits (ids must be < 2^32), outputs F/O[nq,k_out]
+ * (score descending, id ascending) and optional methods[nq,k_out] (bit 0 dense, bit 1 BM25). */
+int b2r_hybrid_fuse_dev(const float* D, const int64_t* I, const double* S, const int64_t* J, int nq,
+                        int k_dense, int k_bm25, int k_out, float* F, int64_t* O,
+                        unsigned char* methods, void* stream);
 
 /* ---- N x N cosine analysis ---------------------------------------------------------------- */
 /* compute_cosine_similarity_matrix + off-diagonal statistics

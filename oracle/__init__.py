@@ -16,4 +16,5 @@ rank_bm25 replaced by this oracle (tests/golden/make_golden.py).
 """
 from .flat_ip import flat_ip_search_ref, flat_ip_scores_ref, assert_topk_equivalent  # noqa: F401
 from .bm25 import BM25OkapiRef, bm25_topn_ref  # noqa: F401
+from .fusion import merge_lists_ref, hybrid_fuse_ref  # noqa: F401
 from .cosine import cosine_matrix_ref, cosine_stats_ref  # noqa: F401

@@ -21,7 +21,7 @@ def flat_ip_scores_ref(xb, xq, dtype=np.float32):
     """All inner products, [nq, n].  dtype=np.float64 gives the exact-arithmetic reference."""
     xb = np.asarray(xb, dtype=np.float32)
     xq = np.asarray(xq, dtype=np.float32).reshape(-1, xb.shape[1])
-    return xq.astype(dtype) @ xb.astype(dtype).T
+    return xq.astype(dtype, copy=False) @ xb.astype(dtype, copy=False).T
 
 
 def topk_from_scores(S, k):

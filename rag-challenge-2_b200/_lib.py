@@ -47,6 +47,8 @@ SIGNATURES = {
     "b2r_flat_destroy": (C.c_int, [_vp]),
     "b2r_last_launch_count": (C.c_int, []),
     "b2r_topk_merge_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "b2r_topk_merge_f64_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "b2r_hybrid_fuse_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "b2r_topk_merge_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "b2r_bm25_create": (C.c_int, [C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_double,
                                   C.c_double, C.c_int, C.POINTER(_vp)]),

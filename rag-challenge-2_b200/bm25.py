@@ -219,7 +219,9 @@ class BM25Okapi:
     def __getstate__(self):
         if self.doc_freqs is None:
             raise pickle.PicklingError("an index built from raw postings cannot be pickled")
-        return {k: getattr(self, k) for k in self._STATE_KEYS}
+        state = {k: getattr(self, k) for k in self._STATE_KEYS}
+        state["weight_bits"] = self.weight_bits  # ours only; rank_bm25's own pickles simply lack it
+        return state
 
     def __setstate__(self, state):
         # accepts the attribute dict of a genuine rank_bm25.BM25Okapi pickle as well as our own

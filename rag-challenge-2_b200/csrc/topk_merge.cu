@@ -15,12 +15,37 @@
 
 namespace b2r {
 
-__global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ D_lists,
+// score type -> key type / packing.  float: 64-bit key; double (BM25): 128-bit key.
+template <class T>
+struct MergeKey;
+template <>
+struct MergeKey<float> {
+  typedef u64 K;
+  static __device__ __forceinline__ K pack(float s, u32 pos) { return make_key(s, pos); }
+  static __device__ __forceinline__ u32 pos(K k) { return key_id(k); }
+  static __device__ __forceinline__ float pad() { return -3.4028235e38f; }
+};
+template <>
+struct MergeKey<double> {
+  typedef u128 K;
+  static __device__ __forceinline__ K pack(double s, u32 pos) {
+    s = s + 0.0;
+    const u64 u = static_cast<u64>(__double_as_longlong(s));
+    const u64 o = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    return (static_cast<u128>(o) << 64) | static_cast<u128>(0xFFFFFFFFu - pos);
+  }
+  static __device__ __forceinline__ u32 pos(K k) { return 0xFFFFFFFFu - static_cast<u32>(k); }
+  static __device__ __forceinline__ double pad() { return -1.7976931348623157e308; }
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) topk_merge_kernel(const T* __restrict__ D_lists,
                                                          const long long* __restrict__ I_lists, int n_lists, int nq,
-                                                         int k_in, int k_out, float* __restrict__ D,
+                                                         int k_in, int k_out, T* __restrict__ D,
                                                          long long* __restrict__ I, int buf_cap) {
+  typedef typename MergeKey<T>::K K;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* buf = reinterpret_cast<u64*>(smem_raw);
+  K* buf = reinterpret_cast<K*>(smem_raw);
   const int qi = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int total = n_lists * k_in;
@@ -30,11 +55,11 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
   for (int base = 0; base < total; base += chunk) {
     for (int i = tid; i < chunk; i += nt) {
       const int g = base + i;
-      u64 key = 0;
+      K key = 0;
       if (g < total) {
         const int l = g / k_in, s = g - l * k_in;
         const size_t idx = (static_cast<size_t>(l) * nq + qi) * k_in + s;
-        if (I_lists[idx] >= 0) key = make_key(D_lists[idx], static_cast<u32>(g));
+        if (I_lists[idx] >= 0) key = MergeKey<T>::pack(D_lists[idx], static_cast<u32>(g));
       }
       buf[k_out + i] = key;
     }
@@ -42,13 +67,13 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
     block_sort_desc(buf, buf_cap);
   }
   for (int i = tid; i < k_out; i += nt) {
-    const u64 key = buf[i];
+    const K key = buf[i];
     const size_t o = static_cast<size_t>(qi) * k_out + i;
     if (key == 0) {
-      D[o] = -3.4028235e38f;
+      D[o] = MergeKey<T>::pad();
       I[o] = -1;
     } else {
-      const int g = static_cast<int>(key_id(key));
+      const int g = static_cast<int>(MergeKey<T>::pos(key));
       const int l = g / k_in, s = g - l * k_in;
       const size_t idx = (static_cast<size_t>(l) * nq + qi) * k_in + s;
       D[o] = D_lists[idx];
@@ -63,22 +88,23 @@ static int pow2_ge(int v) {
   return p;
 }
 
-static int merge_launch(const float* D_lists, const int64_t* I_lists, int n_lists, int nq, int k_in, int k_out,
-                        float* D, int64_t* I, cudaStream_t stream) {
+template <class T>
+static int merge_launch(const T* D_lists, const int64_t* I_lists, int n_lists, int nq, int k_in, int k_out,
+                        T* D, int64_t* I, cudaStream_t stream) {
   const long long total = static_cast<long long>(n_lists) * k_in;
   int buf_cap = pow2_ge(static_cast<int>(std::min<long long>(total, 4096)) + k_out);
   buf_cap = std::max(buf_cap, 2 * pow2_ge(k_out));
   buf_cap = std::min(buf_cap, 8192);
-  const size_t smem = static_cast<size_t>(buf_cap) * sizeof(u64);
-  B2R_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  topk_merge_kernel<<<nq, 256, smem, stream>>>(D_lists, reinterpret_cast<const long long*>(I_lists), n_lists, nq,
+  const size_t smem = static_cast<size_t>(buf_cap) * sizeof(typename MergeKey<T>::K);
+  B2R_CUDA(cudaFuncSetAttribute(topk_merge_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+  topk_merge_kernel<T><<<nq, 256, smem, stream>>>(D_lists, reinterpret_cast<const long long*>(I_lists), n_lists, nq,
                                                k_in, k_out, D, reinterpret_cast<long long*>(I), buf_cap);
   B2R_CUDA(cudaGetLastError());
   return B2R_OK;
 }
 
-static int merge_check(const float* D_lists, const int64_t* I_lists, int n_lists, int nq, int k_in, int k_out,
-                       const float* D, const int64_t* I) {
+static int merge_check(const void* D_lists, const int64_t* I_lists, int n_lists, int nq, int k_in, int k_out,
+                       const void* D, const int64_t* I) {
   if (n_lists < 1 || nq < 0 || k_in < 1 || k_out < 1) return fail(B2R_ERR_INVALID, "b2r_topk_merge: bad sizes");
   if (k_out > B2R_MAX_K) return fail(B2R_ERR_UNSUPPORTED, "b2r_topk_merge: k_out > B2R_MAX_K (1024)");
   if (static_cast<long long>(n_lists) * k_in > (1LL << 30)) return fail(B2R_ERR_UNSUPPORTED, "b2r_topk_merge: too many candidates");
@@ -98,6 +124,14 @@ int b2r_topk_merge_dev(const float* D_lists, const int64_t* I_lists, int n_lists
   if (rc) return rc;
   if (nq == 0) return B2R_OK;
   return merge_launch(D_lists, I_lists, n_lists, nq, k_in, k_out, D, I, static_cast<cudaStream_t>(stream));
+}
+
+int b2r_topk_merge_f64_dev(const double* S_lists, const int64_t* I_lists, int n_lists, int nq, int k_in, int k_out,
+                           double* S, int64_t* I, void* stream) {
+  int rc = merge_check(S_lists, I_lists, n_lists, nq, k_in, k_out, S, I);
+  if (rc) return rc;
+  if (nq == 0) return B2R_OK;
+  return merge_launch(S_lists, I_lists, n_lists, nq, k_in, k_out, S, I, static_cast<cudaStream_t>(stream));
 }
 
 int b2r_topk_merge_host(const float* D_lists, const int64_t* I_lists, int n_lists, int nq, int k_in, int k_out,

@@ -1,0 +1,216 @@
+"""Row-sharded exact search, top-k merge and the dense + BM25 hybrid top-k (BASELINE configs 3/4).
+
+One process per GPU (torch.distributed, NCCL over NVLink): rank r holds rows / documents
+[bounds[r], bounds[r+1]) of the corpus.  A search is: local scan with global ids -> all-gather of
+the per-rank [nq, k] lists (360 B per query per rank at k = 30) -> merge kernel on every rank, so
+all ranks end with the same answer.  With one rank the gather and merge are skipped.
+The union of per-shard top-k contains the global top-k, so the result is exact.
+
+Replaces, for a corpus that does not fit the reference's one-faiss-index-per-report design, the
+Python merge of per-report hits (src/retrieval.py:1108-1113, 1719, 1754; BM25 :293-295).
+"""
+import ctypes as C
+
+from . import _lib
+
+
+def shard_bounds(n, world_size, align=1):
+    """Contiguous row ranges, one per rank, starting on multiples of `align` (the synthetic
+    generators are seeded per block); the last rank takes the remainder."""
+    per = -(-n // world_size)
+    per = -(-per // align) * align
+    bounds = [min(n, r * per) for r in range(world_size)] + [n]
+    return bounds
+
+
+def merge_topk(D_lists, I_lists, k_out, stream=None):
+    """K3 on device tensors laid out [n_lists, nq, k_in] (float32 or float64 scores)."""
+    import torch
+
+    lib = _lib.load()
+    n_lists, nq, k_in = D_lists.shape
+    D = torch.empty((nq, k_out), dtype=D_lists.dtype, device=D_lists.device)
+    I = torch.empty((nq, k_out), dtype=torch.int64, device=D_lists.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(D_lists.device).cuda_stream
+    fn = lib.b2r_topk_merge_dev if D_lists.dtype == torch.float32 else lib.b2r_topk_merge_f64_dev
+    _lib.check(fn(C.c_void_p(D_lists.data_ptr()), C.c_void_p(I_lists.data_ptr()), int(n_lists), int(nq), int(k_in),
+                  int(k_out), C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()), C.c_void_p(stream)))
+    return D, I
+
+
+def hybrid_fuse(D, I, S, J, k_out, want_methods=False, stream=None):
+    """Dense + BM25 fusion kernel (csrc/hybrid_fuse.cu) on device tensors."""
+    import torch
+
+    lib = _lib.load()
+    nq = D.shape[0]
+    F = torch.empty((nq, k_out), dtype=torch.float32, device=D.device)
+    O = torch.empty((nq, k_out), dtype=torch.int64, device=D.device)
+    M = torch.empty((nq, k_out), dtype=torch.uint8, device=D.device) if want_methods else None
+    if stream is None:
+        stream = torch.cuda.current_stream(D.device).cuda_stream
+    _lib.check(lib.b2r_hybrid_fuse_dev(C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()), C.c_void_p(S.data_ptr()),
+                                       C.c_void_p(J.data_ptr()), int(nq), int(D.shape[1]), int(S.shape[1]), int(k_out),
+                                       C.c_void_p(F.data_ptr()), C.c_void_p(O.data_ptr()),
+                                       C.c_void_p(M.data_ptr()) if M is not None else None, C.c_void_p(stream)))
+    return (F, O, M) if want_methods else (F, O)
+
+
+class ShardedSearcher:
+    """SPMD search over a row-sharded corpus.
+
+    local_dense(q, k)            -> (D[nq,k] float32, I[nq,k] int64 GLOBAL ids) on this rank's shard
+    local_bm25(tids, toffs, k)   -> (S[nq,k] float64, J[nq,k] int64 GLOBAL ids)  (optional)
+    gather(t)                    -> tensor [world, *t.shape] (all ranks' t, rank order)
+    merge(D_lists, I_lists, k)   -> merged (D, I)
+    fuse(D, I, S, J, k)          -> fused (F, O)
+    The defaults bind the CUDA kernels and torch.distributed; tests inject CPU stand-ins to cover the
+    partition / gather / merge plumbing with the gloo backend.
+    """
+
+    def __init__(self, local_dense=None, local_bm25=None, group=None, world_size=None, gather=None, merge=None,
+                 fuse=None):
+        self.local_dense = local_dense
+        self.local_bm25 = local_bm25
+        self.group = group
+        if world_size is None:
+            import torch.distributed as dist
+
+            world_size = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.world_size = world_size
+        self._gather = gather or self._dist_gather
+        self._merge = merge or merge_topk
+        self._fuse = fuse or hybrid_fuse
+        self.launches = 0      # kernels of this library enqueued by the last call
+        self.collectives = 0   # collectives enqueued by the last call
+
+    def _dist_gather(self, t):
+        import torch
+        import torch.distributed as dist
+
+        flat = t.contiguous().view(-1)
+        out = torch.empty(self.world_size * flat.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, flat, group=self.group)
+        self.collectives += 1
+        return out.view((self.world_size,) + tuple(t.shape))
+
+    def _gather_pair(self, scores, ids):
+        """One collective for a (scores, ids) pair: both are packed into an int64 buffer."""
+        import torch
+
+        if scores.dtype == torch.float64:
+            packed = torch.stack([scores.view(torch.int64), ids])
+        else:
+            packed = torch.stack([scores.to(torch.float64).view(torch.int64), ids])
+        g = self._gather(packed)  # [world, 2, nq, k]
+        s = g[:, 0].contiguous().view(torch.float64)
+        if scores.dtype != torch.float64:
+            s = s.to(scores.dtype)  # float32 -> float64 -> float32 is exact
+        return s.contiguous(), g[:, 1].contiguous()
+
+    def search_dense(self, q, k):
+        self.launches = self.collectives = 0
+        D, I = self.local_dense(q, k)
+        self.launches += self._last_dense_launches()
+        if self.world_size == 1:
+            return D, I
+        Dl, Il = self._gather_pair(D, I)
+        self.launches += 1
+        return self._merge(Dl, Il, k)
+
+    def search_bm25(self, term_ids, term_offsets, k):
+        self.launches = self.collectives = 0
+        S, J = self.local_bm25(term_ids, term_offsets, k)
+        self.launches += 1
+        if self.world_size == 1:
+            return S, J
+        Sl, Jl = self._gather_pair(S, J)
+        self.launches += 1
+        return self._merge(Sl, Jl, k)
+
+    def search_hybrid(self, q, term_ids, term_offsets, k):
+        """Dense top-k + BM25 top-k + fusion; with several ranks both lists travel in ONE all-gather."""
+        import torch
+
+        self.launches = self.collectives = 0
+        D, I = self.local_dense(q, k)
+        self.launches += self._last_dense_launches()
+        S, J = self.local_bm25(term_ids, term_offsets, k)
+        self.launches += 1
+        if self.world_size > 1:
+            packed = torch.stack([D.to(torch.float64).view(torch.int64), I, S.view(torch.int64), J])
+            g = self._gather(packed)  # [world, 4, nq, k]
+            Dl = g[:, 0].contiguous().view(torch.float64).to(torch.float32)
+            Sl = g[:, 2].contiguous().view(torch.float64)
+            D, I = self._merge(Dl, g[:, 1].contiguous(), k)
+            S, J = self._merge(Sl, g[:, 3].contiguous(), k)
+            self.launches += 2
+        out = self._fuse(D, I, S, J, k)
+        self.launches += 1
+        return out
+
+    def _last_dense_launches(self):
+        n = getattr(self.local_dense, "last_launches", None)
+        return n() if callable(n) else 1
+
+
+class HybridIndex:
+    """Resident dense rows + BM25 postings of one rank's shard, searched together.
+
+    `flat` is a FlatIPIndex over this rank's rows, `bm25` a BM25Okapi over the same chunks (built
+    with corpus-global idf / avgdl), `offset` the global id of local row 0."""
+
+    def __init__(self, flat, bm25=None, offset=0, group=None, world_size=None):
+        self.flat, self.bm25, self.offset = flat, bm25, int(offset)
+
+        def local_dense(q, k):
+            return flat.search_dev(q, k, id_offset=self.offset)
+
+        local_dense.last_launches = flat.last_launch_count
+
+        def local_bm25(tids, toffs, k):
+            return bm25.topk_dev(tids, toffs, k, id_offset=self.offset)
+
+        self.searcher = ShardedSearcher(local_dense, local_bm25 if bm25 is not None else None, group=group,
+                                        world_size=world_size)
+        self._pinned = {}
+
+    # resident API -----------------------------------------------------------------------------------
+    def search_dev(self, q, k):
+        return self.searcher.search_dense(q, k)
+
+    def search_hybrid_dev(self, q, term_ids, term_offsets, k):
+        return self.searcher.search_hybrid(q, term_ids, term_offsets, k)
+
+    # host API: the call a user makes (numpy in, numpy out; copies inside) ------------------------------
+    def _stage(self, name, arr, dtype):
+        """host array -> pinned staging tensor -> device (non_blocking)."""
+        import numpy as np
+        import torch
+
+        a = np.ascontiguousarray(arr, dtype=dtype)
+        buf = self._pinned.get(name)
+        if buf is None or buf.numel() < a.size or buf.dtype != torch.from_numpy(a).dtype:
+            buf = torch.empty(max(a.size, 1024), dtype=torch.from_numpy(a).dtype).pin_memory()
+            self._pinned[name] = buf
+        view = buf[: a.size].view(a.shape) if a.size else buf[:0]
+        view.copy_(torch.from_numpy(a))
+        dev = torch.device("cuda", self.flat.device)
+        return view.to(dev, non_blocking=True), a.nbytes
+
+    def search_hybrid(self, x, queries_term_ids, k):
+        """x float32[nq,d] (host), queries_term_ids: list of int term-id lists -> (F, O) numpy.
+        Returns also the bytes copied each way (bench accounting)."""
+        import numpy as np
+
+        offs = np.zeros(len(queries_term_ids) + 1, dtype=np.int32)
+        np.cumsum([len(t) for t in queries_term_ids], out=offs[1:])
+        flat_ids = np.concatenate([np.asarray(t, np.int32) for t in queries_term_ids]) if len(queries_term_ids) else np.zeros(0, np.int32)
+        q_dev, b1 = self._stage("q", x, np.float32)
+        t_dev, b2 = self._stage("t", flat_ids, np.int32)
+        o_dev, b3 = self._stage("o", offs, np.int32)
+        F, O = self.searcher.search_hybrid(q_dev, t_dev, o_dev, k)
+        Fh, Oh = F.cpu(), O.cpu()  # device -> host, synchronises
+        self.last_h2d_bytes, self.last_d2h_bytes = b1 + b2 + b3, Fh.numel() * 4 + Oh.numel() * 8
+        return Fh.numpy(), Oh.numpy()

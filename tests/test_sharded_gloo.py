@@ -1,0 +1,111 @@
+"""CPU, world_size 2, gloo: the SPMD plumbing of ShardedSearcher (shard bounds, global ids, the
+packed all-gather, list-major merge order, fusion) with oracle stand-ins for the CUDA kernels."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cpu_merge(D_lists, I_lists, k):
+    pad = np.float32(-3.4028235e38) if D_lists.dtype == torch.float32 else -1.7976931348623157e308
+    D, I = oracle.merge_lists_ref(D_lists.numpy(), I_lists.numpy(), k, pad)
+    return torch.from_numpy(D), torch.from_numpy(I)
+
+
+def _cpu_fuse(D, I, S, J, k):
+    F, O, _ = oracle.hybrid_fuse_ref(D.numpy(), I.numpy(), S.numpy(), J.numpy(), k)
+    return torch.from_numpy(F), torch.from_numpy(O)
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rag_challenge_2_b200.hybrid import ShardedSearcher, shard_bounds
+
+    n, d, k, V = 5000, 64, 30, 300
+    rng = np.random.default_rng(0)
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xb[3000:3010] = xb[10:20]      # ties across the shard boundary
+    xq = np.concatenate([xb[[12, 4000]], rng.standard_normal((3, d)).astype(np.float32)])
+    docs = [[f"t{int(t)}" for t in rng.integers(0, V, int(rng.integers(5, 30)))] for _ in range(n)]
+    bm_full = oracle.BM25OkapiRef(docs)
+    queries = [[f"t{int(t)}" for t in rng.integers(0, V, 4)] for _ in range(5)]
+    bounds = shard_bounds(n, world, align=128)
+    lo, hi = bounds[rank], bounds[rank + 1]
+
+    def local_dense(q, kk):
+        D, I = oracle.flat_ip_search_ref(xb[lo:hi], q.numpy(), kk)
+        return torch.from_numpy(D), torch.from_numpy(np.where(I >= 0, I + lo, -1))
+
+    def local_bm25(tids, toffs, kk):
+        S = np.full((len(queries), kk), -1.7976931348623157e308)
+        J = np.full((len(queries), kk), -1, dtype=np.int64)
+        for qi, q in enumerate(queries):
+            sc = bm_full.get_scores(q)[lo:hi]          # global idf / avgdl, local documents
+            top = oracle.bm25_topn_ref(sc, kk)
+            S[qi, :len(top)] = sc[top]
+            J[qi, :len(top)] = np.array(top) + lo
+        return torch.from_numpy(S), torch.from_numpy(J)
+
+    s = ShardedSearcher(local_dense, local_bm25, merge=_cpu_merge, fuse=_cpu_fuse)
+    assert s.world_size == world
+    D, I = s.search_dense(torch.from_numpy(xq), k)
+    assert s.collectives == 1
+    S, J = s.search_bm25(None, None, k)
+    F, O = s.search_hybrid(torch.from_numpy(xq), None, None, k)
+    assert s.collectives == 1      # dense and BM25 lists travel in one all-gather
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D.numpy(), I=I.numpy(), S=S.numpy(), J=J.numpy(), F=F.numpy(),
+             O=O.numpy(), bounds=np.array(bounds))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_search_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    for key in ("D", "I", "S", "J", "F", "O"):
+        assert np.array_equal(r0[key], r1[key]), f"ranks disagree on {key}"
+    assert r0["bounds"].tolist() == [0, 2560, 5000]
+    # against the unsharded oracle
+    n, d, k, V = 5000, 64, 30, 300
+    rng = np.random.default_rng(0)
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    xb[3000:3010] = xb[10:20]
+    xq = np.concatenate([xb[[12, 4000]], rng.standard_normal((3, d)).astype(np.float32)])
+    docs = [[f"t{int(t)}" for t in rng.integers(0, V, int(rng.integers(5, 30)))] for _ in range(n)]
+    bm_full = oracle.BM25OkapiRef(docs)
+    queries = [[f"t{int(t)}" for t in rng.integers(0, V, 4)] for _ in range(5)]
+    Dr, Ir = oracle.flat_ip_search_ref(xb, xq, k)
+    assert np.array_equal(r0["I"], Ir) and np.array_equal(r0["D"], Dr)
+    assert r0["I"][0, 0] == 12 and r0["I"][0, 1] == 3002      # tie across shards: lower global id first
+    Sr = np.stack([bm_full.get_scores(q) for q in queries])
+    Jr = np.array([oracle.bm25_topn_ref(s, k) for s in Sr])
+    assert np.array_equal(r0["J"], Jr)
+    assert np.array_equal(r0["S"], np.take_along_axis(Sr, Jr, 1))
+    Fr, Or, _ = oracle.hybrid_fuse_ref(Dr, Ir, np.take_along_axis(Sr, Jr, 1), Jr, k)
+    assert np.array_equal(r0["O"], Or) and np.array_equal(r0["F"], Fr)
+
+
+def test_shard_bounds():
+    from rag_challenge_2_b200.hybrid import shard_bounds
+
+    assert shard_bounds(10_000_000, 8, 1 << 18) == [0, 1310720, 2621440, 3932160, 5242880, 6553600, 7864320, 9175040, 10_000_000]
+    assert shard_bounds(10, 4) == [0, 3, 6, 9, 10]
+    assert shard_bounds(5, 8) == [0, 1, 2, 3, 4, 5, 5, 5, 5]
+    assert shard_bounds(1000, 1, 128) == [0, 1000]
