@@ -234,9 +234,22 @@ __device__ __forceinline__ void block_select_lists(const K* __restrict__ src, in
   }
   __syncthreads();
   const u64 thr = *s_thr;
+  // Second, usually much tighter bound when there are many lists: the k-th largest of the lists'
+  // best entries.  Those k lists each hold at least one key >= theta, so >= k keys survive, and
+  // for data spread over many lists only a little over k do.  Compared as full keys, so runs of
+  // equal scores (BM25's zero-score tail) do not all survive.
+  K theta = 0;
+  const int lp = next_pow2(n_lists < 2 ? 2 : n_lists);
+  if (n_lists >= k && lp <= buf_cap) {
+    for (int l = tid; l < lp; l += nt) buf[l] = l < n_lists ? src[static_cast<long long>(l) * stride] : static_cast<K>(0);
+    __syncthreads();
+    block_sort_desc(buf, lp);
+    theta = buf[k - 1];
+    __syncthreads();
+  }
   for (long long i = tid; i < total; i += nt) {
     const K v = src[i];
-    if (v != 0 && key_prune_part(v) >= thr) {
+    if (v != 0 && key_prune_part(v) >= thr && v >= theta) {
       const u32 pos = atomicAdd(s_cnt, 1u);
       if (pos < static_cast<u32>(buf_cap)) buf[pos] = v;
     }

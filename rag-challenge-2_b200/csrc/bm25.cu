@@ -122,9 +122,25 @@ __global__ void __launch_bounds__(kBm25Warps * 32) bm25_kernel(const Bm25Args<W>
       const int term = a.term_ids[tc + j];
       const double idf = a.idf[term];
       const long long p0 = seg[2 * j], p1 = seg[2 * j + 1];
-      for (long long p = p0 + tid; p < p1; p += nt) {
+      // 4 independent (doc id, weight) loads in flight per thread before the dependent updates
+      long long p = p0 + tid;
+      for (; p + 3LL * nt < p1; p += 4LL * nt) {
+        int dd[4];
+        W ww[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          dd[u] = __ldg(a.doc_ids + p + static_cast<long long>(u) * nt);
+          ww[u] = __ldg(a.weight + p + static_cast<long long>(u) * nt);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int dl = dd[u] - static_cast<int>(lo);
+          // explicit rn intrinsics: no FMA contraction, numpy forms idf*w and the sum separately
+          acc[dl] = __dadd_rn(acc[dl], __dmul_rn(idf, static_cast<double>(ww[u])));
+        }
+      }
+      for (; p < p1; p += nt) {
         const int dl = __ldg(a.doc_ids + p) - static_cast<int>(lo);
-        // explicit rn intrinsics: no FMA contraction, numpy forms idf*w and the sum separately
         acc[dl] = __dadd_rn(acc[dl], __dmul_rn(idf, static_cast<double>(__ldg(a.weight + p))));
       }
       __syncthreads();
