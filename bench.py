@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=1_000_000, help="rows of the CPU-baseline dense sample")
     ap.add_argument("--cpu-docs", type=int, default=50_000, help="documents of the CPU-baseline BM25 sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run BM25 after the scan instead of under it")
     return ap.parse_args()
 
 
@@ -190,7 +191,7 @@ def workload_config(args, world):
     return {"workload": f"hybrid top-{args.k}: flat IP over {args.rows} x {args.dim} fp32 + BM25Okapi over {args.rows} "
                         f"chunks (vocab {args.vocab}, Zipf) + fusion; {args.nq} query/step",
             "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "k": args.k, "queries_per_step": args.nq,
-            "sharding": f"rows/{world}", "l2": "inputs (rows + postings) far larger than the 126 MB L2; no flush needed"}
+            "sharding": f"rows/{world}", "bm25_overlapped_with_scan": not args.no_overlap, "l2": "inputs (rows + postings) far larger than the 126 MB L2; no flush needed"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -234,7 +235,7 @@ def run_b200(args):
     n_post, wbits = bm25.n_postings()
     del post
     torch.cuda.empty_cache()
-    index = hybrid.HybridIndex(flat, bm25, lo)
+    index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap)
 
     # ---- queries (rank 0 decides, everyone gets the same) --------------------------------------------
     pool = max(args.pool, args.nq)

@@ -163,36 +163,109 @@ __global__ void __launch_bounds__((CW + 1) * 32) flat_scan_tma_kernel(const Scan
     }
     int s = 0;
     u32 ph = 0;
+    // lane-constant bookkeeping of the multi-query path: after the transposed reduction lane l owns
+    // the dot product number vi = bits 4,3,2 of l, i.e. (row slot vi / NQ, query vi % NQ)
+    constexpr int R = NQ > 1 ? 8 / NQ : 1;  // rows processed together
+    const int vi = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const int my_q = vi % NQ, my_r = vi / NQ;
+    u64 tau_mine = 0;
     for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
       mbar_wait(&full[s], ph);
       const float* tile = stage0 + static_cast<size_t>(s) * tile_floats;
       const long long row0 = t * a.tile_rows;
       const int rows = static_cast<int>(min(static_cast<long long>(a.tile_rows), a.n - row0));
-      for (int r = warp; r < rows; r += CW) {
-        const float* row = tile + r * d;
-        float4 x[DV];
+      if constexpr (NQ == 1) {
+        for (int r = warp; r < rows; r += CW) {
+          const float* row = tile + r * d;
+          float4 x[DV];
 #pragma unroll
-        for (int j = 0; j < DV; ++j) x[j] = lds128(row + (lane + 32 * j) * 4);
-        const u32 rid = static_cast<u32>(row0 + r);
-#pragma unroll
-        for (int qi = 0; qi < NQ; ++qi) {
+          for (int j = 0; j < DV; ++j) x[j] = lds128(row + (lane + 32 * j) * 4);
+          const u32 rid = static_cast<u32>(row0 + r);
           // two accumulators (even / odd chunks) to shorten the dependent FMA chain
           float a0 = 0.f, a1 = 0.f;
 #pragma unroll
           for (int j = 0; j < DV; ++j) {
             float& acc = (j & 1) ? a1 : a0;
-            acc = fmaf(x[j].x, qf[qi][j].x, acc);
-            acc = fmaf(x[j].y, qf[qi][j].y, acc);
-            acc = fmaf(x[j].z, qf[qi][j].z, acc);
-            acc = fmaf(x[j].w, qf[qi][j].w, acc);
+            acc = fmaf(x[j].x, qf[0][j].x, acc);
+            acc = fmaf(x[j].y, qf[0][j].y, acc);
+            acc = fmaf(x[j].z, qf[0][j].z, acc);
+            acc = fmaf(x[j].w, qf[0][j].w, acc);
           }
           float sum = a0 + a1;
 #pragma unroll
           for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
           const u64 key = make_key(sum, rid);
-          if (qi < a.nq && key > tau[qi]) {
-            warp_list_push(cand + (static_cast<size_t>(qi) * CW + warp) * a.cap, a.cap, a.k, cnt[qi], tau[qi],
-                           key, lane);
+          if (key > tau[0]) {
+            warp_list_push(cand + static_cast<size_t>(warp) * a.cap, a.cap, a.k, cnt[0], tau[0], key, lane);
+          }
+        }
+      } else {
+        // R rows x NQ queries = 8 dot products per pass: 8 independent FMA chains, then a
+        // transposed reduction (4 + 2 + 1 + 1 + 1 shuffles instead of 8 x 5)
+        for (int r0 = warp; r0 < rows; r0 += CW * R) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < DV; ++j) {
+            float4 x[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+              // rows past the end of a short tile re-read row r0 (their results are discarded)
+              const int r = (r0 + rr * CW < rows) ? r0 + rr * CW : r0;
+              x[rr] = lds128(tile + r * d + (lane + 32 * j) * 4);
+            }
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+              for (int qi = 0; qi < NQ; ++qi) {
+                float& acc = v[rr * NQ + qi];
+                acc = fmaf(x[rr].x, qf[qi][j].x, acc);
+                acc = fmaf(x[rr].y, qf[qi][j].y, acc);
+                acc = fmaf(x[rr].z, qf[qi][j].z, acc);
+                acc = fmaf(x[rr].w, qf[qi][j].w, acc);
+              }
+            }
+          }
+          // transposed reduction: halve the number of live values at each of the first 3 steps
+          const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
+          float w4[4], w2[2], tot;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float send = up16 ? v[i] : v[i + 4];
+            const float keep = up16 ? v[i + 4] : v[i];
+            w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float send = up8 ? w4[i] : w4[i + 2];
+            const float keep = up8 ? w4[i + 2] : w4[i];
+            w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          {
+            const float send = up4 ? w2[0] : w2[1];
+            const float keep = up4 ? w2[1] : w2[0];
+            tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+          tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+          const int my_row = r0 + my_r * CW;
+          const u64 key = make_key(tot, static_cast<u32>(row0 + my_row));
+          const bool want = (my_row < rows) && (my_q < a.nq) && (key > tau_mine);
+          unsigned m = __ballot_sync(0xffffffffu, want) & 0x11111111u;  // one lane per value
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const u64 kk = __shfl_sync(0xffffffffu, key, src);
+            const int q2 = (((src >> 4) & 1) * 4 + ((src >> 3) & 1) * 2 + ((src >> 2) & 1)) % NQ;
+#pragma unroll
+            for (int qi = 0; qi < NQ; ++qi) {
+              if (q2 == qi && kk > tau[qi]) {
+                warp_list_push(cand + (static_cast<size_t>(qi) * CW + warp) * a.cap, a.cap, a.k, cnt[qi], tau[qi], kk,
+                               lane);
+                if (my_q == qi) tau_mine = tau[qi];
+              }
+            }
           }
         }
       }

@@ -82,6 +82,7 @@ class ShardedSearcher:
         self._gather = gather or self._dist_gather
         self._merge = merge or merge_topk
         self._fuse = fuse or hybrid_fuse
+        self.side_stream = None  # set to a torch.cuda.Stream to overlap BM25 with the dense scan
         self.launches = 0      # kernels of this library enqueued by the last call
         self.collectives = 0   # collectives enqueued by the last call
 
@@ -134,9 +135,23 @@ class ShardedSearcher:
         import torch
 
         self.launches = self.collectives = 0
-        D, I = self.local_dense(q, k)
-        self.launches += self._last_dense_launches()
-        S, J = self.local_bm25(term_ids, term_offsets, k)
+        side = self.side_stream
+        if side is not None:
+            # BM25 is latency-bound and small (its CTAs co-reside with the scan's on every SM):
+            # enqueue it on a side stream so it runs under the HBM-bound scan
+            main = torch.cuda.current_stream(q.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                S, J = self.local_bm25(term_ids, term_offsets, k)
+            D, I = self.local_dense(q, k)
+            self.launches += self._last_dense_launches()
+            main.wait_stream(side)
+            for t in (S, J):
+                t.record_stream(main)
+        else:
+            D, I = self.local_dense(q, k)
+            self.launches += self._last_dense_launches()
+            S, J = self.local_bm25(term_ids, term_offsets, k)
         self.launches += 1
         if self.world_size > 1:
             packed = torch.stack([D.to(torch.float64).view(torch.int64), I, S.view(torch.int64), J])
@@ -161,7 +176,7 @@ class HybridIndex:
     `flat` is a FlatIPIndex over this rank's rows, `bm25` a BM25Okapi over the same chunks (built
     with corpus-global idf / avgdl), `offset` the global id of local row 0."""
 
-    def __init__(self, flat, bm25=None, offset=0, group=None, world_size=None):
+    def __init__(self, flat, bm25=None, offset=0, group=None, world_size=None, overlap=True):
         self.flat, self.bm25, self.offset = flat, bm25, int(offset)
 
         def local_dense(q, k):
@@ -174,6 +189,10 @@ class HybridIndex:
 
         self.searcher = ShardedSearcher(local_dense, local_bm25 if bm25 is not None else None, group=group,
                                         world_size=world_size)
+        if bm25 is not None and overlap:
+            import torch
+
+            self.searcher.side_stream = torch.cuda.Stream(device=torch.device("cuda", flat.device))
         self._pinned = {}
 
     # resident API -----------------------------------------------------------------------------------

@@ -42,6 +42,11 @@ def main():
     qall = torch.randn((8, d), generator=gq, device="cuda")
     qall /= qall.norm(dim=1, keepdim=True)
     gbytes = n * d * 4 / 1e9
+    for nq in (1, 2, 3, 4, 8):
+        ms = time_search(index, qall[:nq].contiguous(), 30)
+        print(json.dumps({"defaults": 1, "nq": nq, "ms": round(ms, 4), "gbps": round(gbytes / ms * 1e3, 1)}), flush=True)
+    if len(sys.argv) > 3 and sys.argv[3] == "defaults":
+        return
     results = []
     grid = {
         "flat.consumer_warps": [4, 8],
