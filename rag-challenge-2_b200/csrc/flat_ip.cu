@@ -526,7 +526,7 @@ static int make_plan(const b2r_flat* h, int nq_left, int k, ScanPlan* p) {
   if (p->tma) {
     p->dv = d / 128;
     // defaults from the B200 sweep (profiles/r01_flat_sweep.md): 8 consumer warps, 1 CTA / SM;
-    // single query: 32 KiB tiles x 4 stages; several queries per pass: 64 KiB tiles x 2 stages
+    // single query: 32 KiB tiles x 4 stages; several queries per pass: 64 KiB tiles x 3 stages
     p->cw = tunable("flat.consumer_warps") == 4 ? 4 : 8;
     const int row_bytes = d * 4;
     int tile_rows = tunable("flat.tile_rows");
@@ -535,7 +535,7 @@ static int make_plan(const b2r_flat* h, int nq_left, int k, ScanPlan* p) {
     int ctas_per_sm = tunable("flat.ctas_per_sm");
     if (ctas_per_sm <= 0) ctas_per_sm = 1;
     int stages = tunable("flat.stages");
-    if (stages <= 0) stages = nq == 1 ? 4 : 2;
+    if (stages <= 0) stages = nq == 1 ? 4 : 3;
     for (;;) {
       const size_t cand = static_cast<size_t>(nq) * p->cw * p->cap * sizeof(u64);
       const size_t fixed = static_cast<size_t>(2 * stages + 4) * sizeof(u64) + cand + 128;
