@@ -32,6 +32,10 @@ static std::map<std::string, int>& tunables() {
       {"flat.consumer_warps", 0},  // 4 or 8
       {"flat.max_nq", 0},          // cap on queries sharing one pass (1, 2 or 4)
       {"flat.force_generic", 0},   // 1: use the non-TMA kernel even for templated widths
+      {"flat.no_gemm", 0},         // 1: never use the tensor-core batch kernel
+      {"flat.gemm_min_nq", 0},     // smallest batch that goes to the tensor-core kernel (default 5)
+      {"flat.gemm_max_n", 0},      // queries per tensor-core pass (default 64)
+      {"gemm.stages", 0},          // depth of the tensor-core kernel's TMA ring
       {"select.buf_cap", 0},       // cap on the final-select scratch (keys); small values force the fallback
       {"bm25.block_docs", 0},      // documents per CTA in the BM25 kernel
   };

@@ -1,0 +1,508 @@
+// flat_gemm.cu — K2: batched exact inner-product top-k on the 5th-gen tensor cores (tcgen05).
+//
+// Replaces index.search(x[nq, d], k) for query batches (the multi-query fan-out of
+// src/retrieval.py:1475-1504 and 127-question batches): every row tile is read from HBM once and
+// scored against up to N = 64 queries.
+//
+//   S[128 rows, N queries] = A[128, d] * B[N, d]^T          per row tile, accumulated over d in TMEM
+//
+// fp32 parity through 3xTF32: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi); the kernel
+// issues A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (kind::tf32, fp32 accumulate), dropping only the
+// lo*lo term (~2^-22 relative) — the same order of error as a different fp32 summation order.
+//
+// Warp roles (320 threads, 1 CTA / SM, persistent over row tiles t = cta, cta + grid, ...):
+//   warp 0      TMA producer: per K-slab (32 floats = 128 B, SWIZZLE_128B) one 2-D tensor copy of
+//               the A slab [128 x 32] and two of the query slabs B_hi / B_lo [N x 32] (L2 resident)
+//   warp 1      allocates TMEM; one lane issues tcgen05.mma (M = 128, N, K = 8) x 4 k-steps x 3 terms
+//               per slab, tcgen05.commit releases the shared-memory slots / publishes the tile
+//   warps 2-5   transform: split the landed A slab into hi (in place) and lo (second ring),
+//               fence.proxy.async, signal the MMA warp
+//   warps 6-9   epilogue: tcgen05.ld the 128 x N accumulator tile (thread = row), fused select with
+//               per-query threshold + candidate lists in shared memory (retry on overflow)
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// A second tiny kernel (one CTA per query) merges the per-CTA lists.
+//
+// Rooflines: HBM for N up to ~100 (4*n*d bytes per launch, independent of N); tensor beyond.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "b2r_common.cuh"
+
+namespace b2r {
+
+static const int kGemmThreads = 320;
+static const int kSlabK = 32;          // floats per K-slab = one 128-byte swizzle row
+static const int kTileM = 128;
+static const int kLoStages = 2;
+
+struct GemmArgs {
+  long long n;
+  int d;
+  int nq;       // active queries (<= N)
+  int k, cap;   // cap: per-query candidate capacity (power of two >= 2k)
+  int raw_stages;
+  long long n_tiles;
+  u64* partial;  // [N][gridDim.x][k]
+};
+
+// ---------------- PTX wrappers specific to this kernel ----------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, u64* bar,
+                                            u64 policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_alloc(u32* slot, u32 ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(u32 taddr, u32 ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void tc_mma_tf32(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void tc_commit(u64* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base + i)
+__device__ __forceinline__ void tc_ld16(u32 taddr, float* v) {
+  u32 r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  u32 u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups
+// 1024 B apart (the layout a {32 x rows} fp32 TMA box with SWIZZLE_128B produces)
+__device__ __forceinline__ u64 make_kmajor_sw128_desc(u32 smem_addr) {
+  u64 desc = 0;
+  desc |= static_cast<u64>((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  desc |= static_cast<u64>(1) << 16;                      // leading byte offset (unused for swizzled K-major)
+  desc |= static_cast<u64>(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+  desc |= static_cast<u64>(1) << 46;                      // descriptor version (Blackwell)
+  desc |= static_cast<u64>(2) << 61;                      // SWIZZLE_128B
+  return desc;
+}
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N
+__host__ __device__ constexpr u32 make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<u32>(n >> 3) << 17) | (static_cast<u32>(kTileM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: split the queries into tf32 hi / lo parts: Bs[0][q][:] = hi, Bs[1][q][:] = lo; rows nq..N-1 zero
+// ---------------------------------------------------------------------------------------------
+__global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, int N, int d, float* __restrict__ Bs) {
+  const long long total = static_cast<long long>(N) * d;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / d);
+    float hi = 0.f, lo = 0.f;
+    if (row < nq) {
+      const float x = q[i];
+      hi = rna_tf32(x);
+      lo = rna_tf32(x - hi);
+    }
+    Bs[i] = hi;
+    Bs[total + i] = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the scan
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    flat_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const GemmArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // SWIZZLE_128B atoms must start on 1024-byte boundaries: align by hand (the host reserves the slack)
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr u32 kABytes = kTileM * kSlabK * 4;            // 16 KiB
+  constexpr u32 kBBytes = N * kSlabK * 4;                 // N * 128 B
+  constexpr u32 kRawStage = kABytes + 2 * kBBytes;        // A (raw -> hi) | B_hi | B_lo
+  constexpr u32 kTmemCols = (2 * N) < 32 ? 32 : 2 * N;    // two accumulator tiles (power of two for N = 16/32/64)
+  const int R = a.raw_stages;
+  const int n_slabs = a.d / kSlabK;
+
+  unsigned char* raw_ring = smem_raw;                                  // R stages
+  unsigned char* lo_ring = raw_ring + static_cast<size_t>(R) * kRawStage;  // kLoStages x 16 KiB
+  u64* bars = reinterpret_cast<u64*>(lo_ring + kLoStages * kABytes);
+  u64* full = bars;                    // [R]   TMA landed
+  u64* empty = full + R;               // [R]   MMAs that read the raw stage are done
+  u64* xf_full = empty + R;            // [kLoStages] hi/lo written
+  u64* xf_empty = xf_full + kLoStages; // [kLoStages] MMAs that read the lo stage are done
+  u64* tm_full = xf_empty + kLoStages; // [2] accumulator tile complete
+  u64* tm_empty = tm_full + 2;         // [2] accumulator tile drained
+  u64* tau_s = tm_empty + 2;           // [N]
+  u32* cnt_s = reinterpret_cast<u32*>(tau_s + N);  // [N]
+  u32* flags = cnt_s + N;              // [2] retry flags, [2] tmem base slot
+  u32* tmem_slot = flags + 2;
+  u64* lists = reinterpret_cast<u64*>(tmem_slot + 2);  // [N][cap]
+
+  if (tid == 0) {
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < kLoStages; ++s) {
+      mbar_init(&xf_full[s], 4);   // one arrive per transform warp
+      mbar_init(&xf_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tm_full[b], 1);
+      mbar_init(&tm_empty[b], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  for (int i = tid; i < N; i += blockDim.x) {
+    tau_s[i] = 0;
+    cnt_s[i] = 0;
+  }
+  if (tid < 2) flags[tid] = 0;
+  if (warp == 1) tc_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      const u64 pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
+      int s = 0;
+      u32 ph = 0;
+      for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        const int row0 = static_cast<int>(t * kTileM);
+        for (int sl = 0; sl < n_slabs; ++sl) {
+          mbar_wait(&empty[s], ph ^ 1u);
+          unsigned char* st = raw_ring + static_cast<size_t>(s) * kRawStage;
+          mbar_arrive_expect_tx(&full[s], kRawStage);
+          tma_load_2d(st, &map_a, sl * kSlabK, row0, &full[s], pol_a);
+          tma_load_2d(st + kABytes, &map_b, sl * kSlabK, 0, &full[s], pol_b);
+          tma_load_2d(st + kABytes + kBBytes, &map_b, sl * kSlabK, N, &full[s], pol_b);
+          if (++s == R) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr u32 idesc = make_idesc_tf32(N);
+      int s = 0, l = 0, buf = 0;
+      u32 ph_l = 0, ph_buf[2] = {0, 0};
+      for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        mbar_wait(&tm_empty[buf], ph_buf[buf] ^ 1u);  // epilogue drained this accumulator tile
+        tc_fence_after();
+        const u32 tmem_d = tmem_base + static_cast<u32>(buf * N);
+        for (int sl = 0; sl < n_slabs; ++sl) {
+          mbar_wait(&xf_full[l], ph_l);
+          tc_fence_after();
+          const u32 st = smem_u32(raw_ring + static_cast<size_t>(s) * kRawStage);
+          const u64 d_ahi = make_kmajor_sw128_desc(st);
+          const u64 d_bhi = make_kmajor_sw128_desc(st + kABytes);
+          const u64 d_blo = make_kmajor_sw128_desc(st + kABytes + kBBytes);
+          const u64 d_alo = make_kmajor_sw128_desc(smem_u32(lo_ring + static_cast<size_t>(l) * kABytes));
+#pragma unroll
+          for (int kk = 0; kk < kSlabK / 8; ++kk) {
+            const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);  // 32 bytes per k-step inside the swizzle row
+            tc_mma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, idesc, (sl | kk) ? 1u : 0u);
+            tc_mma_tf32(tmem_d, d_alo + adv, d_bhi + adv, idesc, 1u);
+            tc_mma_tf32(tmem_d, d_ahi + adv, d_blo + adv, idesc, 1u);
+          }
+          tc_commit(&empty[s]);      // raw stage reusable once these MMAs have read it
+          tc_commit(&xf_empty[l]);   // lo stage likewise
+          if (++s == R) s = 0;
+          if (++l == kLoStages) {
+            l = 0;
+            ph_l ^= 1u;
+          }
+        }
+        tc_commit(&tm_full[buf]);    // accumulator tile complete
+        ph_buf[buf] ^= 1u;
+        buf ^= 1;
+      }
+    }
+  } else if (warp < 6) {
+    // ======================= transform warps: A -> hi (in place), lo =======================
+    const int xt = tid - 64;  // 0..127
+    int s = 0, l = 0;
+    u32 ph_s = 0, ph_l = 0;
+    for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      for (int sl = 0; sl < n_slabs; ++sl) {
+        mbar_wait(&full[s], ph_s);
+        mbar_wait(&xf_empty[l], ph_l ^ 1u);
+        float4* hi = reinterpret_cast<float4*>(raw_ring + static_cast<size_t>(s) * kRawStage);
+        float4* lo = reinterpret_cast<float4*>(lo_ring + static_cast<size_t>(l) * kABytes);
+#pragma unroll
+        for (int i = 0; i < static_cast<int>(kABytes / 16 / 128); ++i) {
+          const int idx = xt + i * 128;
+          const float4 x = hi[idx];
+          float4 h, r;
+          h.x = rna_tf32(x.x);
+          h.y = rna_tf32(x.y);
+          h.z = rna_tf32(x.z);
+          h.w = rna_tf32(x.w);
+          r.x = rna_tf32(x.x - h.x);
+          r.y = rna_tf32(x.y - h.y);
+          r.z = rna_tf32(x.z - h.z);
+          r.w = rna_tf32(x.w - h.w);
+          hi[idx] = h;
+          lo[idx] = r;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_full[l]);
+        if (++s == R) {
+          s = 0;
+          ph_s ^= 1u;
+        }
+        if (++l == kLoStages) {
+          l = 0;
+          ph_l ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue warps: TMEM -> registers -> fused select =======================
+    const int ew = warp - 6;       // 0..3
+    const int quad = warp & 3;     // TMEM lane quadrant this warp may access
+    const int cap = a.cap, k = a.k;
+    int buf = 0, it = 0;
+    u32 ph_buf[2] = {0, 0};
+    for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      mbar_wait(&tm_full[buf], ph_buf[buf]);
+      tc_fence_after();
+      float sc[N];
+      const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(buf * N);
+#pragma unroll
+      for (int c = 0; c < N; c += 16) tc_ld16(taddr + c, sc + c);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tm_empty[buf]);
+      ph_buf[buf] ^= 1u;
+      buf ^= 1;
+
+      const long long row = t * kTileM + quad * 32 + lane;
+      u64 pend = (row < a.n) ? ((a.nq >= 64) ? ~0ull : ((1ull << a.nq) - 1ull)) : 0ull;
+      for (;;) {
+        u32* flag = flags + (it & 1);
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          if ((pend >> c) & 1ull) {
+            const u64 key = make_key(sc[c], static_cast<u32>(row));
+            if (key > tau_s[c]) {
+              const u32 pos = atomicAdd(&cnt_s[c], 1u);
+              if (pos < static_cast<u32>(cap)) {
+                lists[static_cast<size_t>(c) * cap + pos] = key;
+                pend &= ~(1ull << c);
+              }
+            } else {
+              pend &= ~(1ull << c);
+            }
+          }
+        }
+        if (pend) *flag = 1u;
+        named_bar_sync(1, 128);
+        // compaction: a list that is more than half full (or overflowed) is cut back to its best k
+        for (int c = ew; c < a.nq; c += 4) {
+          const u32 nc = cnt_s[c];
+          if (nc > static_cast<u32>(cap / 2)) {
+            u64* list = lists + static_cast<size_t>(c) * cap;
+            const int valid = nc < static_cast<u32>(cap) ? static_cast<int>(nc) : cap;
+            for (int i = valid + lane; i < cap; i += 32) list[i] = 0;
+            __syncwarp();
+            warp_sort_desc(list, cap, lane);
+            if (lane == 0) {
+              const int keep = valid < k ? valid : k;
+              cnt_s[c] = static_cast<u32>(keep);
+              if (valid >= k) tau_s[c] = list[k - 1];
+            }
+            __syncwarp();
+          }
+        }
+        const u32 again = *flag;
+        if (tid == 6 * 32) flags[(it + 1) & 1] = 0;
+        named_bar_sync(1, 128);
+        ++it;
+        if (!again) break;
+      }
+    }
+    // per-CTA result: best k of every query's list -> global scratch
+    named_bar_sync(1, 128);
+    for (int c = ew; c < a.nq; c += 4) {
+      u64* list = lists + static_cast<size_t>(c) * cap;
+      const u32 nc = cnt_s[c];
+      const int valid = nc < static_cast<u32>(cap) ? static_cast<int>(nc) : cap;
+      for (int i = valid + lane; i < cap; i += 32) list[i] = 0;
+      __syncwarp();
+      warp_sort_desc(list, cap, lane);
+      u64* dst = a.partial + (static_cast<size_t>(c) * gridDim.x + blockIdx.x) * k;
+      for (int i = lane; i < k; i += 32) dst[i] = i < cap ? list[i] : 0ull;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// one CTA per query: merge the per-CTA lists of the scan into the final top-k
+__global__ void __launch_bounds__(256) select_partials_kernel(const u64* __restrict__ partial, int n_lists, int k,
+                                                              float* __restrict__ D, long long* __restrict__ I,
+                                                              long long id_offset) {
+  __shared__ u64 buf[4096];
+  __shared__ u64 ctl[4];
+  const int q = blockIdx.x;
+  block_select_lists(partial + static_cast<size_t>(q) * n_lists * k, n_lists, k, k, buf, 4096, ctl);
+  block_emit_keys(buf, k, D + static_cast<size_t>(q) * k, I + static_cast<size_t>(q) * k, id_offset);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+  }
+  return fn;
+}
+
+static int make_map_2d(CUtensorMap* map, const float* base, unsigned long long inner, unsigned long long outer,
+                       unsigned box_inner, unsigned box_outer) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
+  if (!enc) return fail(B2R_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2R_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return B2R_OK;
+}
+
+template <int N>
+static int gemm_launch_n(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, int grid, size_t smem,
+                         cudaStream_t stream) {
+  auto kern = flat_gemm_tc_kernel<N>;
+  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<grid, kGemmThreads, smem, stream>>>(ma, mb, a);
+  B2R_CUDA(cudaGetLastError());
+  return B2R_OK;
+}
+
+bool gemm_path_supported(int d, int k) { return d % kSlabK == 0 && d >= kSlabK && k <= 128; }
+
+// Scores `nq` (<= 64) queries against the whole shard in one pass.  bsplit: device scratch of
+// 2 * 64 * d floats; partial: device scratch of 64 * 148 * k keys.
+int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
+                      long long* I_dev, long long id_offset, float* bsplit, u64* partial, int num_sms,
+                      cudaStream_t stream, int* launches) {
+  const int N = nq <= 16 ? 16 : (nq <= 32 ? 32 : 64);
+  const int cap = [&] {
+    int c = 64;
+    while (c < 2 * k) c <<= 1;
+    return c;
+  }();
+  const long long n_tiles = (n + kTileM - 1) / kTileM;
+  const int grid = static_cast<int>(std::min<long long>(n_tiles, num_sms));
+  gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit);
+  B2R_CUDA(cudaGetLastError());
+  CUtensorMap ma, mb;
+  int rc = make_map_2d(&ma, rows, static_cast<unsigned long long>(d), static_cast<unsigned long long>(n), kSlabK, kTileM);
+  if (rc) return rc;
+  rc = make_map_2d(&mb, bsplit, static_cast<unsigned long long>(d), static_cast<unsigned long long>(2 * N), kSlabK, N);
+  if (rc) return rc;
+  const size_t raw_stage = kTileM * kSlabK * 4 + 2 * static_cast<size_t>(N) * kSlabK * 4;
+  const size_t fixed = kLoStages * kTileM * kSlabK * 4 + 64 * 8 /*barriers*/ + static_cast<size_t>(N) * 12 + 32 +
+                       static_cast<size_t>(N) * cap * 8 + 1024 /*alignment slack*/;
+  int stages = tunable("gemm.stages");
+  if (stages <= 0) stages = 8;
+  while (stages > 2 && stages * raw_stage + fixed > 227 * 1024 - 1024) --stages;
+  if (stages * raw_stage + fixed > 227 * 1024 - 1024) return fail(B2R_ERR_UNSUPPORTED, "tensor-core scan: k too large for shared memory");
+  GemmArgs a;
+  a.n = n;
+  a.d = d;
+  a.nq = nq;
+  a.k = k;
+  a.cap = cap;
+  a.raw_stages = stages;
+  a.n_tiles = n_tiles;
+  a.partial = partial;
+  const size_t smem = stages * raw_stage + fixed;
+  switch (N) {
+    case 16: rc = gemm_launch_n<16>(ma, mb, a, grid, smem, stream); break;
+    case 32: rc = gemm_launch_n<32>(ma, mb, a, grid, smem, stream); break;
+    default: rc = gemm_launch_n<64>(ma, mb, a, grid, smem, stream); break;
+  }
+  if (rc) return rc;
+  select_partials_kernel<<<nq, 256, 0, stream>>>(partial, grid, k, D_dev, I_dev, id_offset);
+  B2R_CUDA(cudaGetLastError());
+  *launches += 3;
+  return B2R_OK;
+}
+
+}  // namespace b2r

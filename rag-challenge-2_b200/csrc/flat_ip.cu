@@ -394,9 +394,16 @@ struct Workspace {
   size_t bytes = 0;
 };
 
-static size_t workspace_bytes() {
-  return 256 + static_cast<size_t>(kMaxNQ) * kMaxGrid * B2R_MAX_K * sizeof(u64);
-}
+static const size_t kPartialBytes = static_cast<size_t>(kMaxNQ) * kMaxGrid * B2R_MAX_K * sizeof(u64);
+static const size_t kBsplitBytes = static_cast<size_t>(2) * 64 * 16384 * sizeof(float);  // tensor-core path: hi/lo queries
+
+static size_t workspace_bytes() { return 256 + kPartialBytes + kBsplitBytes; }
+
+// csrc/flat_gemm.cu
+bool gemm_path_supported(int d, int k);
+int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
+                      long long* I_dev, long long id_offset, float* bsplit, u64* partial, int num_sms,
+                      cudaStream_t stream, int* launches);
 
 struct HostCtx {
   cudaStream_t stream = nullptr;
@@ -612,6 +619,24 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
   int rc = get_workspace(h, stream, &ws);
   if (rc) return rc;
   int done = 0;
+  // batches go to the tensor cores (K2): one pass over the rows per <= 64 queries
+  int gemm_min = tunable("flat.gemm_min_nq");
+  if (gemm_min <= 0) gemm_min = 5;
+  int gemm_max = tunable("flat.gemm_max_n");
+  if (gemm_max <= 0 || gemm_max > 64) gemm_max = 64;
+  while (nq - done >= gemm_min && gemm_path_supported(h->d, k) && !tunable("flat.force_generic") &&
+         !tunable("flat.no_gemm") && h->n >= 128) {
+    const int chunk = std::min(nq - done, gemm_max);
+    int launches = 0;
+    rc = gemm_search_chunk(h->rows, h->n, h->d, q_dev + static_cast<size_t>(done) * h->d, chunk, k,
+                           D_dev + static_cast<size_t>(done) * k,
+                           reinterpret_cast<long long*>(I_dev) + static_cast<size_t>(done) * k, id_offset,
+                           reinterpret_cast<float*>(ws.base + 256 + kPartialBytes),
+                           reinterpret_cast<u64*>(ws.base + 256), h->num_sms, stream, &launches);
+    if (rc) return rc;
+    launch_counter() += launches;
+    done += chunk;
+  }
   while (done < nq) {
     ScanPlan p;
     rc = make_plan(h, nq - done, k, &p);

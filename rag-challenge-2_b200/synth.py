@@ -14,8 +14,8 @@ import math
 
 import numpy as np
 
-ROW_BLOCK = 1 << 18   # rows per seeded block (dense)
-DOC_BLOCK = 1 << 17   # documents per seeded block (tokens)
+ROW_BLOCK = 1 << 14   # rows per seeded block (dense)
+DOC_BLOCK = 1 << 14   # documents per seeded block (tokens)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,102 @@
+"""GPU parity: K2, the tcgen05 (3xTF32) batched scan, through the C ABI, vs the float64 oracle.
+Same bar as the SIMT path: ids equal up to swaps inside a 1e-5-relative band, scores 1e-5 relative."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def unit_rows(n, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x
+
+
+def queries_for(xb, nq, seed):
+    rng = np.random.default_rng(seed)
+    d = xb.shape[1]
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    for i in range(0, nq, 2):
+        j = int(rng.integers(0, xb.shape[0]))
+        q[i] = xb[j] + 0.1 * rng.standard_normal(d, dtype=np.float32) / np.sqrt(d)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return q
+
+
+def check(index, xb, xq, k):
+    D, I = index.search(xq, k)
+    S = oracle.flat_ip_scores_ref(xb, xq, np.float64)
+    oracle.assert_topk_equivalent(D, I, S, k, rtol=1e-5, what=f"gemm n={xb.shape[0]} d={xb.shape[1]} nq={xq.shape[0]} k={k}")
+    return D, I
+
+
+@pytest.mark.parametrize("nq", [5, 16, 17, 32, 33, 64, 65, 130])
+def test_batches_d1024(b2r, nq):
+    xb = unit_rows(30011, 1024, 41)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    check(index, xb, queries_for(xb, nq, 42 + nq), 30)
+    assert index.last_launch_count() >= 3      # split + tcgen05 scan + select (per <= 64 queries)
+
+
+@pytest.mark.parametrize("n", [128, 129, 255, 1000, 18945])
+@pytest.mark.parametrize("k", [1, 10, 64, 128])
+def test_tile_edges_and_k(b2r, n, k):
+    xb = unit_rows(n, 1024, 43)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    check(index, xb, queries_for(xb, 12, 44), k)
+
+
+@pytest.mark.parametrize("d", [32, 96, 256, 768, 1536, 2048])
+def test_other_widths(b2r, d):
+    xb = unit_rows(9001, d, 45)
+    index = b2r.FlatIPIndex(d)
+    index.add(xb)
+    check(index, xb, queries_for(xb, 20, 46), 30)
+
+
+def test_unnormalised_large_magnitudes(b2r):
+    """3xTF32 error is relative to |a||b|: check rows / queries far from unit norm."""
+    rng = np.random.default_rng(47)
+    xb = (rng.standard_normal((20000, 1024)) * rng.uniform(0.01, 50.0, (20000, 1))).astype(np.float32)
+    xq = (rng.standard_normal((24, 1024)) * 7.0).astype(np.float32)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    D, I = index.search(xq, 30)
+    S = oracle.flat_ip_scores_ref(xb, xq, np.float64)
+    # tolerance relative to the score scale of each query (|q| * max|x|), as the SIMT path
+    scale = np.abs(S).max(axis=1, keepdims=True)
+    got = np.take_along_axis(S, I, 1)
+    assert np.all(np.abs(D - got) <= 1e-5 * scale)
+    kth = np.sort(S, axis=1)[:, -30][:, None]
+    assert np.all(got >= kth - 1e-5 * scale)
+
+
+def test_ties_and_matches_simt_path(b2r):
+    from rag_challenge_2_b200 import _lib
+
+    base = unit_rows(64, 1024, 48)
+    xb = np.concatenate([base] * 80, axis=0)          # heavy exact ties: row i == row i + 64 j
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    xq = base[:8].copy()
+    D, I = index.search(xq, 30)
+    for qi in range(8):
+        top = I[qi][D[qi] == D[qi, 0]]
+        assert np.array_equal(top, qi + 64 * np.arange(len(top)))   # equal scores: ascending id
+    xb2 = unit_rows(50000, 1024, 49)
+    index2 = b2r.FlatIPIndex(1024)
+    index2.add(xb2)
+    q2 = queries_for(xb2, 8, 50)
+    D1, I1 = check(index2, xb2, q2, 30)
+    _lib.tunable_set("flat.no_gemm", 1)
+    try:
+        D2, I2 = check(index2, xb2, q2, 30)
+    finally:
+        _lib.tunable_set("flat.no_gemm", 0)
+    assert np.array_equal(I1, I2)
+    assert np.allclose(D1, D2, rtol=2e-6, atol=1e-7)

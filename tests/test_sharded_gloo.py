@@ -105,7 +105,7 @@ def test_sharded_search_world2_gloo(tmp_path):
 def test_shard_bounds():
     from rag_challenge_2_b200.hybrid import shard_bounds
 
-    assert shard_bounds(10_000_000, 8, 1 << 18) == [0, 1310720, 2621440, 3932160, 5242880, 6553600, 7864320, 9175040, 10_000_000]
+    assert shard_bounds(10_000_000, 8, 1 << 14) == [0, 1261568, 2523136, 3784704, 5046272, 6307840, 7569408, 8830976, 10_000_000]
     assert shard_bounds(10, 4) == [0, 3, 6, 9, 10]
     assert shard_bounds(5, 8) == [0, 1, 2, 3, 4, 5, 5, 5, 5]
     assert shard_bounds(1000, 1, 128) == [0, 1000]
