@@ -170,7 +170,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   constexpr u32 kABytes = kTileM * kSlabK * 4;            // 16 KiB
   constexpr u32 kBBytes = N * kSlabK * 4;                 // N * 128 B
   constexpr u32 kRawStage = kABytes + 2 * kBBytes;        // A (raw -> hi) | B_hi | B_lo
-  constexpr u32 kTmemCols = (2 * N) < 32 ? 32 : 2 * N;    // two accumulator tiles (power of two for N = 16/32/64)
+  // The tensor core truncates when it accumulates in fp32, so the error of a long MMA chain grows
+  // with its length and with the size of the running sum.  Per tile we therefore keep FOUR
+  // accumulators of N columns: hi*hi split 2-way over K (even / odd slabs) and the two small
+  // cross terms likewise; the epilogue adds them in fp32 (round-to-nearest).  x2 tiles in flight.
+  constexpr u32 kTmemCols = 8 * N;                        // 128 / 256 / 512 columns for N = 16 / 32 / 64
   const int R = a.raw_stages;
   const int n_slabs = a.d / kSlabK;
 
@@ -246,8 +250,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
         mbar_wait(&tm_empty[buf], ph_buf[buf] ^ 1u);  // epilogue drained this accumulator tile
         tc_fence_after();
-        const u32 tmem_d = tmem_base + static_cast<u32>(buf * N);
+        const u32 tile_d = tmem_base + static_cast<u32>(buf * 4 * N);
         for (int sl = 0; sl < n_slabs; ++sl) {
+          const u32 d_main = tile_d + static_cast<u32>((sl & 1) * N);
+          const u32 d_small = tile_d + static_cast<u32>((2 + (sl & 1)) * N);
+          const bool first = sl < 2;  // first slab of this K-split: overwrite instead of accumulate
           mbar_wait(&xf_full[l], ph_l);
           tc_fence_after();
           const u32 st = smem_u32(raw_ring + static_cast<size_t>(s) * kRawStage);
@@ -258,9 +265,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
           for (int kk = 0; kk < kSlabK / 8; ++kk) {
             const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);  // 32 bytes per k-step inside the swizzle row
-            tc_mma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, idesc, (sl | kk) ? 1u : 0u);
-            tc_mma_tf32(tmem_d, d_alo + adv, d_bhi + adv, idesc, 1u);
-            tc_mma_tf32(tmem_d, d_ahi + adv, d_blo + adv, idesc, 1u);
+            const u32 acc = (first && kk == 0) ? 0u : 1u;
+            tc_mma_tf32(d_main, d_ahi + adv, d_bhi + adv, idesc, acc);
+            tc_mma_tf32(d_small, d_alo + adv, d_bhi + adv, idesc, acc);
+            tc_mma_tf32(d_small, d_ahi + adv, d_blo + adv, idesc, 1u);
           }
           tc_commit(&empty[s]);      // raw stage reusable once these MMAs have read it
           tc_commit(&xf_empty[l]);   // lo stage likewise
@@ -326,10 +334,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       mbar_wait(&tm_full[buf], ph_buf[buf]);
       tc_fence_after();
       float sc[N];
-      const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(buf * N);
+      const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(buf * 4 * N);
 #pragma unroll
-      for (int c = 0; c < N; c += 16) tc_ld16(taddr + c, sc + c);
-      tc_wait_ld();
+      for (int c = 0; c < N; c += 16) {
+        float m0[16], m1[16], s0[16], s1[16];
+        tc_ld16(taddr + c, m0);
+        tc_ld16(taddr + 2 * N + c, s0);
+        if (n_slabs > 1) {
+          tc_ld16(taddr + N + c, m1);
+          tc_ld16(taddr + 3 * N + c, s1);
+        }
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          sc[c + i] = (n_slabs > 1) ? (m0[i] + m1[i]) + (s0[i] + s1[i]) : m0[i] + s0[i];
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tm_empty[buf]);
