@@ -35,7 +35,7 @@ namespace b2r {
 static const int kGemmThreads = 320;
 static const int kSlabK = 32;          // floats per K-slab = one 128-byte swizzle row
 static const int kTileM = 128;
-static const int kLoStages = 2;
+static const int kLoStages = 4;
 
 struct GemmArgs {
   long long n;
@@ -109,10 +109,10 @@ __device__ __forceinline__ void tc_ld16(u32 taddr, float* v) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// round-to-nearest (ties away) to tf32 precision with two integer ops (cvt.rna.tf32.f32 runs on
+// the slow conversion pipe): add half an ulp of the 10-bit mantissa to the magnitude, clear 13 bits
 __device__ __forceinline__ float rna_tf32(float x) {
-  u32 u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -148,7 +148,7 @@ __global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, i
     if (row < nq) {
       const float x = q[i];
       hi = rna_tf32(x);
-      lo = rna_tf32(x - hi);
+      lo = x - hi;
     }
     Bs[i] = hi;
     Bs[total + i] = lo;
@@ -303,10 +303,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           h.y = rna_tf32(x.y);
           h.z = rna_tf32(x.z);
           h.w = rna_tf32(x.w);
-          r.x = rna_tf32(x.x - h.x);
-          r.y = rna_tf32(x.y - h.y);
-          r.z = rna_tf32(x.z - h.z);
-          r.w = rna_tf32(x.w - h.w);
+          // the remainder is exact in fp32 (<= 13 significant bits); the tensor core drops at most
+          // its 2 lowest bits (2^-23 relative to x), so it is stored un-rounded
+          r.x = x.x - h.x;
+          r.y = x.y - h.y;
+          r.z = x.z - h.z;
+          r.w = x.w - h.w;
           hi[idx] = h;
           lo[idx] = r;
         }
