@@ -6,9 +6,18 @@
 //
 //   S[128 rows, N queries] = A[128, d] * B[N, d]^T          per row tile, accumulated over d in TMEM
 //
-// fp32 parity through 3xTF32: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi); the kernel
-// issues A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (kind::tf32, fp32 accumulate), dropping only the
-// lo*lo term (~2^-22 relative) — the same order of error as a different fp32 summation order.
+// Exactness.  The kernel has two modes (template TERMS):
+//   TERMS = 1  one tf32 MMA per k-step on the raw fp32 data (the tensor core uses the top 19 bits):
+//              scores are approximate, |err| <= 2^-9 |q||x|.  It selects k' > k candidates per
+//              query; `gemm_rescore_kernel` then recomputes their scores in fp32 with the SIMT
+//              kernel's arithmetic, takes the best k and CHECKS that no row outside the candidate
+//              set can reach the k-th exact score (approx k'-th + bound < exact k-th).  Queries
+//              that fail the check are redone by the TERMS = 3 pass.
+//   TERMS = 3  3xTF32: x = hi + lo with hi = rna_tf32(x), lo = x - hi; issues A_hi*B_hi +
+//              A_lo*B_hi + A_hi*B_lo (fp32 accumulate, separate TMEM accumulators for the large
+//              and the small terms, 2-way split-K), dropping only lo*lo: ~3e-6 relative, the same
+//              order as a different fp32 summation order.  Shared-memory bound (7x the HBM stream:
+//              ncu r01), hence only the fallback and the N x N cosine path.
 //
 // Warp roles (320 threads, 1 CTA / SM, persistent over row tiles t = cta, cta + grid, ...):
 //   warp 0      TMA producer: per K-slab (32 floats = 128 B, SWIZZLE_128B) one 2-D tensor copy of
@@ -44,7 +53,8 @@ struct GemmArgs {
   int k, cap;   // cap: per-query candidate capacity (power of two >= 2k)
   int raw_stages;
   long long n_tiles;
-  u64* partial;  // [N][gridDim.x][k]
+  u64* partial;        // [N][gridDim.x][k]
+  const u32* active;   // optional per-query flags (device); NULL = all queries active
 };
 
 // ---------------- PTX wrappers specific to this kernel ----------------
@@ -139,7 +149,8 @@ __host__ __device__ constexpr u32 make_idesc_tf32(int n) {
 // ---------------------------------------------------------------------------------------------
 // prep: split the queries into tf32 hi / lo parts: Bs[0][q][:] = hi, Bs[1][q][:] = lo; rows nq..N-1 zero
 // ---------------------------------------------------------------------------------------------
-__global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, int N, int d, float* __restrict__ Bs) {
+__global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, int N, int d, float* __restrict__ Bs,
+                                          int split) {
   const long long total = static_cast<long long>(N) * d;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -147,7 +158,7 @@ __global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, i
     float hi = 0.f, lo = 0.f;
     if (row < nq) {
       const float x = q[i];
-      hi = rna_tf32(x);
+      hi = split ? rna_tf32(x) : x;  // split == 0: raw queries for the single-pass mode
       lo = x - hi;
     }
     Bs[i] = hi;
@@ -158,7 +169,7 @@ __global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, i
 // ---------------------------------------------------------------------------------------------
 // the scan
 // ---------------------------------------------------------------------------------------------
-template <int N>
+template <int N, int TERMS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     flat_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const GemmArgs a) {
@@ -169,7 +180,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int warp = tid >> 5, lane = tid & 31;
   constexpr u32 kABytes = kTileM * kSlabK * 4;            // 16 KiB
   constexpr u32 kBBytes = N * kSlabK * 4;                 // N * 128 B
-  constexpr u32 kRawStage = kABytes + 2 * kBBytes;        // A (raw -> hi) | B_hi | B_lo
+  constexpr u32 kRawStage = kABytes + (TERMS == 3 ? 2 : 1) * kBBytes;  // A (raw -> hi) | B[_hi] | (B_lo)
+  constexpr int kLo = TERMS == 3 ? kLoStages : 0;
   // The tensor core truncates when it accumulates in fp32, so the error of a long MMA chain grows
   // with its length and with the size of the running sum.  Per tile we therefore keep FOUR
   // accumulators of N columns: hi*hi split 2-way over K (even / odd slabs) and the two small
@@ -180,7 +192,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
   unsigned char* raw_ring = smem_raw;                                  // R stages
   unsigned char* lo_ring = raw_ring + static_cast<size_t>(R) * kRawStage;  // kLoStages x 16 KiB
-  u64* bars = reinterpret_cast<u64*>(lo_ring + kLoStages * kABytes);
+  u64* bars = reinterpret_cast<u64*>(lo_ring + kLo * kABytes);
   u64* full = bars;                    // [R]   TMA landed
   u64* empty = full + R;               // [R]   MMAs that read the raw stage are done
   u64* xf_full = empty + R;            // [kLoStages] hi/lo written
@@ -214,6 +226,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
   if (tid < 2) flags[tid] = 0;
   if (warp == 1) tc_alloc(tmem_slot, kTmemCols);
+  // queries this launch has to answer; none (all flags clear) -> skip the scan entirely
+  u64 active_mask = (a.nq >= 64) ? ~0ull : ((1ull << a.nq) - 1ull);
+  if (a.active) {
+    u64 m = 0;
+    for (int c = 0; c < a.nq; ++c) m |= a.active[c] ? (1ull << c) : 0ull;
+    active_mask &= m;
+  }
+  const long long n_tiles = active_mask ? a.n_tiles : 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -225,7 +245,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const u64 pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
       int s = 0;
       u32 ph = 0;
-      for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int row0 = static_cast<int>(t * kTileM);
         for (int sl = 0; sl < n_slabs; ++sl) {
           mbar_wait(&empty[s], ph ^ 1u);
@@ -233,7 +253,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           mbar_arrive_expect_tx(&full[s], kRawStage);
           tma_load_2d(st, &map_a, sl * kSlabK, row0, &full[s], pol_a);
           tma_load_2d(st + kABytes, &map_b, sl * kSlabK, 0, &full[s], pol_b);
-          tma_load_2d(st + kABytes + kBBytes, &map_b, sl * kSlabK, N, &full[s], pol_b);
+          if constexpr (TERMS == 3) tma_load_2d(st + kABytes + kBBytes, &map_b, sl * kSlabK, N, &full[s], pol_b);
           if (++s == R) {
             s = 0;
             ph ^= 1u;
@@ -246,8 +266,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (lane == 0) {
       constexpr u32 idesc = make_idesc_tf32(N);
       int s = 0, l = 0, buf = 0;
-      u32 ph_l = 0, ph_buf[2] = {0, 0};
-      for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      u32 ph_s = 0, ph_l = 0, ph_buf[2] = {0, 0};
+      (void)l;
+      (void)ph_l;
+      for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         mbar_wait(&tm_empty[buf], ph_buf[buf] ^ 1u);  // epilogue drained this accumulator tile
         tc_fence_after();
         const u32 tile_d = tmem_base + static_cast<u32>(buf * 4 * N);
@@ -255,27 +277,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           const u32 d_main = tile_d + static_cast<u32>((sl & 1) * N);
           const u32 d_small = tile_d + static_cast<u32>((2 + (sl & 1)) * N);
           const bool first = sl < 2;  // first slab of this K-split: overwrite instead of accumulate
-          mbar_wait(&xf_full[l], ph_l);
+          if constexpr (TERMS == 3) {
+            mbar_wait(&xf_full[l], ph_l);
+          } else {
+            mbar_wait(&full[s], ph_s);
+          }
           tc_fence_after();
           const u32 st = smem_u32(raw_ring + static_cast<size_t>(s) * kRawStage);
           const u64 d_ahi = make_kmajor_sw128_desc(st);
           const u64 d_bhi = make_kmajor_sw128_desc(st + kABytes);
-          const u64 d_blo = make_kmajor_sw128_desc(st + kABytes + kBBytes);
-          const u64 d_alo = make_kmajor_sw128_desc(smem_u32(lo_ring + static_cast<size_t>(l) * kABytes));
+          if constexpr (TERMS == 3) {
+            const u64 d_blo = make_kmajor_sw128_desc(st + kABytes + kBBytes);
+            const u64 d_alo = make_kmajor_sw128_desc(smem_u32(lo_ring + static_cast<size_t>(l) * kABytes));
 #pragma unroll
-          for (int kk = 0; kk < kSlabK / 8; ++kk) {
-            const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);  // 32 bytes per k-step inside the swizzle row
-            const u32 acc = (first && kk == 0) ? 0u : 1u;
-            tc_mma_tf32(d_main, d_ahi + adv, d_bhi + adv, idesc, acc);
-            tc_mma_tf32(d_small, d_alo + adv, d_bhi + adv, idesc, acc);
-            tc_mma_tf32(d_small, d_ahi + adv, d_blo + adv, idesc, 1u);
+            for (int kk = 0; kk < kSlabK / 8; ++kk) {
+              const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);  // 32 bytes per k-step inside the swizzle row
+              const u32 acc = (first && kk == 0) ? 0u : 1u;
+              tc_mma_tf32(d_main, d_ahi + adv, d_bhi + adv, idesc, acc);
+              tc_mma_tf32(d_small, d_alo + adv, d_bhi + adv, idesc, acc);
+              tc_mma_tf32(d_small, d_ahi + adv, d_blo + adv, idesc, 1u);
+            }
+            tc_commit(&empty[s]);      // raw stage reusable once these MMAs have read it
+            tc_commit(&xf_empty[l]);   // lo stage likewise
+            if (++l == kLoStages) {
+              l = 0;
+              ph_l ^= 1u;
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < kSlabK / 8; ++kk) {
+              const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);
+              tc_mma_tf32(d_main, d_ahi + adv, d_bhi + adv, idesc, (first && kk == 0) ? 0u : 1u);
+            }
+            tc_commit(&empty[s]);
           }
-          tc_commit(&empty[s]);      // raw stage reusable once these MMAs have read it
-          tc_commit(&xf_empty[l]);   // lo stage likewise
-          if (++s == R) s = 0;
-          if (++l == kLoStages) {
-            l = 0;
-            ph_l ^= 1u;
+          if (++s == R) {
+            s = 0;
+            ph_s ^= 1u;
           }
         }
         tc_commit(&tm_full[buf]);    // accumulator tile complete
@@ -285,10 +323,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else if (warp < 6) {
     // ======================= transform warps: A -> hi (in place), lo =======================
+    if constexpr (TERMS == 3) {
     const int xt = tid - 64;  // 0..127
     int s = 0, l = 0;
     u32 ph_s = 0, ph_l = 0;
-    for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       for (int sl = 0; sl < n_slabs; ++sl) {
         mbar_wait(&full[s], ph_s);
         mbar_wait(&xf_empty[l], ph_l ^ 1u);
@@ -325,6 +364,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
     }
+    }
   } else {
     // ======================= epilogue warps: TMEM -> registers -> fused select =======================
     const int ew = warp - 6;       // 0..3
@@ -332,24 +372,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int cap = a.cap, k = a.k;
     int buf = 0, it = 0;
     u32 ph_buf[2] = {0, 0};
-    for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&tm_full[buf], ph_buf[buf]);
       tc_fence_after();
       float sc[N];
       const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(buf * 4 * N);
 #pragma unroll
       for (int c = 0; c < N; c += 16) {
-        float m0[16], m1[16], s0[16], s1[16];
+        float m0[16], m1[16];
         tc_ld16(taddr + c, m0);
-        tc_ld16(taddr + 2 * N + c, s0);
-        if (n_slabs > 1) {
-          tc_ld16(taddr + N + c, m1);
-          tc_ld16(taddr + 3 * N + c, s1);
-        }
-        tc_wait_ld();
+        if (n_slabs > 1) tc_ld16(taddr + N + c, m1);
+        if constexpr (TERMS == 3) {
+          float s0[16], s1[16];
+          tc_ld16(taddr + 2 * N + c, s0);
+          if (n_slabs > 1) tc_ld16(taddr + 3 * N + c, s1);
+          tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          sc[c + i] = (n_slabs > 1) ? (m0[i] + m1[i]) + (s0[i] + s1[i]) : m0[i] + s0[i];
+          for (int i = 0; i < 16; ++i) {
+            sc[c + i] = (n_slabs > 1) ? (m0[i] + m1[i]) + (s0[i] + s1[i]) : m0[i] + s0[i];
+          }
+        } else {
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sc[c + i] = (n_slabs > 1) ? m0[i] + m1[i] : m0[i];
         }
       }
       tc_fence_before();
@@ -359,7 +404,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       buf ^= 1;
 
       const long long row = t * kTileM + quad * 32 + lane;
-      u64 pend = (row < a.n) ? ((a.nq >= 64) ? ~0ull : ((1ull << a.nq) - 1ull)) : 0ull;
+      u64 pend = (row < a.n) ? active_mask : 0ull;
       for (;;) {
         u32* flag = flags + (it & 1);
 #pragma unroll
@@ -406,6 +451,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // per-CTA result: best k of every query's list -> global scratch
     named_bar_sync(1, 128);
     for (int c = ew; c < a.nq; c += 4) {
+      if (!((active_mask >> c) & 1ull)) continue;  // not this launch's query: its lists are never read
       u64* list = lists + static_cast<size_t>(c) * cap;
       const u32 nc = cnt_s[c];
       const int valid = nc < static_cast<u32>(cap) ? static_cast<int>(nc) : cap;
@@ -424,15 +470,100 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 }
 
-// one CTA per query: merge the per-CTA lists of the scan into the final top-k
+// one CTA per query: merge the per-CTA lists of the scan into that query's top-k
 __global__ void __launch_bounds__(256) select_partials_kernel(const u64* __restrict__ partial, int n_lists, int k,
                                                               float* __restrict__ D, long long* __restrict__ I,
-                                                              long long id_offset) {
+                                                              long long id_offset, const u32* __restrict__ active) {
   __shared__ u64 buf[4096];
   __shared__ u64 ctl[4];
   const int q = blockIdx.x;
+  if (active && !active[q]) return;  // answered by an earlier pass
   block_select_lists(partial + static_cast<size_t>(q) * n_lists * k, n_lists, k, k, buf, 4096, ctl);
   block_emit_keys(buf, k, D + static_cast<size_t>(q) * k, I + static_cast<size_t>(q) * k, id_offset);
+}
+
+// max over rows of |x|^2 (one pass over the shard, cached per index): the error bound of the
+// single-pass tf32 scores is 2^-9 * |q| * max|x|
+__global__ void max_row_norm2_kernel(const float* __restrict__ xb, long long n, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float best = 0.f;
+  for (long long r = gw; r < n; r += nw) {
+    const float* row = xb + r * d;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc = fmaf(row[c], row[c], acc);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    best = fmaxf(best, acc);
+  }
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(best));  // non-negative floats order as ints
+}
+
+// Exact fp32 rescoring of the k' candidates of every query, final top-k, and the exactness check.
+// One CTA per query; a warp scores one candidate at a time with the SIMT scan's arithmetic
+// (lanes over 128-bit chunks, even / odd accumulators, xor butterfly).
+__global__ void __launch_bounds__(256) gemm_rescore_kernel(const float* __restrict__ xb, int d,
+                                                           const float* __restrict__ q, const float* __restrict__ Dp,
+                                                           const long long* __restrict__ Ip, int kp, int k,
+                                                           const float* __restrict__ max_norm2, float* __restrict__ D,
+                                                           long long* __restrict__ I, long long id_offset,
+                                                           u32* __restrict__ redo) {
+  __shared__ u64 keys[256];
+  __shared__ float s_qn2;
+  const int qi = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* qv = q + static_cast<size_t>(qi) * d;
+  const long long* cand = Ip + static_cast<size_t>(qi) * kp;
+  keys[tid] = 0;
+  if (warp == 0) {
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc = fmaf(qv[c], qv[c], acc);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (lane == 0) s_qn2 = acc;
+  }
+  __syncthreads();
+  const bool vec4 = (d & 3) == 0;
+  for (int c = warp; c < kp; c += 8) {
+    const long long id = cand[c];
+    if (id < 0) continue;  // warp-uniform
+    const float* row = xb + id * d;
+    float a0 = 0.f, a1 = 0.f;
+    if (vec4) {
+      int j = 0;
+      for (int ch = lane; ch < (d >> 2); ch += 32, ++j) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(row) + ch);
+        const float4 y = *reinterpret_cast<const float4*>(qv + ch * 4);
+        float& acc = (j & 1) ? a1 : a0;
+        acc = fmaf(x.x, y.x, acc);
+        acc = fmaf(x.y, y.y, acc);
+        acc = fmaf(x.z, y.z, acc);
+        acc = fmaf(x.w, y.w, acc);
+      }
+    } else {
+      for (int ch = lane; ch < d; ch += 32) a0 = fmaf(__ldg(row + ch), qv[ch], a0);
+    }
+    float sum = a0 + a1;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    if (lane == 0) keys[c] = make_key(sum, static_cast<u32>(id));
+  }
+  __syncthreads();
+  block_sort_desc(keys, 256);
+  block_emit_keys(keys, k, D + static_cast<size_t>(qi) * k, I + static_cast<size_t>(qi) * k, id_offset);
+  if (tid == 0) {
+    // Rows outside the candidate set have approx score <= the k'-th approx score, hence exact
+    // score <= that + bound.  If this cannot reach the exact k-th score the answer is proven exact.
+    u32 need_redo = 0;
+    const bool list_full = cand[kp - 1] >= 0;  // fewer than k' rows in the shard: every row was rescored
+    if (list_full) {
+      const float bound = 0.001953125f * 1.0625f * sqrtf(s_qn2) * sqrtf(*max_norm2) + 1e-6f;  // 2^-9 (+6 %) |q| max|x|
+      const u64 kth = keys[k - 1];
+      const float exact_kth = kth ? key_score(kth) : -3.4028235e38f;
+      if (!(Dp[static_cast<size_t>(qi) * kp + kp - 1] + bound < exact_kth)) need_redo = 1;
+    }
+    redo[qi] = need_redo;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -466,64 +597,126 @@ static int make_map_2d(CUtensorMap* map, const float* base, unsigned long long i
   return B2R_OK;
 }
 
-template <int N>
-static int gemm_launch_n(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, int grid, size_t smem,
-                         cudaStream_t stream) {
-  auto kern = flat_gemm_tc_kernel<N>;
+template <int N, int TERMS>
+static int gemm_launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, int grid, size_t smem,
+                          cudaStream_t stream) {
+  auto kern = flat_gemm_tc_kernel<N, TERMS>;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<grid, kGemmThreads, smem, stream>>>(ma, mb, a);
   B2R_CUDA(cudaGetLastError());
   return B2R_OK;
 }
 
-bool gemm_path_supported(int d, int k) { return d % kSlabK == 0 && d >= kSlabK && k <= 128; }
+static int pow2_ge_g(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
 
-// Scores `nq` (<= 64) queries against the whole shard in one pass.  bsplit: device scratch of
-// 2 * 64 * d floats; partial: device scratch of 64 * 148 * k keys.
-int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
-                      long long* I_dev, long long id_offset, float* bsplit, u64* partial, int num_sms,
-                      cudaStream_t stream, int* launches) {
-  const int N = nq <= 16 ? 16 : (nq <= 32 ? 32 : 64);
-  const int cap = [&] {
-    int c = 64;
-    while (c < 2 * k) c <<= 1;
-    return c;
-  }();
+// one scan pass: `terms` = 1 (approximate, raw tf32) or 3 (3xTF32); selects `ksel` per query
+static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, int nq, int ksel, int terms,
+                     const u32* active, float* D_out, long long* I_out, long long id_offset, float* bsplit,
+                     u64* partial, int num_sms, cudaStream_t stream) {
+  const int cap = pow2_ge_g(std::max(2 * ksel, 64));
+  // candidate lists (N x cap keys) get at most 64 KiB of shared memory
+  int N = nq <= 16 ? 16 : (nq <= 32 ? 32 : 64);
+  if (static_cast<size_t>(N) * cap * 8 > 64 * 1024) return fail(B2R_ERR_INVALID, "gemm_scan: batch too wide for this k");
   const long long n_tiles = (n + kTileM - 1) / kTileM;
   const int grid = static_cast<int>(std::min<long long>(n_tiles, num_sms));
-  gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit);
+  gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit, terms == 3 ? 1 : 0);
   B2R_CUDA(cudaGetLastError());
   CUtensorMap ma, mb;
   int rc = make_map_2d(&ma, rows, static_cast<unsigned long long>(d), static_cast<unsigned long long>(n), kSlabK, kTileM);
   if (rc) return rc;
   rc = make_map_2d(&mb, bsplit, static_cast<unsigned long long>(d), static_cast<unsigned long long>(2 * N), kSlabK, N);
   if (rc) return rc;
-  const size_t raw_stage = kTileM * kSlabK * 4 + 2 * static_cast<size_t>(N) * kSlabK * 4;
-  const size_t fixed = kLoStages * kTileM * kSlabK * 4 + 64 * 8 /*barriers*/ + static_cast<size_t>(N) * 12 + 32 +
-                       static_cast<size_t>(N) * cap * 8 + 1024 /*alignment slack*/;
+  const size_t raw_stage = kTileM * kSlabK * 4 + static_cast<size_t>(terms == 3 ? 2 : 1) * N * kSlabK * 4;
+  const size_t fixed = (terms == 3 ? kLoStages : 0) * static_cast<size_t>(kTileM) * kSlabK * 4 + 64 * 8 /*barriers*/ +
+                       static_cast<size_t>(N) * 12 + 32 + static_cast<size_t>(N) * cap * 8 + 1024 /*alignment slack*/;
   int stages = tunable("gemm.stages");
   if (stages <= 0) stages = 8;
-  while (stages > 2 && stages * raw_stage + fixed > 227 * 1024 - 1024) --stages;
-  if (stages * raw_stage + fixed > 227 * 1024 - 1024) return fail(B2R_ERR_UNSUPPORTED, "tensor-core scan: k too large for shared memory");
+  const size_t limit = 227 * 1024 - 1024;
+  while (stages > 2 && stages * raw_stage + fixed > limit) --stages;
+  if (stages * raw_stage + fixed > limit) return fail(B2R_ERR_UNSUPPORTED, "tensor-core scan: k too large for shared memory");
   GemmArgs a;
   a.n = n;
   a.d = d;
   a.nq = nq;
-  a.k = k;
+  a.k = ksel;
   a.cap = cap;
   a.raw_stages = stages;
   a.n_tiles = n_tiles;
   a.partial = partial;
+  a.active = active;
   const size_t smem = stages * raw_stage + fixed;
-  switch (N) {
-    case 16: rc = gemm_launch_n<16>(ma, mb, a, grid, smem, stream); break;
-    case 32: rc = gemm_launch_n<32>(ma, mb, a, grid, smem, stream); break;
-    default: rc = gemm_launch_n<64>(ma, mb, a, grid, smem, stream); break;
+  if (terms == 3) {
+    switch (N) {
+      case 16: rc = gemm_launch_nt<16, 3>(ma, mb, a, grid, smem, stream); break;
+      case 32: rc = gemm_launch_nt<32, 3>(ma, mb, a, grid, smem, stream); break;
+      default: rc = gemm_launch_nt<64, 3>(ma, mb, a, grid, smem, stream); break;
+    }
+  } else {
+    switch (N) {
+      case 16: rc = gemm_launch_nt<16, 1>(ma, mb, a, grid, smem, stream); break;
+      case 32: rc = gemm_launch_nt<32, 1>(ma, mb, a, grid, smem, stream); break;
+      default: rc = gemm_launch_nt<64, 1>(ma, mb, a, grid, smem, stream); break;
+    }
   }
   if (rc) return rc;
-  select_partials_kernel<<<nq, 256, 0, stream>>>(partial, grid, k, D_dev, I_dev, id_offset);
+  select_partials_kernel<<<nq, 256, 0, stream>>>(partial, grid, ksel, D_out, I_out, id_offset, active);
   B2R_CUDA(cudaGetLastError());
-  *launches += 3;
+  return B2R_OK;
+}
+
+bool gemm_path_supported(int d, int k) { return d % kSlabK == 0 && d >= kSlabK && k <= 128; }
+
+// largest batch one pass can take for this k (candidate lists are capped at 64 KiB of shared memory)
+int gemm_max_batch(int k) {
+  const int kp = std::max(64, 2 * k);               // candidates of the approximate pass
+  const int cap = pow2_ge_g(2 * std::min(kp, 128));
+  int n = 64;
+  while (n > 16 && static_cast<size_t>(n) * cap * 8 > 64 * 1024) n >>= 1;
+  return n;
+}
+
+int gemm_max_row_norm2(const float* rows, long long n, int d, float* out_dev, cudaStream_t stream) {
+  B2R_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(float), stream));
+  max_row_norm2_kernel<<<148 * 8, 256, 0, stream>>>(rows, n, d, out_dev);
+  B2R_CUDA(cudaGetLastError());
+  return B2R_OK;
+}
+
+// Scores `nq` (<= gemm_max_batch(k)) queries against the whole shard.  scratch: device buffer of
+// kGemmScratchBytes (hi/lo queries, candidate lists, redo flags); partial: 64 * grid * 128 keys.
+int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
+                      long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial,
+                      const float* max_norm2_dev, int num_sms, cudaStream_t stream, int* launches) {
+  float* bsplit = reinterpret_cast<float*>(scratch);
+  unsigned char* extra = scratch + static_cast<size_t>(2) * 64 * 16384 * sizeof(float);
+  float* Dp = reinterpret_cast<float*>(extra);                         // [64][128]
+  long long* Ip = reinterpret_cast<long long*>(extra + 64 * 128 * 4);  // [64][128]
+  u32* redo = reinterpret_cast<u32*>(extra + 64 * 128 * 12);           // [64]
+  const int mode = tunable("gemm.mode");  // 0/1: approximate pass + exact rescoring (+ verified fallback); 3: 3xTF32 only
+  int rc;
+  if (mode == 3 || k > 64) {
+    rc = gemm_scan(rows, n, d, q_dev, nq, k, 3, nullptr, D_dev, I_dev, id_offset, bsplit, partial, num_sms, stream);
+    if (rc) return rc;
+    *launches += 3;
+    return B2R_OK;
+  }
+  const int kp = std::min(128, std::max(64, 2 * k));
+  rc = gemm_scan(rows, n, d, q_dev, nq, kp, 1, nullptr, Dp, Ip, 0, bsplit, partial, num_sms, stream);
+  if (rc) return rc;
+  gemm_rescore_kernel<<<nq, 256, 0, stream>>>(rows, d, q_dev, Dp, Ip, kp, k, max_norm2_dev, D_dev, I_dev, id_offset, redo);
+  B2R_CUDA(cudaGetLastError());
+  *launches += 4;
+  if (!tunable("gemm.no_verify")) {
+    // queries whose candidate set could not be proven complete are redone with 3xTF32 accuracy;
+    // the kernels exit at once when no flag is set
+    rc = gemm_scan(rows, n, d, q_dev, nq, k, 3, redo, D_dev, I_dev, id_offset, bsplit, partial, num_sms, stream);
+    if (rc) return rc;
+    *launches += 3;
+  }
   return B2R_OK;
 }
 

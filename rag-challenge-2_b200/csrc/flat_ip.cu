@@ -395,15 +395,18 @@ struct Workspace {
 };
 
 static const size_t kPartialBytes = static_cast<size_t>(kMaxNQ) * kMaxGrid * B2R_MAX_K * sizeof(u64);
-static const size_t kBsplitBytes = static_cast<size_t>(2) * 64 * 16384 * sizeof(float);  // tensor-core path: hi/lo queries
+// tensor-core path scratch: hi/lo queries + candidate lists [64][128] (score, id) + redo flags + max row norm
+static const size_t kBsplitBytes = static_cast<size_t>(2) * 64 * 16384 * sizeof(float) + 64 * 128 * 12 + 1024;
 
 static size_t workspace_bytes() { return 256 + kPartialBytes + kBsplitBytes; }
 
 // csrc/flat_gemm.cu
 bool gemm_path_supported(int d, int k);
+int gemm_max_batch(int k);
+int gemm_max_row_norm2(const float* rows, long long n, int d, float* out_dev, cudaStream_t stream);
 int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
-                      long long* I_dev, long long id_offset, float* bsplit, u64* partial, int num_sms,
-                      cudaStream_t stream, int* launches);
+                      long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial,
+                      const float* max_norm2_dev, int num_sms, cudaStream_t stream, int* launches);
 
 struct HostCtx {
   cudaStream_t stream = nullptr;
@@ -431,6 +434,8 @@ struct b2r_flat {
   std::map<cudaStream_t, Workspace> stream_ws;
   std::vector<HostCtx*> free_ctx;
   std::vector<HostCtx*> all_ctx;
+  float* max_norm2 = nullptr;      // device scalar: max |row|^2 (error bound of the tf32 candidate pass)
+  long long max_norm2_rows = -1;   // number of rows it was computed for
 };
 
 namespace b2r {
@@ -448,6 +453,20 @@ static int get_workspace(b2r_flat* h, cudaStream_t stream, Workspace* out) {
   B2R_CUDA(cudaMemsetAsync(ws.base, 0, 256, stream));
   h->stream_ws[stream] = ws;
   *out = ws;
+  return B2R_OK;
+}
+
+// max |row|^2 over the shard, computed once per index size on the searching stream
+static int ensure_row_norm(b2r_flat* h, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->max_norm2) B2R_CUDA(cudaMalloc(&h->max_norm2, 256));
+  if (h->max_norm2_rows != h->n) {
+    int rc = gemm_max_row_norm2(h->rows, h->n, h->d, h->max_norm2, stream);
+    if (rc) return rc;
+    // later searches may run on other streams: make the value visible before anyone else uses it
+    B2R_CUDA(cudaStreamSynchronize(stream));
+    h->max_norm2_rows = h->n;
+  }
   return B2R_OK;
 }
 
@@ -624,15 +643,21 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
   if (gemm_min <= 0) gemm_min = 5;
   int gemm_max = tunable("flat.gemm_max_n");
   if (gemm_max <= 0 || gemm_max > 64) gemm_max = 64;
-  while (nq - done >= gemm_min && gemm_path_supported(h->d, k) && !tunable("flat.force_generic") &&
-         !tunable("flat.no_gemm") && h->n >= 128) {
+  const bool use_gemm = nq >= gemm_min && gemm_path_supported(h->d, k) && !tunable("flat.force_generic") &&
+                        !tunable("flat.no_gemm") && h->n >= 128;
+  if (use_gemm) {
+    gemm_max = std::min(gemm_max, gemm_max_batch(k));
+    rc = ensure_row_norm(h, stream);
+    if (rc) return rc;
+  }
+  while (use_gemm && nq - done >= gemm_min) {
     const int chunk = std::min(nq - done, gemm_max);
     int launches = 0;
     rc = gemm_search_chunk(h->rows, h->n, h->d, q_dev + static_cast<size_t>(done) * h->d, chunk, k,
                            D_dev + static_cast<size_t>(done) * k,
                            reinterpret_cast<long long*>(I_dev) + static_cast<size_t>(done) * k, id_offset,
-                           reinterpret_cast<float*>(ws.base + 256 + kPartialBytes),
-                           reinterpret_cast<u64*>(ws.base + 256), h->num_sms, stream, &launches);
+                           ws.base + 256 + kPartialBytes, reinterpret_cast<u64*>(ws.base + 256), h->max_norm2,
+                           h->num_sms, stream, &launches);
     if (rc) return rc;
     launch_counter() += launches;
     done += chunk;
@@ -912,6 +937,7 @@ int b2r_flat_destroy(b2r_flat* h) {
     if (kv.second.base) cudaFree(kv.second.base);
   }
   if (h->owns && h->rows) cudaFree(h->rows);
+  if (h->max_norm2) cudaFree(h->max_norm2);
   delete h;
   return B2R_OK;
 }

@@ -100,3 +100,52 @@ def test_ties_and_matches_simt_path(b2r):
         _lib.tunable_set("flat.no_gemm", 0)
     assert np.array_equal(I1, I2)
     assert np.allclose(D1, D2, rtol=1e-5, atol=1e-6)
+
+
+def test_3xtf32_mode(b2r):
+    """gemm.mode = 3: the 3xTF32 kernel alone (the redo path of the default mode, and k > 64)."""
+    from rag_challenge_2_b200 import _lib
+
+    xb = unit_rows(25000, 1024, 51)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    _lib.tunable_set("gemm.mode", 3)
+    try:
+        for nq in (7, 40, 64):
+            check(index, xb, queries_for(xb, nq, 52 + nq), 30)
+    finally:
+        _lib.tunable_set("gemm.mode", 0)
+
+
+def test_unprovable_queries_are_redone(b2r):
+    """Thousands of rows within 1e-4 of each other around the k-th score: the tf32 candidate set
+    cannot be proven complete, so those queries must go through the 3xTF32 redo pass and still
+    satisfy the parity bar; with verification disabled the approximate pass alone may miss rows."""
+    rng = np.random.default_rng(53)
+    base = unit_rows(8, 1024, 54)
+    reps = 4000
+    xb = np.repeat(base, reps, axis=0) + 1e-4 * rng.standard_normal((8 * reps, 1024)).astype(np.float32) / 32.0
+    xb = np.concatenate([xb, unit_rows(8000, 1024, 55)]).astype(np.float32)
+    xq = np.concatenate([base, unit_rows(4, 1024, 56)])          # 8 "crowded" queries + 4 ordinary ones
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    check(index, xb, xq, 30)
+
+
+def test_exact_scores_equal_simt_scores(b2r):
+    """Rescoring uses the SIMT scan's arithmetic: for well-separated data the tensor-core path returns
+    bit-identical scores and ids to the nq <= 4 path."""
+    from rag_challenge_2_b200 import _lib
+
+    xb = unit_rows(40000, 1024, 57)
+    xq = queries_for(xb, 16, 58)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    D1, I1 = index.search(xq, 30)
+    _lib.tunable_set("flat.no_gemm", 1)
+    try:
+        D2, I2 = index.search(xq, 30)
+    finally:
+        _lib.tunable_set("flat.no_gemm", 0)
+    assert np.array_equal(I1, I2)
+    assert np.array_equal(D1, D2)
