@@ -424,10 +424,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         if (pend) *flag = 1u;
         named_bar_sync(1, 128);
-        // compaction: a list that is more than half full (or overflowed) is cut back to its best k
+        // compaction: a list filled past the midpoint between k and its capacity (or overflowed) is
+        // cut back to its best k, which also raises the query's threshold
         for (int c = ew; c < a.nq; c += 4) {
           const u32 nc = cnt_s[c];
-          if (nc > static_cast<u32>(cap / 2)) {
+          if (nc >= static_cast<u32>((k + cap + 1) / 2)) {
             u64* list = lists + static_cast<size_t>(c) * cap;
             const int valid = nc < static_cast<u32>(cap) ? static_cast<int>(nc) : cap;
             for (int i = valid + lane; i < cap; i += 32) list[i] = 0;
