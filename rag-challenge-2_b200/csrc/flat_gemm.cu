@@ -178,7 +178,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  constexpr u32 kABytes = kTileM * kSlabK * 4;            // 16 KiB
+  // TERMS == 1 scores 256 rows (two M = 128 MMAs) per query slab, halving the L2 traffic of the
+  // re-fetched queries; TERMS == 3 keeps 128 (its shared memory holds the lo ring instead)
+  constexpr int kSub = TERMS == 3 ? 1 : 2;                // 128-row sub-tiles per tile
+  constexpr int kAcc = TERMS == 3 ? 4 : 2;                // TMEM accumulators per sub-tile
+  constexpr u32 kSubBytes = kTileM * kSlabK * 4;          // 16 KiB: one sub-tile slab
+  constexpr u32 kABytes = kSub * kSubBytes;
   constexpr u32 kBBytes = N * kSlabK * 4;                 // N * 128 B
   constexpr u32 kRawStage = kABytes + (TERMS == 3 ? 2 : 1) * kBBytes;  // A (raw -> hi) | B[_hi] | (B_lo)
   constexpr int kLo = TERMS == 3 ? kLoStages : 0;
@@ -186,13 +191,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   // with its length and with the size of the running sum.  Per tile we therefore keep FOUR
   // accumulators of N columns: hi*hi split 2-way over K (even / odd slabs) and the two small
   // cross terms likewise; the epilogue adds them in fp32 (round-to-nearest).  x2 tiles in flight.
-  constexpr u32 kTmemCols = 8 * N;                        // 128 / 256 / 512 columns for N = 16 / 32 / 64
+  constexpr u32 kTileCols = kSub * kAcc * N;              // TMEM columns of one tile (= 4N in both modes)
+  constexpr u32 kTmemCols = 2 * kTileCols;                // 128 / 256 / 512 columns for N = 16 / 32 / 64
   const int R = a.raw_stages;
   const int n_slabs = a.d / kSlabK;
 
   unsigned char* raw_ring = smem_raw;                                  // R stages
   unsigned char* lo_ring = raw_ring + static_cast<size_t>(R) * kRawStage;  // kLoStages x 16 KiB
-  u64* bars = reinterpret_cast<u64*>(lo_ring + kLo * kABytes);
+  u64* bars = reinterpret_cast<u64*>(lo_ring + kLo * kSubBytes);
   u64* full = bars;                    // [R]   TMA landed
   u64* empty = full + R;               // [R]   MMAs that read the raw stage are done
   u64* xf_full = empty + R;            // [kLoStages] hi/lo written
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       int s = 0;
       u32 ph = 0;
       for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int row0 = static_cast<int>(t * kTileM);
+        const int row0 = static_cast<int>(t * (kTileM * kSub));
         for (int sl = 0; sl < n_slabs; ++sl) {
           mbar_wait(&empty[s], ph ^ 1u);
           unsigned char* st = raw_ring + static_cast<size_t>(s) * kRawStage;
@@ -272,10 +278,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         mbar_wait(&tm_empty[buf], ph_buf[buf] ^ 1u);  // epilogue drained this accumulator tile
         tc_fence_after();
-        const u32 tile_d = tmem_base + static_cast<u32>(buf * 4 * N);
+        const u32 tile_d = tmem_base + static_cast<u32>(buf) * kTileCols;
         for (int sl = 0; sl < n_slabs; ++sl) {
           const u32 d_main = tile_d + static_cast<u32>((sl & 1) * N);
-          const u32 d_small = tile_d + static_cast<u32>((2 + (sl & 1)) * N);
+          const u32 d_small = tile_d + static_cast<u32>((2 + (sl & 1)) * N);  // TERMS == 3 only
+          (void)d_small;
           const bool first = sl < 2;  // first slab of this K-split: overwrite instead of accumulate
           if constexpr (TERMS == 3) {
             mbar_wait(&xf_full[l], ph_l);
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           const u64 d_bhi = make_kmajor_sw128_desc(st + kABytes);
           if constexpr (TERMS == 3) {
             const u64 d_blo = make_kmajor_sw128_desc(st + kABytes + kBBytes);
-            const u64 d_alo = make_kmajor_sw128_desc(smem_u32(lo_ring + static_cast<size_t>(l) * kABytes));
+            const u64 d_alo = make_kmajor_sw128_desc(smem_u32(lo_ring + static_cast<size_t>(l) * kSubBytes));
 #pragma unroll
             for (int kk = 0; kk < kSlabK / 8; ++kk) {
               const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);  // 32 bytes per k-step inside the swizzle row
@@ -305,9 +312,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             }
           } else {
 #pragma unroll
-            for (int kk = 0; kk < kSlabK / 8; ++kk) {
-              const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);
-              tc_mma_tf32(d_main, d_ahi + adv, d_bhi + adv, idesc, (first && kk == 0) ? 0u : 1u);
+            for (int sub = 0; sub < kSub; ++sub) {
+              const u64 d_a = make_kmajor_sw128_desc(st + sub * kSubBytes);
+              const u32 d_acc = d_main + static_cast<u32>(sub * kAcc * N);
+#pragma unroll
+              for (int kk = 0; kk < kSlabK / 8; ++kk) {
+                const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);
+                tc_mma_tf32(d_acc, d_a + adv, d_bhi + adv, idesc, (first && kk == 0) ? 0u : 1u);
+              }
             }
             tc_commit(&empty[s]);
           }
@@ -332,9 +344,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         mbar_wait(&full[s], ph_s);
         mbar_wait(&xf_empty[l], ph_l ^ 1u);
         float4* hi = reinterpret_cast<float4*>(raw_ring + static_cast<size_t>(s) * kRawStage);
-        float4* lo = reinterpret_cast<float4*>(lo_ring + static_cast<size_t>(l) * kABytes);
+        float4* lo = reinterpret_cast<float4*>(lo_ring + static_cast<size_t>(l) * kSubBytes);
 #pragma unroll
-        for (int i = 0; i < static_cast<int>(kABytes / 16 / 128); ++i) {
+        for (int i = 0; i < static_cast<int>(kSubBytes / 16 / 128); ++i) {
           const int idx = xt + i * 128;
           const float4 x = hi[idx];
           float4 h, r;
@@ -375,8 +387,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(&tm_full[buf], ph_buf[buf]);
       tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < kSub; ++sub) {
       float sc[N];
-      const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(buf * 4 * N);
+      const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(buf) * kTileCols +
+                        static_cast<u32>(sub * kAcc * N);
 #pragma unroll
       for (int c = 0; c < N; c += 16) {
         float m0[16], m1[16];
@@ -397,13 +412,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           for (int i = 0; i < 16; ++i) sc[c + i] = (n_slabs > 1) ? m0[i] + m1[i] : m0[i];
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tm_empty[buf]);
-      ph_buf[buf] ^= 1u;
-      buf ^= 1;
+      if (sub == kSub - 1) {  // last sub-tile is in registers: hand the accumulator tile back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tm_empty[buf]);
+      }
 
-      const long long row = t * kTileM + quad * 32 + lane;
+      const long long row = t * (kTileM * kSub) + sub * kTileM + quad * 32 + lane;
       u64 pend = (row < a.n) ? active_mask : 0ull;
       for (;;) {
         u32* flag = flags + (it & 1);
@@ -448,6 +463,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         ++it;
         if (!again) break;
       }
+      }  // sub-tiles
+      ph_buf[buf] ^= 1u;
+      buf ^= 1;
     }
     // per-CTA result: best k of every query's list -> global scratch
     named_bar_sync(1, 128);
@@ -622,7 +640,8 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   // candidate lists (N x cap keys) get at most 64 KiB of shared memory
   int N = nq <= 16 ? 16 : (nq <= 32 ? 32 : 64);
   if (static_cast<size_t>(N) * cap * 8 > 64 * 1024) return fail(B2R_ERR_INVALID, "gemm_scan: batch too wide for this k");
-  const long long n_tiles = (n + kTileM - 1) / kTileM;
+  const int tile_rows = terms == 3 ? kTileM : 2 * kTileM;
+  const long long n_tiles = (n + tile_rows - 1) / tile_rows;
   const int grid = static_cast<int>(std::min<long long>(n_tiles, num_sms));
   gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit, terms == 3 ? 1 : 0);
   B2R_CUDA(cudaGetLastError());
@@ -631,7 +650,7 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   if (rc) return rc;
   rc = make_map_2d(&mb, bsplit, static_cast<unsigned long long>(d), static_cast<unsigned long long>(2 * N), kSlabK, N);
   if (rc) return rc;
-  const size_t raw_stage = kTileM * kSlabK * 4 + static_cast<size_t>(terms == 3 ? 2 : 1) * N * kSlabK * 4;
+  const size_t raw_stage = static_cast<size_t>(tile_rows) * kSlabK * 4 + static_cast<size_t>(terms == 3 ? 2 : 1) * N * kSlabK * 4;
   const size_t fixed = (terms == 3 ? kLoStages : 0) * static_cast<size_t>(kTileM) * kSlabK * 4 + 64 * 8 /*barriers*/ +
                        static_cast<size_t>(N) * 12 + 32 + static_cast<size_t>(N) * cap * 8 + 1024 /*alignment slack*/;
   int stages = tunable("gemm.stages");
