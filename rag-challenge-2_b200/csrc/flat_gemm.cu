@@ -169,7 +169,7 @@ __global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, i
 // ---------------------------------------------------------------------------------------------
 // the scan
 // ---------------------------------------------------------------------------------------------
-template <int N, int TERMS>
+template <int N, int TERMS, int SUB>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     flat_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const GemmArgs a) {
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int warp = tid >> 5, lane = tid & 31;
   // TERMS == 1 scores 256 rows (two M = 128 MMAs) per query slab, halving the L2 traffic of the
   // re-fetched queries; TERMS == 3 keeps 128 (its shared memory holds the lo ring instead)
-  constexpr int kSub = TERMS == 3 ? 1 : 2;                // 128-row sub-tiles per tile
+  constexpr int kSub = SUB;                               // 128-row sub-tiles per tile (2 only with TERMS == 1)
   constexpr int kAcc = TERMS == 3 ? 4 : 2;                // TMEM accumulators per sub-tile
   constexpr u32 kSubBytes = kTileM * kSlabK * 4;          // 16 KiB: one sub-tile slab
   constexpr u32 kABytes = kSub * kSubBytes;
@@ -616,10 +616,10 @@ static int make_map_2d(CUtensorMap* map, const float* base, unsigned long long i
   return B2R_OK;
 }
 
-template <int N, int TERMS>
+template <int N, int TERMS, int SUB>
 static int gemm_launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, int grid, size_t smem,
                           cudaStream_t stream) {
-  auto kern = flat_gemm_tc_kernel<N, TERMS>;
+  auto kern = flat_gemm_tc_kernel<N, TERMS, SUB>;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<grid, kGemmThreads, smem, stream>>>(ma, mb, a);
   B2R_CUDA(cudaGetLastError());
@@ -640,7 +640,8 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   // candidate lists (N x cap keys) get at most 64 KiB of shared memory
   int N = nq <= 16 ? 16 : (nq <= 32 ? 32 : 64);
   if (static_cast<size_t>(N) * cap * 8 > 64 * 1024) return fail(B2R_ERR_INVALID, "gemm_scan: batch too wide for this k");
-  const int tile_rows = terms == 3 ? kTileM : 2 * kTileM;
+  const int sub = (terms == 1 && tunable("gemm.tile256") && n >= 256) ? 2 : 1;
+  const int tile_rows = sub * kTileM;
   const long long n_tiles = (n + tile_rows - 1) / tile_rows;
   const int grid = static_cast<int>(std::min<long long>(n_tiles, num_sms));
   gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit, terms == 3 ? 1 : 0);
@@ -671,15 +672,21 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   const size_t smem = stages * raw_stage + fixed;
   if (terms == 3) {
     switch (N) {
-      case 16: rc = gemm_launch_nt<16, 3>(ma, mb, a, grid, smem, stream); break;
-      case 32: rc = gemm_launch_nt<32, 3>(ma, mb, a, grid, smem, stream); break;
-      default: rc = gemm_launch_nt<64, 3>(ma, mb, a, grid, smem, stream); break;
+      case 16: rc = gemm_launch_nt<16, 3, 1>(ma, mb, a, grid, smem, stream); break;
+      case 32: rc = gemm_launch_nt<32, 3, 1>(ma, mb, a, grid, smem, stream); break;
+      default: rc = gemm_launch_nt<64, 3, 1>(ma, mb, a, grid, smem, stream); break;
+    }
+  } else if (sub == 2) {
+    switch (N) {
+      case 16: rc = gemm_launch_nt<16, 1, 2>(ma, mb, a, grid, smem, stream); break;
+      case 32: rc = gemm_launch_nt<32, 1, 2>(ma, mb, a, grid, smem, stream); break;
+      default: rc = gemm_launch_nt<64, 1, 2>(ma, mb, a, grid, smem, stream); break;
     }
   } else {
     switch (N) {
-      case 16: rc = gemm_launch_nt<16, 1>(ma, mb, a, grid, smem, stream); break;
-      case 32: rc = gemm_launch_nt<32, 1>(ma, mb, a, grid, smem, stream); break;
-      default: rc = gemm_launch_nt<64, 1>(ma, mb, a, grid, smem, stream); break;
+      case 16: rc = gemm_launch_nt<16, 1, 1>(ma, mb, a, grid, smem, stream); break;
+      case 32: rc = gemm_launch_nt<32, 1, 1>(ma, mb, a, grid, smem, stream); break;
+      default: rc = gemm_launch_nt<64, 1, 1>(ma, mb, a, grid, smem, stream); break;
     }
   }
   if (rc) return rc;

@@ -644,7 +644,7 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
   int gemm_max = tunable("flat.gemm_max_n");
   if (gemm_max <= 0 || gemm_max > 64) gemm_max = 64;
   const bool use_gemm = nq >= gemm_min && gemm_path_supported(h->d, k) && !tunable("flat.force_generic") &&
-                        !tunable("flat.no_gemm") && h->n >= 256;
+                        !tunable("flat.no_gemm") && h->n >= 128;
   if (use_gemm) {
     gemm_max = std::min(gemm_max, gemm_max_batch(k));
     rc = ensure_row_norm(h, stream);
