@@ -35,6 +35,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdio.h>
+
 #include <algorithm>
 
 #include "b2r_common.cuh"
@@ -123,6 +125,28 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // the slow conversion pipe): add half an ulp of the 10-bit mantissa to the magnitude, clear 13 bits
 __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+// mbarrier wait with a watchdog: a pipeline bug shows up as a trap with the barrier's tag, not a hang
+__device__ __forceinline__ void mbar_wait_tag(u64* bar, u32 parity, int tag) {
+  const u32 addr = smem_u32(bar);
+  for (u32 spins = 0;; ++spins) {
+    u32 done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins == (1u << 26)) {
+      printf("b2r flat_gemm: barrier wait stuck: tag %d block %d thread %d parity %u\n", tag, blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -254,10 +278,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int row0 = static_cast<int>(t * (kTileM * kSub));
         for (int sl = 0; sl < n_slabs; ++sl) {
-          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_wait_tag(&empty[s], ph ^ 1u, 100 + s);
           unsigned char* st = raw_ring + static_cast<size_t>(s) * kRawStage;
           mbar_arrive_expect_tx(&full[s], kRawStage);
-          tma_load_2d(st, &map_a, sl * kSlabK, row0, &full[s], pol_a);
+#pragma unroll
+          for (int sub = 0; sub < kSub; ++sub) {
+            tma_load_2d(st + sub * kSubBytes, &map_a, sl * kSlabK, row0 + sub * kTileM, &full[s], pol_a);
+          }
           tma_load_2d(st + kABytes, &map_b, sl * kSlabK, 0, &full[s], pol_b);
           if constexpr (TERMS == 3) tma_load_2d(st + kABytes + kBBytes, &map_b, sl * kSlabK, N, &full[s], pol_b);
           if (++s == R) {
@@ -276,7 +303,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       (void)l;
       (void)ph_l;
       for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        mbar_wait(&tm_empty[buf], ph_buf[buf] ^ 1u);  // epilogue drained this accumulator tile
+        mbar_wait_tag(&tm_empty[buf], ph_buf[buf] ^ 1u, 200 + buf);  // epilogue drained this accumulator tile
         tc_fence_after();
         const u32 tile_d = tmem_base + static_cast<u32>(buf) * kTileCols;
         for (int sl = 0; sl < n_slabs; ++sl) {
@@ -285,9 +312,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           (void)d_small;
           const bool first = sl < 2;  // first slab of this K-split: overwrite instead of accumulate
           if constexpr (TERMS == 3) {
-            mbar_wait(&xf_full[l], ph_l);
+            mbar_wait_tag(&xf_full[l], ph_l, 300 + l);
           } else {
-            mbar_wait(&full[s], ph_s);
+            mbar_wait_tag(&full[s], ph_s, 400 + s);
           }
           tc_fence_after();
           const u32 st = smem_u32(raw_ring + static_cast<size_t>(s) * kRawStage);
@@ -341,8 +368,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     u32 ph_s = 0, ph_l = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       for (int sl = 0; sl < n_slabs; ++sl) {
-        mbar_wait(&full[s], ph_s);
-        mbar_wait(&xf_empty[l], ph_l ^ 1u);
+        mbar_wait_tag(&full[s], ph_s, 500 + s);
+        mbar_wait_tag(&xf_empty[l], ph_l ^ 1u, 600 + l);
         float4* hi = reinterpret_cast<float4*>(raw_ring + static_cast<size_t>(s) * kRawStage);
         float4* lo = reinterpret_cast<float4*>(lo_ring + static_cast<size_t>(l) * kSubBytes);
 #pragma unroll
@@ -385,7 +412,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int buf = 0, it = 0;
     u32 ph_buf[2] = {0, 0};
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      mbar_wait(&tm_full[buf], ph_buf[buf]);
+      mbar_wait_tag(&tm_full[buf], ph_buf[buf], 700 + buf);
       tc_fence_after();
 #pragma unroll 1
       for (int sub = 0; sub < kSub; ++sub) {
