@@ -148,12 +148,15 @@ int b2r_hybrid_fuse_dev(const float* D, const int64_t* I, const double* S, const
 /* ---- N x N cosine analysis ---------------------------------------------------------------- */
 /* compute_cosine_similarity_matrix + off-diagonal statistics
  *                             semantic_similarity_analysis/generate_similarity_matrix.py:84-98,162-171
- * rows_dev[n,d] float32.  Never materialises the n x n matrix: streams tiles of
- * S = Xn Xn^T (Xn = X / (|X| + 1e-8), diagonal forced to 1, clipped to [-1,1]) and reduces them.
+ * rows_dev[n,d] float32 (d a multiple of 32).  Never materialises the n x n matrix: streams tiles of
+ * S = Xn Xn^T (Xn = X / (|X| + 1e-8), clipped to [-1,1]) through the tensor cores (3xTF32) and
+ * reduces them.  Uses the symmetry of S: the pairs (i, j) with i < j and j in [row_begin, row_end)
+ * are visited once and counted twice, so ranges covering [0, n) add up to all off-diagonal entries
+ * (the unit of sharding across GPUs; work grows with j).
  * stats[0..5] = off-diagonal sum, sum of squares, min, max, count, (reserved);
- * hist[n_bins] counts off-diagonal entries over [-1,1] (for the median);
- * if k > 0: topk_S[n,k] / topk_I[n,k] per-row nearest neighbours (self excluded).
- * Rows [row_begin,row_end) of S are processed (row-block sharding across GPUs). */
+ * hist[n_bins] (n_bins <= 8192) counts the off-diagonal entries over [-1,1] (for the median).
+ * Synchronises `stream` before returning (scratch is freed).  k must be 0: per-row nearest
+ * neighbours are b2r_flat_search_dev on the normalised rows. */
 int b2r_cosine_stats_dev(const float* rows_dev, int64_t n, int d, int64_t row_begin, int64_t row_end,
                          double* stats_dev, unsigned long long* hist_dev, int n_bins, int k,
                          float* topk_S_dev, int64_t* topk_I_dev, int device, void* stream);

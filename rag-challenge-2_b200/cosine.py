@@ -1,0 +1,103 @@
+"""N x N cosine-similarity analysis on the GPU — the arithmetic of
+semantic_similarity_analysis/generate_similarity_matrix.py (compute_cosine_similarity_matrix :66-100
+and the off-diagonal statistics of generate_heatmap :162-171) without materialising the matrix.
+
+The reference normalises the rows (X / (|X| + 1e-8)), forms S = Xn Xn^T with numpy (160 GB at
+N = 200k), forces the diagonal to 1, clips to [-1, 1] and takes mean / median / std / max / min of
+the off-diagonal entries.  Here the tiles of S are produced by the tensor-core kernel (3xTF32,
+csrc/flat_gemm.cu, STATS epilogue) and reduced on the fly; the median comes from a histogram.
+Per-row nearest neighbours (the heat-map's structure) are the batched exact search on Xn.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+N_BINS = 8192
+
+
+def cosine_stats(rows, col_begin=0, col_end=None, n_bins=N_BINS, finalize=True):
+    """rows: float32 CUDA tensor [n, d] (or a FlatIPIndex's adopted tensor).  Returns the statistics
+    dictionary of the reference (avg / median / std / max / min similarity) for the pairs (i, j),
+    i != j; with a column range, the partial sums of that shard (finalize=False returns raw
+    accumulators + histogram for an all-reduce across GPUs)."""
+    import torch
+
+    if not (rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous() and rows.dim() == 2):
+        raise ValueError("cosine_stats needs a contiguous float32 CUDA tensor [n, d]")
+    n, d = int(rows.shape[0]), int(rows.shape[1])
+    col_end = n if col_end is None else int(col_end)
+    stats = torch.zeros(6, dtype=torch.float64, device=rows.device)
+    hist = torch.zeros(n_bins, dtype=torch.int64, device=rows.device)
+    stream = torch.cuda.current_stream(rows.device).cuda_stream
+    lib = _lib.load()
+    _lib.check(lib.b2r_cosine_stats_dev(C.c_void_p(rows.data_ptr()), n, d, int(col_begin), col_end,
+                                        C.c_void_p(stats.data_ptr()), C.c_void_p(hist.data_ptr()), int(n_bins), 0,
+                                        None, None, rows.device.index or 0, C.c_void_p(stream)))
+    if not finalize:
+        return stats, hist
+    return finalize_stats(stats.cpu().numpy(), hist.cpu().numpy())
+
+
+def finalize_stats(stats, hist):
+    """[sum, sumsq, min, max, count] + histogram -> the reference's statistics (generate_similarity_matrix.py:165-171)."""
+    total, sumsq, mn, mx, count = (float(stats[i]) for i in range(5))
+    if count <= 0:
+        raise ValueError("no off-diagonal entries")
+    mean = total / count
+    var = max(0.0, sumsq / count - mean * mean)  # np.std: population standard deviation
+    return {
+        "avg_similarity": mean,
+        "median_similarity": histogram_median(np.asarray(hist, dtype=np.float64), count),
+        "std_similarity": var ** 0.5,
+        "max_similarity": mx,
+        "min_similarity": mn,
+        "count": int(round(count)),
+    }
+
+
+def histogram_median(hist, count):
+    """Median of `count` values from equal-width bins over [-1, 1], linear inside the median bin.
+    np.median averages the two middle order statistics for an even count; both lie in (or next to)
+    the same bin, so the interpolated midpoint is within one bin width (2 / n_bins) of it."""
+    n_bins = hist.shape[0]
+    width = 2.0 / n_bins
+    cum = np.cumsum(hist)
+    target = 0.5 * count
+    b = int(np.searchsorted(cum, target, side="left"))
+    b = min(b, n_bins - 1)
+    before = cum[b - 1] if b > 0 else 0.0
+    inside = hist[b] if hist[b] > 0 else 1.0
+    return -1.0 + width * (b + (target - before) / inside)
+
+
+def cosine_topk(rows, k, batch=4096):
+    """Per-row k nearest neighbours by cosine similarity (self excluded): exact batched search on the
+    normalised rows.  Returns CUDA tensors (S float32 [n, k], I int64 [n, k])."""
+    import torch
+
+    from .flat_index import FlatIPIndex
+
+    n = rows.shape[0]
+    norms = rows.norm(dim=1, keepdim=True)
+    xn = (rows / (norms + 1e-8)).contiguous()
+    index = FlatIPIndex.from_device_tensor(xn)
+    kk = min(k + 1, n)
+    S = torch.empty((n, k), dtype=torch.float32, device=rows.device)
+    I = torch.empty((n, k), dtype=torch.int64, device=rows.device)
+    for lo in range(0, n, batch):
+        hi = min(n, lo + batch)
+        D, J = index.search_dev(xn[lo:hi].contiguous(), kk)
+        # drop the row itself (an exact duplicate with a lower id may rank above it: drop by id)
+        self_col = (J == torch.arange(lo, hi, device=rows.device).unsqueeze(1))
+        has_self = self_col.any(dim=1, keepdim=True)
+        drop = torch.where(has_self, self_col.float().argmax(dim=1, keepdim=True),
+                           torch.full((hi - lo, 1), kk - 1, device=rows.device, dtype=torch.int64))
+        keep = torch.ones_like(J, dtype=torch.bool).scatter_(1, drop, False)
+        S[lo:hi, : kk - 1] = D[keep].view(hi - lo, kk - 1)
+        I[lo:hi, : kk - 1] = J[keep].view(hi - lo, kk - 1)
+        if kk - 1 < k:
+            S[lo:hi, kk - 1:] = -3.4028235e38
+            I[lo:hi, kk - 1:] = -1
+    return S, I

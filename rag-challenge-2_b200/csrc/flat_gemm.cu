@@ -57,6 +57,12 @@ struct GemmArgs {
   long long n_tiles;
   u64* partial;        // [N][gridDim.x][k]
   const u32* active;   // optional per-query flags (device); NULL = all queries active
+  // STATS epilogue (N x N cosine analysis): the "queries" are rows [col0, col0 + N) of the same matrix
+  long long col0;
+  double* stats;       // [0] sum, [1] sum of squares, [2] count   (pairs i < j, each once)
+  u32* minmax;         // [0] min, [1] max as ordered float keys (atomicMin / atomicMax)
+  u64* hist;           // [n_bins] counts over [-1, 1]
+  int n_bins;
 };
 
 // ---------------- PTX wrappers specific to this kernel ----------------
@@ -193,7 +199,7 @@ __global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, i
 // ---------------------------------------------------------------------------------------------
 // the scan
 // ---------------------------------------------------------------------------------------------
-template <int N, int TERMS, int SUB>
+template <int N, int TERMS, int SUB, bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     flat_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const GemmArgs a) {
@@ -255,6 +261,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     cnt_s[i] = 0;
   }
   if (tid < 2) flags[tid] = 0;
+  if constexpr (STATS) {
+    u32* hist_s = reinterpret_cast<u32*>(lists);  // the candidate-list area holds the CTA's histogram
+    for (int i = tid; i < a.n_bins; i += blockDim.x) hist_s[i] = 0;
+  }
   if (warp == 1) tc_alloc(tmem_slot, kTmemCols);
   // queries this launch has to answer; none (all flags clear) -> skip the scan entirely
   u64 active_mask = (a.nq >= 64) ? ~0ull : ((1ull << a.nq) - 1ull);
@@ -411,6 +421,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int cap = a.cap, k = a.k;
     int buf = 0, it = 0;
     u32 ph_buf[2] = {0, 0};
+    double st_sum = 0.0, st_sq = 0.0;
+    unsigned long long st_cnt = 0;
+    float st_min = 3.4028235e38f, st_max = -3.4028235e38f;
+    (void)st_sum; (void)st_sq; (void)st_cnt; (void)st_min; (void)st_max;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait_tag(&tm_full[buf], ph_buf[buf], 700 + buf);
       tc_fence_after();
@@ -446,6 +460,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
 
       const long long row = t * (kTileM * kSub) + sub * kTileM + quad * 32 + lane;
+      if constexpr (STATS) {
+        // cosine statistics over the pairs (row, col) with row < col; S = clip(Xn Xn^T, -1, 1)
+        // (generate_similarity_matrix.py:90-98); the diagonal is excluded (:162-163)
+        u32* hist_s = reinterpret_cast<u32*>(lists);
+        const float scale = 0.5f * static_cast<float>(a.n_bins);
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          const long long col = a.col0 + c;
+          if (row < a.n && col < a.n && row < col) {
+            const float v = fminf(1.0f, fmaxf(-1.0f, sc[c]));
+            st_sum += static_cast<double>(v);
+            st_sq += static_cast<double>(v) * static_cast<double>(v);
+            st_min = fminf(st_min, v);
+            st_max = fmaxf(st_max, v);
+            ++st_cnt;
+            int bin = static_cast<int>((v + 1.0f) * scale);
+            bin = bin >= a.n_bins ? a.n_bins - 1 : bin;
+            atomicAdd(&hist_s[bin], 1u);
+          }
+        }
+        continue;
+      }
       u64 pend = (row < a.n) ? active_mask : 0ull;
       for (;;) {
         u32* flag = flags + (it & 1);
@@ -496,7 +532,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     // per-CTA result: best k of every query's list -> global scratch
     named_bar_sync(1, 128);
-    for (int c = ew; c < a.nq; c += 4) {
+    if constexpr (STATS) {
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        st_sum += __shfl_xor_sync(0xffffffffu, st_sum, m);
+        st_sq += __shfl_xor_sync(0xffffffffu, st_sq, m);
+        st_cnt += __shfl_xor_sync(0xffffffffu, st_cnt, m);
+        st_min = fminf(st_min, __shfl_xor_sync(0xffffffffu, st_min, m));
+        st_max = fmaxf(st_max, __shfl_xor_sync(0xffffffffu, st_max, m));
+      }
+      if (lane == 0 && st_cnt) {
+        atomicAdd(a.stats + 0, st_sum);
+        atomicAdd(a.stats + 1, st_sq);
+        atomicAdd(a.stats + 2, static_cast<double>(st_cnt));
+        atomicMin(a.minmax + 0, float_to_ordered(st_min));
+        atomicMax(a.minmax + 1, float_to_ordered(st_max));
+      }
+      const u32* hist_s = reinterpret_cast<const u32*>(lists);
+      for (int b = tid - 6 * 32; b < a.n_bins; b += 128) {
+        const u32 h = hist_s[b];
+        if (h) atomicAdd(a.hist + b, static_cast<u64>(h));
+      }
+    }
+    for (int c = ew; !STATS && c < a.nq; c += 4) {
       if (!((active_mask >> c) & 1ull)) continue;  // not this launch's query: its lists are never read
       u64* list = lists + static_cast<size_t>(c) * cap;
       const u32 nc = cnt_s[c];
@@ -643,10 +701,10 @@ static int make_map_2d(CUtensorMap* map, const float* base, unsigned long long i
   return B2R_OK;
 }
 
-template <int N, int TERMS, int SUB>
+template <int N, int TERMS, int SUB, bool STATS = false>
 static int gemm_launch_nt(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, int grid, size_t smem,
                           cudaStream_t stream) {
-  auto kern = flat_gemm_tc_kernel<N, TERMS, SUB>;
+  auto kern = flat_gemm_tc_kernel<N, TERMS, SUB, STATS>;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<grid, kGemmThreads, smem, stream>>>(ma, mb, a);
   B2R_CUDA(cudaGetLastError());
@@ -696,6 +754,11 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   a.n_tiles = n_tiles;
   a.partial = partial;
   a.active = active;
+  a.col0 = 0;
+  a.stats = nullptr;
+  a.minmax = nullptr;
+  a.hist = nullptr;
+  a.n_bins = 0;
   const size_t smem = stages * raw_stage + fixed;
   if (terms == 3) {
     switch (N) {
@@ -774,4 +837,135 @@ int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev,
   return B2R_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K5: N x N cosine analysis (semantic_similarity_analysis/generate_similarity_matrix.py:84-98,162-171)
+// ---------------------------------------------------------------------------------------------
+// Xn = X / (|X| + 1e-8), one warp per row
+__global__ void cosine_normalize_kernel(const float* __restrict__ x, long long n, int d, float* __restrict__ xn) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = gw; r < n; r += nw) {
+    const float* row = x + r * d;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc = fmaf(row[c], row[c], acc);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    const float inv = 1.0f / (sqrtf(acc) + 1e-8f);
+    for (int c = lane; c < d; c += 32) xn[r * d + c] = row[c] * inv;
+  }
+}
+
+__global__ void cosine_finalize_kernel(const double* acc, const u32* minmax, double* stats_out) {
+  // pairs were visited once (i < j); the matrix is symmetric, so sums and counts double
+  stats_out[0] = 2.0 * acc[0];
+  stats_out[1] = 2.0 * acc[1];
+  stats_out[2] = acc[2] > 0 ? static_cast<double>(ordered_to_float(minmax[0])) : 0.0;
+  stats_out[3] = acc[2] > 0 ? static_cast<double>(ordered_to_float(minmax[1])) : 0.0;
+  stats_out[4] = 2.0 * acc[2];
+  stats_out[5] = 0.0;
+}
+
+__global__ void cosine_double_hist_kernel(u64* hist, int n_bins) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_bins) hist[i] *= 2ull;
+}
+
+int cosine_stats_run(const float* rows_dev, long long n, int d, long long col_begin, long long col_end,
+                     double* stats_dev, u64* hist_dev, int n_bins, int num_sms, cudaStream_t stream) {
+  constexpr int N = 64;
+  float* xn = nullptr;
+  unsigned char* scratch = nullptr;
+  const size_t xn_bytes = static_cast<size_t>(n) * d * sizeof(float);
+  const size_t bs_bytes = static_cast<size_t>(2) * N * d * sizeof(float);
+  B2R_CUDA(cudaMalloc(&xn, xn_bytes));
+  cudaError_t e = cudaMalloc(&scratch, bs_bytes + 256);
+  if (e != cudaSuccess) {
+    cudaFree(xn);
+    return fail(B2R_ERR_NOMEM, "cosine: scratch allocation failed");
+  }
+  float* bsplit = reinterpret_cast<float*>(scratch);
+  double* acc = reinterpret_cast<double*>(scratch + bs_bytes);       // sum, sumsq, count
+  u32* minmax = reinterpret_cast<u32*>(scratch + bs_bytes + 64);
+  int rc = B2R_OK;
+  do {
+    const u32 mm_init[2] = {0xFFFFFFFFu, 0u};
+    if (cudaMemsetAsync(acc, 0, 64, stream) != cudaSuccess ||
+        cudaMemcpyAsync(minmax, mm_init, sizeof(mm_init), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+        cudaMemsetAsync(hist_dev, 0, static_cast<size_t>(n_bins) * sizeof(u64), stream) != cudaSuccess) {
+      rc = fail(B2R_ERR_CUDA, "cosine: memset failed");
+      break;
+    }
+    cosine_normalize_kernel<<<num_sms * 8, 256, 0, stream>>>(rows_dev, n, d, xn);
+    CUtensorMap ma, mb;
+    rc = make_map_2d(&ma, xn, static_cast<unsigned long long>(d), static_cast<unsigned long long>(n), kSlabK, kTileM);
+    if (rc) break;
+    rc = make_map_2d(&mb, bsplit, static_cast<unsigned long long>(d), static_cast<unsigned long long>(2 * N), kSlabK, N);
+    if (rc) break;
+    const int cap = 64;  // N * cap * 8 = 32 KiB: room for 8192 histogram bins
+    const size_t raw_stage = static_cast<size_t>(kTileM) * kSlabK * 4 + static_cast<size_t>(2) * N * kSlabK * 4;
+    const size_t fixed = kLoStages * static_cast<size_t>(kTileM) * kSlabK * 4 + 64 * 8 + static_cast<size_t>(N) * 12 + 32 +
+                         static_cast<size_t>(N) * cap * 8 + 1024;
+    int stages = 8;
+    while (stages > 2 && stages * raw_stage + fixed > 227 * 1024 - 1024) --stages;
+    const size_t smem = stages * raw_stage + fixed;
+    for (long long c0 = (col_begin / N) * N; c0 < col_end && rc == B2R_OK; c0 += N) {
+      const int ncols = static_cast<int>(std::min<long long>(N, n - c0));
+      gemm_split_queries_kernel<<<64, 256, 0, stream>>>(xn + c0 * d, ncols, N, d, bsplit, 1);
+      GemmArgs a;
+      a.n = n;
+      a.d = d;
+      a.nq = N;
+      a.k = 1;
+      a.cap = cap;
+      a.raw_stages = stages;
+      // only row tiles that contain some row i < max column of this block
+      const long long last_col = std::min<long long>(n, c0 + N) - 1;
+      a.n_tiles = last_col <= 0 ? 0 : (last_col - 1) / kTileM + 1;
+      a.partial = nullptr;
+      a.active = nullptr;
+      a.col0 = c0;
+      a.stats = acc;
+      a.minmax = minmax;
+      a.hist = hist_dev;
+      a.n_bins = n_bins;
+      if (a.n_tiles == 0) continue;
+      const int grid = static_cast<int>(std::min<long long>(a.n_tiles, num_sms));
+      rc = gemm_launch_nt<N, 3, 1, true>(ma, mb, a, grid, smem, stream);
+    }
+    if (rc) break;
+    cosine_finalize_kernel<<<1, 1, 0, stream>>>(acc, minmax, stats_dev);
+    cosine_double_hist_kernel<<<(n_bins + 255) / 256, 256, 0, stream>>>(hist_dev, n_bins);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(B2R_ERR_CUDA, "cosine: launch failed");
+  } while (0);
+  cudaStreamSynchronize(stream);  // scratch is freed below
+  cudaFree(xn);
+  cudaFree(scratch);
+  return rc;
+}
+
 }  // namespace b2r
+
+extern "C" int b2r_cosine_stats_dev(const float* rows_dev, int64_t n, int d, int64_t row_begin, int64_t row_end,
+                                    double* stats_dev, unsigned long long* hist_dev, int n_bins, int k, float* topk_S_dev,
+                                    int64_t* topk_I_dev, int device, void* stream) {
+  using namespace b2r;
+  (void)topk_S_dev;
+  (void)topk_I_dev;
+  if (!rows_dev || !stats_dev || !hist_dev) return fail(B2R_ERR_INVALID, "b2r_cosine_stats: NULL buffer");
+  if (n < 2 || d < 32 || d % 32) return fail(B2R_ERR_UNSUPPORTED, "b2r_cosine_stats: need n >= 2 and d a multiple of 32");
+  if (n > 0x7FFFFFF0LL) return fail(B2R_ERR_UNSUPPORTED, "b2r_cosine_stats: n too large");
+  if (n_bins < 2 || n_bins > 8192) return fail(B2R_ERR_INVALID, "b2r_cosine_stats: n_bins must be in [2, 8192]");
+  if (row_begin < 0 || row_end > n || row_begin >= row_end) return fail(B2R_ERR_INVALID, "b2r_cosine_stats: bad column range");
+  if (k != 0) {
+    return fail(B2R_ERR_UNSUPPORTED,
+                "b2r_cosine_stats: per-row top-k is served by b2r_flat_search_dev on the normalised rows (k must be 0 here)");
+  }
+  DeviceGuard g(device);
+  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_cosine_stats: cudaSetDevice failed");
+  cudaDeviceProp prop;
+  B2R_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(B2R_ERR_UNSUPPORTED, "libb2r is built for sm_100a (B200) only");
+  return cosine_stats_run(rows_dev, n, d, row_begin, row_end, stats_dev, reinterpret_cast<u64*>(hist_dev), n_bins,
+                          prop.multiProcessorCount, static_cast<cudaStream_t>(stream));
+}

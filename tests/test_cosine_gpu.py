@@ -1,0 +1,67 @@
+"""GPU parity: K5 N x N cosine statistics vs the numpy restatement of generate_similarity_matrix.py.
+Tolerances: mean / std / min / max 1e-5 relative (+1e-6 abs), median within 1e-4."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def compare(x, got):
+    want = oracle.cosine_stats_ref(oracle.cosine_matrix_ref(x))
+    n = x.shape[0]
+    assert got["count"] == n * (n - 1)
+    for key in ("avg_similarity", "std_similarity", "max_similarity", "min_similarity"):
+        assert abs(got[key] - want[key]) <= 1e-5 * abs(want[key]) + 2e-6, (key, got[key], want[key])
+    assert abs(got["median_similarity"] - want["median_similarity"]) <= 1e-4, (got["median_similarity"], want["median_similarity"])
+
+
+@pytest.mark.parametrize("n,d", [(2, 64), (65, 128), (130, 1024), (1000, 1024), (3001, 1024), (2500, 96)])
+def test_stats_match_reference(b2r, n, d):
+    import torch
+
+    from rag_challenge_2_b200 import cosine
+
+    rng = np.random.default_rng(n + d)
+    # un-normalised rows with very different norms, plus a shared component so the similarities
+    # are not centred on zero, plus exact duplicates (values that must clip at 1.0)
+    x = rng.standard_normal((n, d)).astype(np.float32) + 0.7 * rng.standard_normal((1, d)).astype(np.float32)
+    x *= rng.uniform(0.5, 2.0, (n, 1)).astype(np.float32)
+    if n > 10:
+        x[7] = 3.0 * x[3]
+    got = cosine.cosine_stats(torch.from_numpy(x).cuda())
+    compare(x, got)
+
+
+def test_column_shards_add_up(b2r):
+    """The multi-GPU split: column ranges reduce independently and add up to the whole matrix."""
+    import torch
+
+    from rag_challenge_2_b200 import cosine
+
+    x = np.random.default_rng(5).standard_normal((1500, 256)).astype(np.float32)
+    rows = torch.from_numpy(x).cuda()
+    parts = [cosine.cosine_stats(rows, lo, hi, finalize=False) for lo, hi in ((0, 448), (448, 1024), (1024, 1500))]
+    stats = sum(p[0].cpu().numpy()[[0, 1, 4]] for p in parts)
+    hist = sum(p[1].cpu().numpy() for p in parts)
+    mn = min(float(p[0][2]) for p in parts)
+    mx = max(float(p[0][3]) for p in parts)
+    merged = cosine.finalize_stats(np.array([stats[0], stats[1], mn, mx, stats[2], 0.0]), hist)
+    compare(x, merged)
+
+
+def test_topk_neighbours(b2r):
+    import torch
+
+    from rag_challenge_2_b200 import cosine
+
+    x = np.random.default_rng(6).standard_normal((4000, 1024)).astype(np.float32)
+    x[100] = 2.0 * x[50]                      # cosine 1.0 pair
+    S, I = cosine.cosine_topk(torch.from_numpy(x).cuda(), 10)
+    S, I = S.cpu().numpy(), I.cpu().numpy()
+    sim = oracle.cosine_matrix_ref(x).astype(np.float64)
+    np.fill_diagonal(sim, -np.inf)            # self excluded
+    assert I[50, 0] == 100 and I[100, 0] == 50
+    assert not np.any(I == np.arange(4000)[:, None])
+    oracle.assert_topk_equivalent(S, I, sim, 10, rtol=1e-5, atol=2e-6, what="cosine top-k")
