@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--cpu-docs", type=int, default=50_000, help="documents of the CPU-baseline BM25 sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run BM25 after the scan instead of under it")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU result exchange: one fused kernel over NVLink peer memory, or NCCL all-gather + merges")
     return ap.parse_args()
 
 
@@ -235,7 +237,18 @@ def run_b200(args):
     n_post, wbits = bm25.n_postings()
     del post
     torch.cuda.empty_cache()
-    index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap)
+    exchange = args.exchange
+    if world > 1 and exchange == "peer":
+        try:
+            index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap, exchange="peer")
+        except Exception as e:  # noqa: BLE001 - symmetric memory needs P2P / IPC support on the box
+            if rank == 0:
+                print(f"[bench] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+            exchange = "nccl"
+            index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap)
+    else:
+        exchange = "nccl" if world > 1 else "none"
+        index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap)
 
     # ---- queries (rank 0 decides, everyone gets the same) --------------------------------------------
     pool = max(args.pool, args.nq)
@@ -339,7 +352,7 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "collectives": int(collectives),
+            "gpu_launches": int(launches), "collectives": int(collectives), "exchange": exchange,
             "roofline": {"bound": "hbm", "kernel": "flat_scan_tma_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(hi - lo, args.dim),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,

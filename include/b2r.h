@@ -145,6 +145,18 @@ int b2r_hybrid_fuse_dev(const float* D, const int64_t* I, const double* S, const
                         int k_dense, int k_bm25, int k_out, float* F, int64_t* O,
                         unsigned char* methods, void* stream);
 
+/* Multi-GPU variant: exchange + merge + fusion in ONE kernel over NVLink peer memory (replaces the
+ * all-gather, two merges and the fusion of the NCCL path).  Every rank passes its local hits
+ * D/I/S/J[nq,k] (global ids) and the device addresses of all ranks' symmetric buffers
+ * (peer_bufs[world], each b2r_hybrid_exchange_bytes(nq_max, k_max, world) bytes, zero-initialised,
+ * mapped for peer access); `step` (>= 1) must increase by one per call, in lockstep on all ranks.
+ * The kernel stores the hits into every rank's buffer, publishes system-scope flags, waits for the
+ * peers' flags and merges + fuses; all ranks obtain the same F/O[nq,k]. */
+size_t b2r_hybrid_exchange_bytes(int nq_max, int k_max, int world);
+int b2r_hybrid_exchange_fuse_dev(const float* D, const int64_t* I, const double* S, const int64_t* J,
+                                 int nq, int k, void* const* peer_bufs, int rank, int world, int nq_max,
+                                 int k_max, uint32_t step, float* F, int64_t* O, void* stream);
+
 /* ---- N x N cosine analysis ---------------------------------------------------------------- */
 /* compute_cosine_similarity_matrix + off-diagonal statistics
  *                             semantic_similarity_analysis/generate_similarity_matrix.py:84-98,162-171

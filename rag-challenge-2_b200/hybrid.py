@@ -57,6 +57,51 @@ def hybrid_fuse(D, I, S, J, k_out, want_methods=False, stream=None):
     return (F, O, M) if want_methods else (F, O)
 
 
+def exchange_fuse(D, I, S, J, peer_ptrs, rank, world, nq_max, k_max, step, stream=None):
+    """One-kernel exchange + merge + fusion over peer memory (csrc/hybrid_fuse.cu)."""
+    import torch
+
+    lib = _lib.load()
+    nq, k = int(D.shape[0]), int(D.shape[1])
+    F = torch.empty((nq, k), dtype=torch.float32, device=D.device)
+    O = torch.empty((nq, k), dtype=torch.int64, device=D.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(D.device).cuda_stream
+    arr = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    _lib.check(lib.b2r_hybrid_exchange_fuse_dev(C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
+                                                C.c_void_p(S.data_ptr()), C.c_void_p(J.data_ptr()), nq, k, arr,
+                                                int(rank), int(world), int(nq_max), int(k_max), int(step),
+                                                C.c_void_p(F.data_ptr()), C.c_void_p(O.data_ptr()), C.c_void_p(stream)))
+    return F, O
+
+
+class PeerExchange:
+    """Symmetric buffers of all ranks (torch symmetric memory: CUDA IPC / fabric handles over NVLink)
+    for the one-kernel exchange.  Collective constructor: every rank of `group` must call it."""
+
+    def __init__(self, device, group=None, nq_max=64, k_max=128):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nq_max, self.k_max = nq_max, k_max
+        nbytes = int(_lib.load().b2r_hybrid_exchange_bytes(nq_max, k_max, self.world))
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.handle = symm.rendezvous(self.buf, group)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.step = 0
+
+    def fuse(self, D, I, S, J):
+        self.step += 1
+        return exchange_fuse(D, I, S, J, self.ptrs, self.rank, self.world, self.nq_max, self.k_max, self.step)
+
+
 class ShardedSearcher:
     """SPMD search over a row-sharded corpus.
 
@@ -83,6 +128,7 @@ class ShardedSearcher:
         self._merge = merge or merge_topk
         self._fuse = fuse or hybrid_fuse
         self.side_stream = None  # set to a torch.cuda.Stream to overlap BM25 with the dense scan
+        self.peer_exchange = None  # set to a PeerExchange to replace all-gather + merges + fusion by one kernel
         self.launches = 0      # kernels of this library enqueued by the last call
         self.collectives = 0   # collectives enqueued by the last call
 
@@ -153,6 +199,9 @@ class ShardedSearcher:
             self.launches += self._last_dense_launches()
             S, J = self.local_bm25(term_ids, term_offsets, k)
         self.launches += 1
+        if self.world_size > 1 and self.peer_exchange is not None:
+            self.launches += 1
+            return self.peer_exchange.fuse(D, I, S, J)  # exchange + merge + fusion in one kernel over NVLink
         if self.world_size > 1:
             packed = torch.stack([D.to(torch.float64).view(torch.int64), I, S.view(torch.int64), J])
             g = self._gather(packed)  # [world, 4, nq, k]
@@ -176,7 +225,7 @@ class HybridIndex:
     `flat` is a FlatIPIndex over this rank's rows, `bm25` a BM25Okapi over the same chunks (built
     with corpus-global idf / avgdl), `offset` the global id of local row 0."""
 
-    def __init__(self, flat, bm25=None, offset=0, group=None, world_size=None, overlap=True):
+    def __init__(self, flat, bm25=None, offset=0, group=None, world_size=None, overlap=True, exchange="nccl"):
         self.flat, self.bm25, self.offset = flat, bm25, int(offset)
 
         def local_dense(q, k):
@@ -193,6 +242,10 @@ class HybridIndex:
             import torch
 
             self.searcher.side_stream = torch.cuda.Stream(device=torch.device("cuda", flat.device))
+        if exchange == "peer" and self.searcher.world_size > 1 and bm25 is not None:
+            import torch
+
+            self.searcher.peer_exchange = PeerExchange(torch.device("cuda", flat.device), group)
         self._pinned = {}
 
     # resident API -----------------------------------------------------------------------------------

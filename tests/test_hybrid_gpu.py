@@ -138,3 +138,55 @@ def test_sharded_dense_and_hybrid_match_unsharded(b2r):
     # and the host-facing call agrees with the resident one
     Fh, Oh = whole.search_hybrid(q.cpu().numpy(), queries, k)
     assert np.array_equal(Oh, O0.cpu().numpy()) and np.array_equal(Fh, F0.cpu().numpy())
+
+
+@pytest.mark.parametrize("world,k,step", [(1, 30, 1), (3, 30, 2), (8, 30, 5), (8, 100, 8), (4, 7, 3)])
+def test_exchange_kernel_emulated(b2r, world, k, step):
+    """The one-kernel exchange + merge + fusion, with the other ranks emulated on one GPU: their slots
+    and flags are pre-filled in a plain buffer that stands for every rank's symmetric buffer (the
+    kernel is launched once, as rank 0, so nothing waits on another launch)."""
+    import torch
+
+    from rag_challenge_2_b200 import _lib, hybrid
+
+    nq, nq_max, k_max = 5, 8, 128
+    rng = np.random.default_rng(world * 100 + k)
+    D = -np.sort(-rng.random((world, nq, k)).astype(np.float32), axis=2)
+    S = -np.sort(-(rng.random((world, nq, k)) * 9.0), axis=2)
+    I = rng.integers(0, 5000, (world, nq, k)).astype(np.int64)
+    J = rng.integers(0, 5000, (world, nq, k)).astype(np.int64)
+    for r in range(world):                       # ids unique inside a rank's list; ragged tails
+        for q in range(nq):
+            I[r, q] = rng.choice(5000, k, replace=False) + 5000 * r
+            J[r, q] = rng.choice(5000, k, replace=False) + 5000 * r
+    I[0, 1, k // 2:] = -1
+    J[world - 1, 2, 3:] = -1
+    if world > 1:
+        J[1, 0, :5] = I[0, 0, :5]                # overlap between dense and BM25 hits
+        D[1, 3, 0] = D[0, 3, 0]                  # tie across ranks -> lower rank first
+    nbytes = int(_lib.load().b2r_hybrid_exchange_bytes(nq_max, k_max, world))
+    buf = np.zeros(nbytes, dtype=np.uint8)
+    nk = nq_max * k_max
+    slot = nk * 28
+    parity = step & 1
+    for r in range(1, world):
+        base = (parity * world + r) * slot
+        dD = buf[base: base + nk * 4].view(np.float32).reshape(nq_max, k_max)
+        dI = buf[base + nk * 4: base + nk * 12].view(np.int64).reshape(nq_max, k_max)
+        dS = buf[base + nk * 12: base + nk * 20].view(np.float64).reshape(nq_max, k_max)
+        dJ = buf[base + nk * 20: base + nk * 28].view(np.int64).reshape(nq_max, k_max)
+        dD[:nq, :k], dI[:nq, :k], dS[:nq, :k], dJ[:nq, :k] = D[r], I[r], S[r], J[r]
+    flags = buf[2 * world * slot:].view(np.uint32).reshape(2, world, nq_max)
+    flags[parity, 1:, :] = step
+    dev = torch.from_numpy(buf).cuda()
+    F, O = hybrid.exchange_fuse(torch.from_numpy(D[0]).cuda(), torch.from_numpy(I[0]).cuda(),
+                                torch.from_numpy(S[0]).cuda(), torch.from_numpy(J[0]).cuda(),
+                                [dev.data_ptr()] * world, 0, world, nq_max, k_max, step)
+    torch.cuda.synchronize()
+    Dm, Im = oracle.merge_lists_ref(D, I, k, np.float32(-3.4028235e38))
+    Sm, Jm = oracle.merge_lists_ref(S, J, k, -1.7976931348623157e308)
+    Fr, Or, _ = oracle.hybrid_fuse_ref(Dm, Im, Sm, Jm, k)
+    assert np.array_equal(O.cpu().numpy(), Or)
+    assert np.array_equal(F.cpu().numpy(), Fr)
+    out_flags = dev.cpu().numpy()[2 * world * slot:].view(np.uint32).reshape(2, world, nq_max)
+    assert np.all(out_flags[parity, 0, :nq] == step)       # rank 0 published its own flags
