@@ -256,33 +256,52 @@ class HybridIndex:
         return self.searcher.search_hybrid(q, term_ids, term_offsets, k)
 
     # host API: the call a user makes (numpy in, numpy out; copies inside) ------------------------------
-    def _stage(self, name, arr, dtype):
-        """host array -> pinned staging tensor -> device (non_blocking)."""
-        import numpy as np
+    def _staging(self, nbytes, nk):
+        """Pinned host + device staging buffers (grown on demand), reused across calls."""
         import torch
 
-        a = np.ascontiguousarray(arr, dtype=dtype)
-        buf = self._pinned.get(name)
-        if buf is None or buf.numel() < a.size or buf.dtype != torch.from_numpy(a).dtype:
-            buf = torch.empty(max(a.size, 1024), dtype=torch.from_numpy(a).dtype).pin_memory()
-            self._pinned[name] = buf
-        view = buf[: a.size].view(a.shape) if a.size else buf[:0]
-        view.copy_(torch.from_numpy(a))
         dev = torch.device("cuda", self.flat.device)
-        return view.to(dev, non_blocking=True), a.nbytes
+        st = self._pinned
+        if st.get("in_cap", 0) < nbytes:
+            cap = max(nbytes, 1 << 16)
+            st["in_host"] = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            st["in_dev"] = torch.empty(cap, dtype=torch.uint8, device=dev)
+            st["in_cap"] = cap
+        if st.get("out_cap", 0) < nk:
+            cap = max(nk, 4096)
+            st["F_host"] = torch.empty(cap, dtype=torch.float32).pin_memory()
+            st["O_host"] = torch.empty(cap, dtype=torch.int64).pin_memory()
+            st["out_cap"] = cap
+        return st
 
     def search_hybrid(self, x, queries_term_ids, k):
         """x float32[nq,d] (host), queries_term_ids: list of int term-id lists -> (F, O) numpy.
-        Returns also the bytes copied each way (bench accounting)."""
+        One packed host->device copy from pinned memory, the resident search, pinned device->host
+        copies of the result, one stream synchronisation.  Records the bytes moved each way."""
         import numpy as np
+        import torch
 
-        offs = np.zeros(len(queries_term_ids) + 1, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        nq, d = x.shape
+        offs = np.zeros(nq + 1, dtype=np.int32)
         np.cumsum([len(t) for t in queries_term_ids], out=offs[1:])
-        flat_ids = np.concatenate([np.asarray(t, np.int32) for t in queries_term_ids]) if len(queries_term_ids) else np.zeros(0, np.int32)
-        q_dev, b1 = self._stage("q", x, np.float32)
-        t_dev, b2 = self._stage("t", flat_ids, np.int32)
-        o_dev, b3 = self._stage("o", offs, np.int32)
+        n_terms = int(offs[-1])
+        qb, ob, tb = x.nbytes, offs.nbytes, 4 * n_terms
+        st = self._staging(qb + ob + tb, nq * k)
+        host = st["in_host"].numpy()
+        host[:qb].view(np.float32)[:] = x.reshape(-1)
+        host[qb: qb + ob].view(np.int32)[:] = offs
+        if n_terms:
+            host[qb + ob: qb + ob + tb].view(np.int32)[:] = np.concatenate([np.asarray(t, np.int32) for t in queries_term_ids])
+        dev_buf = st["in_dev"]
+        dev_buf[: qb + ob + tb].copy_(st["in_host"][: qb + ob + tb], non_blocking=True)
+        q_dev = dev_buf[:qb].view(torch.float32).view(nq, d)
+        o_dev = dev_buf[qb: qb + ob].view(torch.int32)
+        t_dev = dev_buf[qb + ob: qb + ob + max(tb, 4)].view(torch.int32)
         F, O = self.searcher.search_hybrid(q_dev, t_dev, o_dev, k)
-        Fh, Oh = F.cpu(), O.cpu()  # device -> host, synchronises
-        self.last_h2d_bytes, self.last_d2h_bytes = b1 + b2 + b3, Fh.numel() * 4 + Oh.numel() * 8
-        return Fh.numpy(), Oh.numpy()
+        Fh, Oh = st["F_host"][: nq * k], st["O_host"][: nq * k]
+        Fh.copy_(F.reshape(-1), non_blocking=True)
+        Oh.copy_(O.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(F.device).synchronize()
+        self.last_h2d_bytes, self.last_d2h_bytes = qb + ob + tb, nq * k * 12
+        return Fh.numpy().reshape(nq, k).copy(), Oh.numpy().reshape(nq, k).copy()

@@ -1,0 +1,71 @@
+"""Multi-GPU correctness check (run under torchrun on G >= 2 GPUs): row-sharded hybrid search through
+(a) the one-kernel peer-memory exchange and (b) NCCL all-gather + merge kernels must both equal the
+unsharded search computed on rank 0 over the whole corpus.  Exit code 0 = identical on every rank."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rag_challenge_2_b200 as pkg  # noqa: E402
+from rag_challenge_2_b200 import hybrid, synth  # noqa: E402
+from rag_challenge_2_b200.bm25 import BM25Okapi  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n, d, V, k, nq = 400_000, 1024, 20_000, 30, 12
+bounds = hybrid.shard_bounds(n, world, synth.ROW_BLOCK)
+lo, hi = bounds[rank], bounds[rank + 1]
+
+
+def build(lo, hi):
+    rows = synth.dense_rows_torch(lo, hi, d, dev)
+    post = synth.token_postings_torch(lo, hi, V, dev)
+    return rows, post
+
+
+rows, post = build(lo, hi)
+df, tot = post["df"].clone(), torch.tensor([post["total_len"]], device=dev)
+dist.all_reduce(df)
+dist.all_reduce(tot)
+idf, _ = synth.bm25_idf_from_df(df.cpu().numpy(), n)
+idf_t, avgdl = torch.from_numpy(idf).to(dev), float(tot.item()) / n
+flat = pkg.FlatIPIndex.from_device_tensor(rows)
+bm = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"], idf_t, avgdl, device=local)
+q = synth.dense_queries_torch(nq, d, dev, rows if rank == 0 else None)
+dist.broadcast(q, 0)
+toks = synth.token_queries_np(nq, vocab=V, seed=4243)
+offs = np.zeros(nq + 1, np.int32)
+np.cumsum([len(t) for t in toks], out=offs[1:])
+tids = torch.from_numpy(np.concatenate(toks).astype(np.int32)).to(dev)
+toffs = torch.from_numpy(offs).to(dev)
+
+peer = hybrid.HybridIndex(flat, bm, lo, exchange="peer")
+nccl = hybrid.HybridIndex(flat, bm, lo, exchange="nccl")
+ok = True
+for it in range(5):  # several steps: exercises the parity double-buffering and the step counter
+    F1, O1 = peer.search_hybrid_dev(q, tids, toffs, k)
+    F2, O2 = nccl.search_hybrid_dev(q, tids, toffs, k)
+    torch.cuda.synchronize()
+    ok &= bool(torch.equal(O1, O2) and torch.equal(F1, F2))
+Fh, Oh = peer.search_hybrid(q.cpu().numpy(), toks, k)  # host API on every rank (SPMD)
+ok &= bool(np.array_equal(Oh, O1.cpu().numpy()) and np.array_equal(Fh, F1.cpu().numpy()))
+if rank == 0:
+    rows_all, post_all = build(0, n)
+    whole = hybrid.HybridIndex(pkg.FlatIPIndex.from_device_tensor(rows_all),
+                               BM25Okapi.from_postings(post_all["indptr"], post_all["doc_ids"], post_all["tf"],
+                                                       post_all["doc_len"], idf_t, avgdl, device=local), 0, world_size=1)
+    F0, O0 = whole.search_hybrid_dev(q, tids, toffs, k)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(O0, O1) and torch.equal(F0, F1))
+    print("sharded == unsharded:", same, "| peer == nccl == host API:", ok, "| top1", O1[:4, 0].tolist())
+    ok &= same
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
