@@ -315,13 +315,7 @@ static int pow2_ge_i(int v) {
 
 static int bm25_plan(const b2r_bm25* h, int k, Bm25Plan* p) {
   int B = tunable("bm25.block_docs");
-  if (B <= 0) {
-    // Small shards: smaller doc blocks give more CTAs (latency-bound kernel) and shorter per-token
-    // posting segments.  The last CTA's select scratch is the accumulator area (B/2 128-bit keys)
-    // and must hold one key per doc block (the "k-th largest top-1" bound), so B grows with n.
-    B = 2048;
-    while (B < 16384 && pow2_ge_i(static_cast<int>(std::min<long long>((h->n_docs + B - 1) / B, 1 << 30))) > B / 2) B <<= 1;
-  }
+  if (B <= 0) B = 8192;
   B = std::max(1024, pow2_ge_i(B));
   p->cap = pow2_ge_i(std::max(2 * k, 64));
   // the accumulator area doubles as the final-select scratch: >= 2 * pow2(k) 128-bit keys
