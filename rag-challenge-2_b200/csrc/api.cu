@@ -37,6 +37,7 @@ static std::map<std::string, int>& tunables() {
       {"flat.gemm_max_n", 0},      // queries per tensor-core pass (default 64)
       {"gemm.stages", 0},          // depth of the tensor-core kernel's TMA ring
       {"gemm.tile256", 0},         // 1: candidate pass scores 256 rows per query slab (experimental)
+      {"gemm.debug_skip", 0},      // perf experiments: 1 skip query-slab reloads, 2 skip MMAs, 4 skip select (wrong results)
       {"gemm.mode", 0},            // 0: tf32 candidates + exact fp32 rescoring (verified); 3: 3xTF32 only
       {"gemm.no_verify", 0},       // 1: skip the 3xTF32 redo pass of unproven queries
       {"select.buf_cap", 0},       // cap on the final-select scratch (keys); small values force the fallback

@@ -57,6 +57,8 @@ struct GemmArgs {
   long long n_tiles;
   u64* partial;        // [N][gridDim.x][k]
   const u32* active;   // optional per-query flags (device); NULL = all queries active
+  int debug_skip;      // perf experiments only (results become wrong): 1 = re-use the tile's first query slab,
+                       // 2 = issue no MMAs, 4 = drain TMEM without selecting
   // STATS epilogue (N x N cosine analysis): the "queries" are rows [col0, col0 + N) of the same matrix
   long long col0;
   double* stats;       // [0] sum, [1] sum of squares, [2] count   (pairs i < j, each once)
@@ -290,13 +292,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         for (int sl = 0; sl < n_slabs; ++sl) {
           mbar_wait_tag(&empty[s], ph ^ 1u, 100 + s);
           unsigned char* st = raw_ring + static_cast<size_t>(s) * kRawStage;
-          mbar_arrive_expect_tx(&full[s], kRawStage);
+          const bool skip_b = (a.debug_skip & 1) && sl > 0;
+          mbar_arrive_expect_tx(&full[s], skip_b ? kABytes : kRawStage);
 #pragma unroll
           for (int sub = 0; sub < kSub; ++sub) {
             tma_load_2d(st + sub * kSubBytes, &map_a, sl * kSlabK, row0 + sub * kTileM, &full[s], pol_a);
           }
-          tma_load_2d(st + kABytes, &map_b, sl * kSlabK, 0, &full[s], pol_b);
-          if constexpr (TERMS == 3) tma_load_2d(st + kABytes + kBBytes, &map_b, sl * kSlabK, N, &full[s], pol_b);
+          if (!skip_b) tma_load_2d(st + kABytes, &map_b, sl * kSlabK, 0, &full[s], pol_b);
+          if constexpr (TERMS == 3) if (!skip_b) tma_load_2d(st + kABytes + kBBytes, &map_b, sl * kSlabK, N, &full[s], pol_b);
           if (++s == R) {
             s = 0;
             ph ^= 1u;
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
               for (int kk = 0; kk < kSlabK / 8; ++kk) {
                 const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);
-                tc_mma_tf32(d_acc, d_a + adv, d_bhi + adv, idesc, (first && kk == 0) ? 0u : 1u);
+                if (!(a.debug_skip & 2)) tc_mma_tf32(d_acc, d_a + adv, d_bhi + adv, idesc, (first && kk == 0) ? 0u : 1u);
               }
             }
             tc_commit(&empty[s]);
@@ -482,7 +485,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         continue;
       }
-      u64 pend = (row < a.n) ? active_mask : 0ull;
+      u64 pend = (row < a.n && !(a.debug_skip & 4)) ? active_mask : 0ull;
       for (;;) {
         u32* flag = flags + (it & 1);
 #pragma unroll
@@ -754,6 +757,7 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   a.n_tiles = n_tiles;
   a.partial = partial;
   a.active = active;
+  a.debug_skip = tunable("gemm.debug_skip");
   a.col0 = 0;
   a.stats = nullptr;
   a.minmax = nullptr;
@@ -924,6 +928,7 @@ int cosine_stats_run(const float* rows_dev, long long n, int d, long long col_be
       a.n_tiles = last_col <= 0 ? 0 : (last_col - 1) / kTileM + 1;
       a.partial = nullptr;
       a.active = nullptr;
+      a.debug_skip = 0;
       a.col0 = c0;
       a.stats = acc;
       a.minmax = minmax;
