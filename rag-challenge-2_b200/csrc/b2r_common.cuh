@@ -157,16 +157,17 @@ __device__ __forceinline__ void cmpxchg_desc(K* a, int i, int j, bool up) {
   }
 }
 
-// one warp sorts a[0..n) descending; all 32 lanes must call it
+// one warp sorts a[0..n) descending; all 32 lanes must call it.  n is a power of two, so all the
+// index arithmetic of the bitonic network is shifts and masks (size = 1 << ls, stride = 1 << lj).
 template <class K>
 __device__ __forceinline__ void warp_sort_desc(K* a, int n, int lane) {
-  for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+  for (int ls = 1; (1 << ls) <= n; ++ls) {
+    for (int lj = ls - 1; lj >= 0; --lj) {
+      const int stride = 1 << lj;
       for (int t = lane; t < (n >> 1); t += 32) {
-        const int i = ((t / stride) * (stride << 1)) + (t % stride);
-        const int j = i + stride;
-        const bool up = (i & size) != 0;
-        cmpxchg_desc(a, i, j, up);
+        const int i = ((t >> lj) << (lj + 1)) | (t & (stride - 1));
+        const bool up = ((i >> ls) & 1) != 0;
+        cmpxchg_desc(a, i, i | stride, up);
       }
       __syncwarp();
     }
@@ -177,13 +178,13 @@ __device__ __forceinline__ void warp_sort_desc(K* a, int n, int lane) {
 template <class K>
 __device__ __forceinline__ void block_sort_desc(K* a, int n) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+  for (int ls = 1; (1 << ls) <= n; ++ls) {
+    for (int lj = ls - 1; lj >= 0; --lj) {
+      const int stride = 1 << lj;
       for (int t = tid; t < (n >> 1); t += nt) {
-        const int i = ((t / stride) * (stride << 1)) + (t % stride);
-        const int j = i + stride;
-        const bool up = (i & size) != 0;
-        cmpxchg_desc(a, i, j, up);
+        const int i = ((t >> lj) << (lj + 1)) | (t & (stride - 1));
+        const bool up = ((i >> ls) & 1) != 0;
+        cmpxchg_desc(a, i, i | stride, up);
       }
       __syncthreads();
     }
