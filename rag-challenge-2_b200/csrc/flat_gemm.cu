@@ -57,7 +57,6 @@ struct GemmArgs {
   long long n_tiles;
   u64* partial;        // [N][gridDim.x][k]
   const u32* active;   // optional per-query flags (device); NULL = all queries active
-  u64* tau_g;          // [N] cross-CTA thresholds: a key below tau_g[c] cannot be in query c's top-k
   int debug_skip;      // perf experiments only (results become wrong): 1 = re-use the tile's first query slab,
                        // 2 = issue no MMAs, 4 = drain TMEM without selecting
   // STATS epilogue (N x N cosine analysis): the "queries" are rows [col0, col0 + N) of the same matrix
@@ -183,8 +182,7 @@ __host__ __device__ constexpr u32 make_idesc_tf32(int n) {
 // prep: split the queries into tf32 hi / lo parts: Bs[0][q][:] = hi, Bs[1][q][:] = lo; rows nq..N-1 zero
 // ---------------------------------------------------------------------------------------------
 __global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, int N, int d, float* __restrict__ Bs,
-                                          int split, u64* __restrict__ tau_g) {
-  if (tau_g && blockIdx.x == 0 && threadIdx.x < 64) tau_g[threadIdx.x] = 0;  // fresh cross-CTA thresholds
+                                          int split) {
   const long long total = static_cast<long long>(N) * d;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -499,8 +497,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               if (pos < static_cast<u32>(cap)) {
                 lists[static_cast<size_t>(c) * cap + pos] = key;
                 pend &= ~(1ull << c);
-              } else if (a.debug_skip & 8) {
-                pend &= ~(1ull << c);  // experiment: drop instead of compact + retry
               }
             } else {
               pend &= ~(1ull << c);
@@ -513,12 +509,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         // cut back to its best k, which also raises the query's threshold
         for (int c = ew; c < a.nq; c += 4) {
           const u32 nc = cnt_s[c];
-          if (a.tau_g && lane == 0) {
-            // any CTA that holds k keys >= t proves the global k-th key is >= t: adopt the best bound
-            const u64 g = *reinterpret_cast<volatile u64*>(a.tau_g + c);
-            if (g > tau_s[c]) tau_s[c] = g;
-          }
-          if (nc >= static_cast<u32>((k + cap + 1) / 2) && !(a.debug_skip & 8)) {
+          if (nc >= static_cast<u32>((k + cap + 1) / 2)) {
             u64* list = lists + static_cast<size_t>(c) * cap;
             const int valid = nc < static_cast<u32>(cap) ? static_cast<int>(nc) : cap;
             for (int i = valid + lane; i < cap; i += 32) list[i] = 0;
@@ -527,11 +518,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             if (lane == 0) {
               const int keep = valid < k ? valid : k;
               cnt_s[c] = static_cast<u32>(keep);
-              if (valid >= k) {
-                const u64 mine = list[k - 1];
-                if (mine > tau_s[c]) tau_s[c] = mine;
-                if (a.tau_g) atomicMax(a.tau_g + c, mine);
-              }
+              if (valid >= k) tau_s[c] = list[k - 1];
             }
             __syncwarp();
           }
@@ -736,7 +723,7 @@ static int pow2_ge_g(int v) {
 // one scan pass: `terms` = 1 (approximate, raw tf32) or 3 (3xTF32); selects `ksel` per query
 static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, int nq, int ksel, int terms,
                      const u32* active, float* D_out, long long* I_out, long long id_offset, float* bsplit,
-                     u64* partial, u64* tau_g, int num_sms, cudaStream_t stream) {
+                     u64* partial, int num_sms, cudaStream_t stream) {
   const int cap = pow2_ge_g(std::max(2 * ksel, 64));
   // candidate lists (N x cap keys) get at most 64 KiB of shared memory
   int N = nq <= 16 ? 16 : (nq <= 32 ? 32 : 64);
@@ -745,7 +732,7 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   const int tile_rows = sub * kTileM;
   const long long n_tiles = (n + tile_rows - 1) / tile_rows;
   const int grid = static_cast<int>(std::min<long long>(n_tiles, num_sms));
-  gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit, terms == 3 ? 1 : 0, tau_g);
+  gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit, terms == 3 ? 1 : 0);
   B2R_CUDA(cudaGetLastError());
   CUtensorMap ma, mb;
   int rc = make_map_2d(&ma, rows, static_cast<unsigned long long>(d), static_cast<unsigned long long>(n), kSlabK, kTileM);
@@ -771,7 +758,6 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   a.partial = partial;
   a.active = active;
   a.debug_skip = tunable("gemm.debug_skip");
-  a.tau_g = tau_g;
   a.col0 = 0;
   a.stats = nullptr;
   a.minmax = nullptr;
@@ -831,17 +817,16 @@ int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev,
   float* Dp = reinterpret_cast<float*>(extra);                         // [64][128]
   long long* Ip = reinterpret_cast<long long*>(extra + 64 * 128 * 4);  // [64][128]
   u32* redo = reinterpret_cast<u32*>(extra + 64 * 128 * 12);           // [64]
-  u64* tau_g = reinterpret_cast<u64*>(extra + 64 * 128 * 12 + 256);    // [64]
   const int mode = tunable("gemm.mode");  // 0/1: approximate pass + exact rescoring (+ verified fallback); 3: 3xTF32 only
   int rc;
   if (mode == 3 || k > 64) {
-    rc = gemm_scan(rows, n, d, q_dev, nq, k, 3, nullptr, D_dev, I_dev, id_offset, bsplit, partial, tau_g, num_sms, stream);
+    rc = gemm_scan(rows, n, d, q_dev, nq, k, 3, nullptr, D_dev, I_dev, id_offset, bsplit, partial, num_sms, stream);
     if (rc) return rc;
     *launches += 3;
     return B2R_OK;
   }
   const int kp = std::min(128, std::max(64, 2 * k));
-  rc = gemm_scan(rows, n, d, q_dev, nq, kp, 1, nullptr, Dp, Ip, 0, bsplit, partial, tau_g, num_sms, stream);
+  rc = gemm_scan(rows, n, d, q_dev, nq, kp, 1, nullptr, Dp, Ip, 0, bsplit, partial, num_sms, stream);
   if (rc) return rc;
   gemm_rescore_kernel<<<nq, 256, 0, stream>>>(rows, d, q_dev, Dp, Ip, kp, k, max_norm2_dev, D_dev, I_dev, id_offset, redo);
   B2R_CUDA(cudaGetLastError());
@@ -849,7 +834,7 @@ int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev,
   if (!tunable("gemm.no_verify")) {
     // queries whose candidate set could not be proven complete are redone with 3xTF32 accuracy;
     // the kernels exit at once when no flag is set
-    rc = gemm_scan(rows, n, d, q_dev, nq, k, 3, redo, D_dev, I_dev, id_offset, bsplit, partial, tau_g, num_sms, stream);
+    rc = gemm_scan(rows, n, d, q_dev, nq, k, 3, redo, D_dev, I_dev, id_offset, bsplit, partial, num_sms, stream);
     if (rc) return rc;
     *launches += 3;
   }
@@ -930,7 +915,7 @@ int cosine_stats_run(const float* rows_dev, long long n, int d, long long col_be
     const size_t smem = stages * raw_stage + fixed;
     for (long long c0 = (col_begin / N) * N; c0 < col_end && rc == B2R_OK; c0 += N) {
       const int ncols = static_cast<int>(std::min<long long>(N, n - c0));
-      gemm_split_queries_kernel<<<64, 256, 0, stream>>>(xn + c0 * d, ncols, N, d, bsplit, 1, nullptr);
+      gemm_split_queries_kernel<<<64, 256, 0, stream>>>(xn + c0 * d, ncols, N, d, bsplit, 1);
       GemmArgs a;
       a.n = n;
       a.d = d;
@@ -944,7 +929,6 @@ int cosine_stats_run(const float* rows_dev, long long n, int d, long long col_be
       a.partial = nullptr;
       a.active = nullptr;
       a.debug_skip = 0;
-      a.tau_g = nullptr;
       a.col0 = c0;
       a.stats = acc;
       a.minmax = minmax;
