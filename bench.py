@@ -335,6 +335,25 @@ def run_b200(args):
     h2d, d2h = index.last_h2d_bytes, index.last_d2h_bytes
     sampler.stop()
 
+    # ---- explanatory extras (not the metric): dense-only single query, and a 64-query dense batch on the
+    # tensor-core path (K2); local shard only, CUDA events, a few iterations each
+    extras = {}
+    index.searcher.local_dense = inner_dense
+    for name, nqx, iters in (("dense_single_query", 1, 20), ("dense_batch64_tensor_core", 64, 5)):
+        qx = q_pool[:nqx].contiguous() if pool >= nqx else q_pool.repeat((nqx + pool - 1) // pool, 1)[:nqx].contiguous()
+        for _ in range(2):
+            flat.search_dev(qx, args.k)
+        torch.cuda.synchronize()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for _ in range(iters):
+            flat.search_dev(qx, args.k)
+        x1.record()
+        torch.cuda.synchronize()
+        msx = x0.elapsed_time(x1) / iters
+        extras[name] = {"ms": msx, "local_rows": hi - lo, "queries_per_s_local_shard": nqx / msx * 1e3,
+                        "GBps_equiv": 4.0 * (hi - lo) * args.dim / msx / 1e6}
+
     times = torch.tensor([ms_total, ms_e2e, scan_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -361,6 +380,7 @@ def run_b200(args):
             "clocks": sampler.summary(t_wall0, t_wall1),
             "bm25": {"postings_local": n_post, "bytes_per_posting": 4 + wbits // 8},
             "top1_last_step": top1,
+            "extras": extras,
         }
         if world == 1 and not args.no_cpu_baseline:
             n_s = min(args.cpu_rows, hi - lo)
