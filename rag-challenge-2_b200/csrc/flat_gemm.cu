@@ -32,20 +32,20 @@
 // A second tiny kernel (one CTA per query) merges the per-CTA lists.
 //
 // Rooflines: HBM for N up to ~100 (4*n*d bytes per launch, independent of N); tensor beyond.
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
-#include <stdio.h>
-
 #include <algorithm>
 
-#include "b2r_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace b2r {
 
 static const int kGemmThreads = 320;
-static const int kSlabK = 32;          // floats per K-slab = one 128-byte swizzle row
-static const int kTileM = 128;
+static const int kGemmMaxBatch = 128;  // queries per gemm_search_chunk call
+
+// csrc/flat_gemm_wide.cu
+bool wide_path_supported(long long n, int d, int kp);
+int wide_candidates(const float* rows, long long n, int d, const float* q_dev, int nq, int kp, float* B, float* tauf,
+                    u32* premax, u32* gcnt, u32* ovf, u64* glists, size_t glists_bytes, float* Dp, long long* Ip,
+                    int num_sms, cudaStream_t stream, int* launches);
 static const int kLoStages = 4;
 
 struct GemmArgs {
@@ -67,116 +67,6 @@ struct GemmArgs {
   int n_bins;
 };
 
-// ---------------- PTX wrappers specific to this kernel ----------------
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, u64* bar,
-                                            u64 policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-
-__device__ __forceinline__ u64 l2_policy_evict_last() {
-  u64 p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_alloc(u32* slot, u32 ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_dealloc(u32 taddr, u32 ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate; issued by ONE thread
-__device__ __forceinline__ void tc_mma_tf32(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void tc_commit(u64* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base + i)
-__device__ __forceinline__ void tc_ld16(u32 taddr, float* v) {
-  u32 r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// round-to-nearest (ties away) to tf32 precision with two integer ops (cvt.rna.tf32.f32 runs on
-// the slow conversion pipe): add half an ulp of the 10-bit mantissa to the magnitude, clear 13 bits
-__device__ __forceinline__ float rna_tf32(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
-
-// mbarrier wait with a watchdog: a pipeline bug shows up as a trap with the barrier's tag, not a hang
-__device__ __forceinline__ void mbar_wait_tag(u64* bar, u32 parity, int tag) {
-  const u32 addr = smem_u32(bar);
-  for (u32 spins = 0;; ++spins) {
-    u32 done;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (spins == (1u << 26)) {
-      printf("b2r flat_gemm: barrier wait stuck: tag %d block %d thread %d parity %u\n", tag, blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups
-// 1024 B apart (the layout a {32 x rows} fp32 TMA box with SWIZZLE_128B produces)
-__device__ __forceinline__ u64 make_kmajor_sw128_desc(u32 smem_addr) {
-  u64 desc = 0;
-  desc |= static_cast<u64>((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
-  desc |= static_cast<u64>(1) << 16;                      // leading byte offset (unused for swizzled K-major)
-  desc |= static_cast<u64>(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
-  desc |= static_cast<u64>(1) << 46;                      // descriptor version (Blackwell)
-  desc |= static_cast<u64>(2) << 61;                      // SWIZZLE_128B
-  return desc;
-}
-
-// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N
-__host__ __device__ constexpr u32 make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<u32>(n >> 3) << 17) | (static_cast<u32>(kTileM >> 4) << 24);
-}
 
 // ---------------------------------------------------------------------------------------------
 // prep: split the queries into tf32 hi / lo parts: Bs[0][q][:] = hi, Bs[1][q][:] = lo; rows nq..N-1 zero
@@ -615,7 +505,7 @@ __global__ void __launch_bounds__(256) gemm_rescore_kernel(const float* __restri
                                                            const long long* __restrict__ Ip, int kp, int k,
                                                            const float* __restrict__ max_norm2, float* __restrict__ D,
                                                            long long* __restrict__ I, long long id_offset,
-                                                           u32* __restrict__ redo) {
+                                                           u32* __restrict__ redo, const u32* __restrict__ ovf) {
   __shared__ u64 keys[256];
   __shared__ float s_qn2;
   const int qi = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -664,11 +554,14 @@ __global__ void __launch_bounds__(256) gemm_rescore_kernel(const float* __restri
     u32 need_redo = 0;
     const bool list_full = cand[kp - 1] >= 0;  // fewer than k' rows in the shard: every row was rescored
     if (list_full) {
-      const float bound = 0.001953125f * 1.0625f * sqrtf(s_qn2) * sqrtf(*max_norm2) + 1e-6f;  // 2^-9 (+6 %) |q| max|x|
+      // operand truncation 2^-9 (+6 %) plus the truncating fp32 accumulation of a length-d chain, d * 2^-24
+      const float rel = 0.001953125f * 1.0625f + static_cast<float>(d) * 5.9604645e-8f;
+      const float bound = rel * sqrtf(s_qn2) * sqrtf(*max_norm2) + 1e-6f;
       const u64 kth = keys[k - 1];
       const float exact_kth = kth ? key_score(kth) : -3.4028235e38f;
       if (!(Dp[static_cast<size_t>(qi) * kp + kp - 1] + bound < exact_kth)) need_redo = 1;
     }
+    if (ovf && ovf[qi]) need_redo = 1;  // a candidate list overflowed: the set may be incomplete
     redo[qi] = need_redo;
   }
 }
@@ -689,7 +582,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-static int make_map_2d(CUtensorMap* map, const float* base, unsigned long long inner, unsigned long long outer,
+int make_map_2d(CUtensorMap* map, const float* base, unsigned long long inner, unsigned long long outer,
                        unsigned box_inner, unsigned box_outer) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
   if (!enc) return fail(B2R_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -789,15 +682,21 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   return B2R_OK;
 }
 
-bool gemm_path_supported(int d, int k) { return d % kSlabK == 0 && d >= kSlabK && k <= 128; }
+bool gemm_path_supported(int d, int k) { return d % kSlabK == 0 && d >= kSlabK && d <= 16384 && k <= 128; }
 
-// largest batch one pass can take for this k (candidate lists are capped at 64 KiB of shared memory)
-int gemm_max_batch(int k) {
-  const int kp = std::max(64, 2 * k);               // candidates of the approximate pass
-  const int cap = pow2_ge_g(2 * std::min(kp, 128));
+// largest batch one pass of the list-keeping scan can take for this k (candidate lists are capped at
+// 64 KiB of shared memory)
+static int list_scan_max_batch(int ksel) {
+  const int cap = pow2_ge_g(std::max(2 * ksel, 64));
   int n = 64;
   while (n > 16 && static_cast<size_t>(n) * cap * 8 > 64 * 1024) n >>= 1;
   return n;
+}
+
+// largest batch gemm_search_chunk accepts
+int gemm_max_batch(int k) {
+  (void)k;
+  return kGemmMaxBatch;
 }
 
 int gemm_max_row_norm2(const float* rows, long long n, int d, float* out_dev, cudaStream_t stream) {
@@ -807,36 +706,74 @@ int gemm_max_row_norm2(const float* rows, long long n, int d, float* out_dev, cu
   return B2R_OK;
 }
 
-// Scores `nq` (<= gemm_max_batch(k)) queries against the whole shard.  scratch: device buffer of
-// kGemmScratchBytes (hi/lo queries, candidate lists, redo flags); partial: 64 * grid * 128 keys.
+// device scratch of one search stream, carved from one allocation
+static const size_t kScrB = static_cast<size_t>(kGemmMaxBatch) * 16384 * sizeof(float);  // query operand(s): 8 MiB
+static const size_t kScrDp = kScrB;                                                   // float [128][128]
+static const size_t kScrIp = kScrDp + static_cast<size_t>(kGemmMaxBatch) * 128 * 4;   // int64 [128][128]
+static const size_t kScrFlags = kScrIp + static_cast<size_t>(kGemmMaxBatch) * 128 * 8;  // redo, ovf, tauf [128] each
+static const size_t kScrGcnt = kScrFlags + 4096;                                      // u32 [<= 256 CTAs][128]
+static const size_t kScrPremax = kScrGcnt + static_cast<size_t>(256) * kGemmMaxBatch * 4;  // u32 [128][8192]
+static const size_t kScrEnd = kScrPremax + static_cast<size_t>(kGemmMaxBatch) * 8192 * 4;
+
+size_t gemm_scratch_bytes() { return kScrEnd + 1024; }
+
+// Scores `nq` (<= kGemmMaxBatch) queries against the whole shard.  scratch: gemm_scratch_bytes() of device
+// memory; partial: list scratch of partial_bytes (>= 64 * grid * 128 keys).
 int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
-                      long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial,
+                      long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial, size_t partial_bytes,
                       const float* max_norm2_dev, int num_sms, cudaStream_t stream, int* launches) {
   float* bsplit = reinterpret_cast<float*>(scratch);
-  unsigned char* extra = scratch + static_cast<size_t>(2) * 64 * 16384 * sizeof(float);
-  float* Dp = reinterpret_cast<float*>(extra);                         // [64][128]
-  long long* Ip = reinterpret_cast<long long*>(extra + 64 * 128 * 4);  // [64][128]
-  u32* redo = reinterpret_cast<u32*>(extra + 64 * 128 * 12);           // [64]
+  float* Dp = reinterpret_cast<float*>(scratch + kScrDp);
+  long long* Ip = reinterpret_cast<long long*>(scratch + kScrIp);
+  u32* redo = reinterpret_cast<u32*>(scratch + kScrFlags);
+  u32* ovf = redo + kGemmMaxBatch;
+  float* tauf = reinterpret_cast<float*>(ovf + kGemmMaxBatch);
+  u32* gcnt = reinterpret_cast<u32*>(scratch + kScrGcnt);
+  u32* premax = reinterpret_cast<u32*>(scratch + kScrPremax);
   const int mode = tunable("gemm.mode");  // 0/1: approximate pass + exact rescoring (+ verified fallback); 3: 3xTF32 only
   int rc;
   if (mode == 3 || k > 64) {
-    rc = gemm_scan(rows, n, d, q_dev, nq, k, 3, nullptr, D_dev, I_dev, id_offset, bsplit, partial, num_sms, stream);
-    if (rc) return rc;
-    *launches += 3;
+    const int step = list_scan_max_batch(k);
+    for (int off = 0; off < nq; off += step) {
+      const int c = std::min(step, nq - off);
+      rc = gemm_scan(rows, n, d, q_dev + static_cast<size_t>(off) * d, c, k, 3, nullptr, D_dev + static_cast<size_t>(off) * k,
+                     I_dev + static_cast<size_t>(off) * k, id_offset, bsplit, partial, num_sms, stream);
+      if (rc) return rc;
+      *launches += 3;
+    }
     return B2R_OK;
   }
   const int kp = std::min(128, std::max(64, 2 * k));
-  rc = gemm_scan(rows, n, d, q_dev, nq, kp, 1, nullptr, Dp, Ip, 0, bsplit, partial, num_sms, stream);
-  if (rc) return rc;
-  gemm_rescore_kernel<<<nq, 256, 0, stream>>>(rows, d, q_dev, Dp, Ip, kp, k, max_norm2_dev, D_dev, I_dev, id_offset, redo);
-  B2R_CUDA(cudaGetLastError());
-  *launches += 4;
-  if (!tunable("gemm.no_verify")) {
-    // queries whose candidate set could not be proven complete are redone with 3xTF32 accuracy;
-    // the kernels exit at once when no flag is set
-    rc = gemm_scan(rows, n, d, q_dev, nq, k, 3, redo, D_dev, I_dev, id_offset, bsplit, partial, num_sms, stream);
+  const bool wide = wide_path_supported(n, d, kp);
+  if (wide) {
+    rc = wide_candidates(rows, n, d, q_dev, nq, kp, bsplit, tauf, premax, gcnt, ovf, partial, partial_bytes, Dp, Ip,
+                         num_sms, stream, launches);
     if (rc) return rc;
-    *launches += 3;
+  } else {
+    const int step = list_scan_max_batch(kp);
+    for (int off = 0; off < nq; off += step) {
+      const int c = std::min(step, nq - off);
+      rc = gemm_scan(rows, n, d, q_dev + static_cast<size_t>(off) * d, c, kp, 1, nullptr, Dp + static_cast<size_t>(off) * kp,
+                     Ip + static_cast<size_t>(off) * kp, 0, bsplit, partial, num_sms, stream);
+      if (rc) return rc;
+      *launches += 3;
+    }
+  }
+  gemm_rescore_kernel<<<nq, 256, 0, stream>>>(rows, d, q_dev, Dp, Ip, kp, k, max_norm2_dev, D_dev, I_dev, id_offset, redo,
+                                              wide ? ovf : nullptr);
+  B2R_CUDA(cudaGetLastError());
+  *launches += 1;
+  if (!tunable("gemm.no_verify")) {
+    // queries whose candidate set could not be proven complete (or whose lists overflowed) are redone with
+    // 3xTF32 accuracy by the list-keeping scan; its kernels exit at once when no flag is set
+    const int step = list_scan_max_batch(k);
+    for (int off = 0; off < nq; off += step) {
+      const int c = std::min(step, nq - off);
+      rc = gemm_scan(rows, n, d, q_dev + static_cast<size_t>(off) * d, c, k, 3, redo + off, D_dev + static_cast<size_t>(off) * k,
+                     I_dev + static_cast<size_t>(off) * k, id_offset, bsplit, partial, num_sms, stream);
+      if (rc) return rc;
+      *launches += 3;
+    }
   }
   return B2R_OK;
 }

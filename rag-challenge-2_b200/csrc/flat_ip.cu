@@ -395,18 +395,17 @@ struct Workspace {
 };
 
 static const size_t kPartialBytes = static_cast<size_t>(kMaxNQ) * kMaxGrid * B2R_MAX_K * sizeof(u64);
-// tensor-core path scratch: hi/lo queries + candidate lists [64][128] (score, id) + redo flags + max row norm
-static const size_t kBsplitBytes = static_cast<size_t>(2) * 64 * 16384 * sizeof(float) + 64 * 128 * 12 + 1024;
 
-static size_t workspace_bytes() { return 256 + kPartialBytes + kBsplitBytes; }
-
-// csrc/flat_gemm.cu
+// csrc/flat_gemm.cu (tensor-core path; its scratch follows the partial lists in the workspace)
 bool gemm_path_supported(int d, int k);
 int gemm_max_batch(int k);
+size_t gemm_scratch_bytes();
 int gemm_max_row_norm2(const float* rows, long long n, int d, float* out_dev, cudaStream_t stream);
 int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
-                      long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial,
+                      long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial, size_t partial_bytes,
                       const float* max_norm2_dev, int num_sms, cudaStream_t stream, int* launches);
+
+static size_t workspace_bytes() { return 256 + kPartialBytes + gemm_scratch_bytes(); }
 
 struct HostCtx {
   cudaStream_t stream = nullptr;
@@ -638,11 +637,11 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
   int rc = get_workspace(h, stream, &ws);
   if (rc) return rc;
   int done = 0;
-  // batches go to the tensor cores (K2): one pass over the rows per <= 64 queries
+  // batches go to the tensor cores (K2): one pass over the rows per <= 128 queries
   int gemm_min = tunable("flat.gemm_min_nq");
   if (gemm_min <= 0) gemm_min = 5;
   int gemm_max = tunable("flat.gemm_max_n");
-  if (gemm_max <= 0 || gemm_max > 64) gemm_max = 64;
+  if (gemm_max <= 0 || gemm_max > 128) gemm_max = 128;
   const bool use_gemm = nq >= gemm_min && gemm_path_supported(h->d, k) && !tunable("flat.force_generic") &&
                         !tunable("flat.no_gemm") && h->n >= 128;
   if (use_gemm) {
@@ -656,7 +655,7 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
     rc = gemm_search_chunk(h->rows, h->n, h->d, q_dev + static_cast<size_t>(done) * h->d, chunk, k,
                            D_dev + static_cast<size_t>(done) * k,
                            reinterpret_cast<long long*>(I_dev) + static_cast<size_t>(done) * k, id_offset,
-                           ws.base + 256 + kPartialBytes, reinterpret_cast<u64*>(ws.base + 256), h->max_norm2,
+                           ws.base + 256 + kPartialBytes, reinterpret_cast<u64*>(ws.base + 256), kPartialBytes, h->max_norm2,
                            h->num_sms, stream, &launches);
     if (rc) return rc;
     launch_counter() += launches;

@@ -149,3 +149,53 @@ def test_exact_scores_equal_simt_scores(b2r):
         _lib.tunable_set("flat.no_gemm", 0)
     assert np.array_equal(I1, I2)
     assert np.allclose(D1, D2, rtol=1e-6, atol=1e-7)   # both fp32 SIMT sums; only the reduction order differs
+
+
+@pytest.mark.parametrize("nq", [100, 128, 129, 300])
+def test_wide_threshold_pass(b2r, nq):
+    """n >= 16384 rows: the candidate pass is the threshold kernel (flat_gemm_wide.cu), up to 128 queries
+    per pass; same parity bar."""
+    xb = unit_rows(70001, 1024, 61)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    check(index, xb, queries_for(xb, nq, 62 + nq), 30)
+
+
+def test_wide_equals_list_scan(b2r):
+    """Threshold candidate pass vs the list-keeping candidate pass (gemm.no_wide): identical answers."""
+    from rag_challenge_2_b200 import _lib
+
+    xb = unit_rows(60000, 1024, 63)
+    xq = queries_for(xb, 64, 64)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    D1, I1 = check(index, xb, xq, 30)
+    _lib.tunable_set("gemm.no_wide", 1)
+    try:
+        D2, I2 = check(index, xb, xq, 30)
+    finally:
+        _lib.tunable_set("gemm.no_wide", 0)
+    assert np.array_equal(I1, I2)
+    assert np.array_equal(D1, D2)   # both rescore the same candidates with the same fp32 arithmetic
+
+
+def test_wide_adversarial_order_overflows_to_redo(b2r):
+    """Rows sorted by ascending score for the queries: the sampled thresholds (taken from the first tiles of
+    every CTA) are far too low, the candidate lists overflow, and the flagged queries must be answered by
+    the robust 3xTF32 pass."""
+    xb = unit_rows(40000, 1024, 65)
+    q = unit_rows(6, 1024, 66)
+    order = np.argsort(xb @ q[0])
+    xb = np.ascontiguousarray(xb[order])
+    xq = np.concatenate([q, queries_for(xb, 10, 67)])
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    check(index, xb, xq, 30)
+
+
+@pytest.mark.parametrize("d", [64, 512, 4096])
+def test_wide_other_widths(b2r, d):
+    xb = unit_rows(20000, d, 68)
+    index = b2r.FlatIPIndex(d)
+    index.add(xb)
+    check(index, xb, queries_for(xb, 70, 69), 10)
