@@ -279,6 +279,118 @@ __device__ __forceinline__ void block_select_lists(const K* __restrict__ src, in
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// device: the kp largest of n UNSORTED keys in shared memory, by histogram (O(n) instead of a full
+// bitonic sort).  Whole-CTA routine; leaves the result sorted descending in out[0..) (zero padded up
+// to at least kp entries).
+//   keys : shared, n keys (u64 ordered keys or u32 ordered scores); clobbered only by the fallback
+//   hist : shared u32[kSelBins + 4]
+//   out  : shared, out_cap keys (power of two, >= 2 kp)
+// Keys are binned linearly over [min, max] of their score bits; the bins are summed from the top until
+// kp keys are covered, the keys of those bins (a little over kp) are compacted into `out` and sorted.
+// If they do not fit (heavy ties) the whole array is sorted instead.
+// ----------------------------------------------------------------------------------------------
+static const int kSelBins = 2048;
+
+__device__ __forceinline__ u32 key_score_bits(u64 k) { return static_cast<u32>(k >> 32); }
+__device__ __forceinline__ u32 key_score_bits(u32 k) { return k; }
+
+template <class K>
+__device__ __forceinline__ void block_topk_hist(K* keys, int n, int n_pow2_cap, int kp, u32* hist, K* out, int out_cap) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (n <= out_cap) {  // small input: sort it directly
+    int p = 2;
+    while (p < n || p < kp) p <<= 1;
+    for (int i = tid; i < p; i += nt) out[i] = i < n ? keys[i] : static_cast<K>(0);
+    __syncthreads();
+    block_sort_desc(out, p);
+    return;
+  }
+  u32* s_lo = hist + kSelBins;      // min score bits
+  u32* s_hi = hist + kSelBins + 1;  // max score bits
+  u32* s_bin = hist + kSelBins + 2; // threshold bin
+  u32* s_cnt = hist + kSelBins + 3; // survivors
+  for (int i = tid; i < kSelBins; i += nt) hist[i] = 0;
+  if (tid == 0) {
+    *s_lo = 0xFFFFFFFFu;
+    *s_hi = 0u;
+    *s_cnt = 0u;
+  }
+  __syncthreads();
+  {
+    u32 lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < n; i += nt) {
+      const u32 s = key_score_bits(keys[i]);
+      lo = s < lo ? s : lo;
+      hi = s > hi ? s : hi;
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((tid & 31) == 0) {
+      atomicMin(s_lo, lo);
+      atomicMax(s_hi, hi);
+    }
+  }
+  __syncthreads();
+  const u32 lo = *s_lo;
+  const u32 range = *s_hi - lo;
+  int sh = 0;
+  while ((range >> sh) >= static_cast<u32>(kSelBins)) ++sh;
+  for (int i = tid; i < n; i += nt) atomicAdd(&hist[(key_score_bits(keys[i]) - lo) >> sh], 1u);
+  __syncthreads();
+  if (tid < 32) {  // one warp walks the bins from the top: lane l owns bins [2048 - 64 (l + 1), 2048 - 64 l)
+    constexpr int per = kSelBins / 32;
+    const int top = kSelBins - per * tid;
+    u32 sum = 0;
+    for (int b = top - 1; b >= top - per; --b) sum += hist[b];
+    u32 incl = sum;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      const u32 v = __shfl_up_sync(0xffffffffu, incl, m);
+      if (tid >= m) incl += v;
+    }
+    const u32 before = incl - sum;  // keys in the bins above this lane's
+    if (before < static_cast<u32>(kp) && incl >= static_cast<u32>(kp)) {
+      u32 acc = before;
+      int b = top - 1;
+      for (; b > top - per; --b) {
+        acc += hist[b];
+        if (acc >= static_cast<u32>(kp)) break;
+      }
+      *s_bin = static_cast<u32>(b);
+    }
+    if (tid == 31 && incl < static_cast<u32>(kp)) *s_bin = 0u;  // fewer than kp keys: keep everything
+  }
+  __syncthreads();
+  const u32 bstar = *s_bin;
+  for (int i = tid; i < n; i += nt) {
+    const K v = keys[i];
+    if (((key_score_bits(v) - lo) >> sh) >= bstar) {
+      const u32 pos = atomicAdd(s_cnt, 1u);
+      if (pos < static_cast<u32>(out_cap)) out[pos] = v;
+    }
+  }
+  __syncthreads();
+  const u32 cnt = *s_cnt;
+  if (cnt <= static_cast<u32>(out_cap)) {
+    int p = 2;
+    while (p < static_cast<int>(cnt) || p < kp) p <<= 1;
+    for (int i = cnt + tid; i < p; i += nt) out[i] = 0;
+    __syncthreads();
+    block_sort_desc(out, p);
+    return;
+  }
+  // too many keys share the threshold bin (ties): sort everything
+  int p = 2;
+  while (p < n) p <<= 1;
+  if (p > n_pow2_cap) p = n_pow2_cap;
+  for (int i = n + tid; i < p; i += nt) keys[i] = 0;
+  __syncthreads();
+  block_sort_desc(keys, p);
+  for (int i = tid; i < out_cap; i += nt) out[i] = i < p ? keys[i] : static_cast<K>(0);
+  __syncthreads();
+}
+
 // write buf[0..k) (sorted keys) as (score, int64 id) with faiss padding for empty slots
 __device__ __forceinline__ void block_emit_keys(const u64* buf, int k, float* D, long long* I,
                                                 long long id_offset) {

@@ -72,7 +72,13 @@ struct GemmArgs {
 // prep: split the queries into tf32 hi / lo parts: Bs[0][q][:] = hi, Bs[1][q][:] = lo; rows nq..N-1 zero
 // ---------------------------------------------------------------------------------------------
 __global__ void gemm_split_queries_kernel(const float* __restrict__ q, int nq, int N, int d, float* __restrict__ Bs,
-                                          int split) {
+                                          int split, const u32* __restrict__ active) {
+  if (active) {  // redo pass: nothing to prepare unless some query is flagged
+    const int lane = threadIdx.x & 31;
+    bool any = false;
+    for (int c = lane; c < nq; c += 32) any |= active[c] != 0u;
+    if (!__any_sync(0xffffffffu, any)) return;
+  }
   const long long total = static_cast<long long>(N) * d;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -133,6 +139,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   u32* tmem_slot = flags + 2;
   u64* lists = reinterpret_cast<u64*>(tmem_slot + 2);  // [N][cap]
 
+  // queries this launch has to answer; none (all redo flags clear) -> leave before touching TMEM
+  u64 active_mask = (a.nq >= 64) ? ~0ull : ((1ull << a.nq) - 1ull);
+  if (a.active) {
+    const u32 f0 = lane < a.nq ? a.active[lane] : 0u;
+    const u32 f1 = lane + 32 < a.nq ? a.active[lane + 32] : 0u;
+    const u64 m = static_cast<u64>(__ballot_sync(0xffffffffu, f0 != 0u)) |
+                  (static_cast<u64>(__ballot_sync(0xffffffffu, f1 != 0u)) << 32);
+    active_mask &= m;
+    if (!active_mask) return;  // uniform over the CTA
+  }
   if (tid == 0) {
     for (int s = 0; s < R; ++s) {
       mbar_init(&full[s], 1);
@@ -158,14 +174,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     for (int i = tid; i < a.n_bins; i += blockDim.x) hist_s[i] = 0;
   }
   if (warp == 1) tc_alloc(tmem_slot, kTmemCols);
-  // queries this launch has to answer; none (all flags clear) -> skip the scan entirely
-  u64 active_mask = (a.nq >= 64) ? ~0ull : ((1ull << a.nq) - 1ull);
-  if (a.active) {
-    u64 m = 0;
-    for (int c = 0; c < a.nq; ++c) m |= a.active[c] ? (1ull << c) : 0ull;
-    active_mask &= m;
-  }
-  const long long n_tiles = active_mask ? a.n_tiles : 0;
+  const long long n_tiles = a.n_tiles;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -500,7 +509,7 @@ __global__ void max_row_norm2_kernel(const float* __restrict__ xb, long long n, 
 // Exact fp32 rescoring of the k' candidates of every query, final top-k, and the exactness check.
 // One CTA per query; a warp scores one candidate at a time with the SIMT scan's arithmetic
 // (lanes over 128-bit chunks, even / odd accumulators, xor butterfly).
-__global__ void __launch_bounds__(256) gemm_rescore_kernel(const float* __restrict__ xb, int d,
+__global__ void __launch_bounds__(512) gemm_rescore_kernel(const float* __restrict__ xb, int d,
                                                            const float* __restrict__ q, const float* __restrict__ Dp,
                                                            const long long* __restrict__ Ip, int kp, int k,
                                                            const float* __restrict__ max_norm2, float* __restrict__ D,
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(256) gemm_rescore_kernel(const float* __restri
   const int qi = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* qv = q + static_cast<size_t>(qi) * d;
   const long long* cand = Ip + static_cast<size_t>(qi) * kp;
-  keys[tid] = 0;
+  if (tid < 256) keys[tid] = 0;
   if (warp == 0) {
     float acc = 0.f;
     for (int c = lane; c < d; c += 32) acc = fmaf(qv[c], qv[c], acc);
@@ -521,21 +530,36 @@ __global__ void __launch_bounds__(256) gemm_rescore_kernel(const float* __restri
   }
   __syncthreads();
   const bool vec4 = (d & 3) == 0;
-  for (int c = warp; c < kp; c += 8) {
+  const int n_warps = blockDim.x >> 5;
+  for (int c = warp; c < kp; c += n_warps) {
     const long long id = cand[c];
     if (id < 0) continue;  // warp-uniform
     const float* row = xb + id * d;
     float a0 = 0.f, a1 = 0.f;
     if (vec4) {
-      int j = 0;
-      for (int ch = lane; ch < (d >> 2); ch += 32, ++j) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(row) + ch);
-        const float4 y = *reinterpret_cast<const float4*>(qv + ch * 4);
-        float& acc = (j & 1) ? a1 : a0;
-        acc = fmaf(x.x, y.x, acc);
-        acc = fmaf(x.y, y.y, acc);
-        acc = fmaf(x.z, y.z, acc);
-        acc = fmaf(x.w, y.w, acc);
+      // chunk j = ch / 32 goes to accumulator j & 1 (the SIMT scan's order); four loads in flight per lane
+      const int n4 = d >> 2;
+      const float4* row4 = reinterpret_cast<const float4*>(row);
+      const float4* q4 = reinterpret_cast<const float4*>(qv);
+      for (int base = 0; base < n4; base += 128) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ch = base + u * 32 + lane;
+          x[u] = ch < n4 ? __ldg(row4 + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ch = base + u * 32 + lane;
+          if (ch < n4) {
+            const float4 y = q4[ch];
+            float& acc = (u & 1) ? a1 : a0;
+            acc = fmaf(x[u].x, y.x, acc);
+            acc = fmaf(x[u].y, y.y, acc);
+            acc = fmaf(x[u].z, y.z, acc);
+            acc = fmaf(x[u].w, y.w, acc);
+          }
+        }
       }
     } else {
       for (int ch = lane; ch < d; ch += 32) a0 = fmaf(__ldg(row + ch), qv[ch], a0);
@@ -625,7 +649,7 @@ static int gemm_scan(const float* rows, long long n, int d, const float* q_dev, 
   const int tile_rows = sub * kTileM;
   const long long n_tiles = (n + tile_rows - 1) / tile_rows;
   const int grid = static_cast<int>(std::min<long long>(n_tiles, num_sms));
-  gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit, terms == 3 ? 1 : 0);
+  gemm_split_queries_kernel<<<64, 256, 0, stream>>>(q_dev, nq, N, d, bsplit, terms == 3 ? 1 : 0, active);
   B2R_CUDA(cudaGetLastError());
   CUtensorMap ma, mb;
   int rc = make_map_2d(&ma, rows, static_cast<unsigned long long>(d), static_cast<unsigned long long>(n), kSlabK, kTileM);
@@ -759,7 +783,7 @@ int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev,
       *launches += 3;
     }
   }
-  gemm_rescore_kernel<<<nq, 256, 0, stream>>>(rows, d, q_dev, Dp, Ip, kp, k, max_norm2_dev, D_dev, I_dev, id_offset, redo,
+  gemm_rescore_kernel<<<nq, 512, 0, stream>>>(rows, d, q_dev, Dp, Ip, kp, k, max_norm2_dev, D_dev, I_dev, id_offset, redo,
                                               wide ? ovf : nullptr);
   B2R_CUDA(cudaGetLastError());
   *launches += 1;
@@ -852,7 +876,7 @@ int cosine_stats_run(const float* rows_dev, long long n, int d, long long col_be
     const size_t smem = stages * raw_stage + fixed;
     for (long long c0 = (col_begin / N) * N; c0 < col_end && rc == B2R_OK; c0 += N) {
       const int ncols = static_cast<int>(std::min<long long>(N, n - c0));
-      gemm_split_queries_kernel<<<64, 256, 0, stream>>>(xn + c0 * d, ncols, N, d, bsplit, 1);
+      gemm_split_queries_kernel<<<64, 256, 0, stream>>>(xn + c0 * d, ncols, N, d, bsplit, 1, nullptr);
       GemmArgs a;
       a.n = n;
       a.d = d;

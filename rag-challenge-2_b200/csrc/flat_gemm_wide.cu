@@ -260,24 +260,26 @@ __global__ void wide_prep_kernel(const float* __restrict__ q, int nq, int N, int
 __global__ void __launch_bounds__(1024) wide_tau_kernel(const u32* __restrict__ premax, int pm_stride, int m, int kp,
                                                         float* __restrict__ tauf) {
   __shared__ u32 buf[kPremaxMax];
+  __shared__ u32 hist[kSelBins + 4];
+  __shared__ u32 top[512];
   const int q = blockIdx.x;
-  int p = 2;
-  while (p < m) p <<= 1;
-  for (int i = threadIdx.x; i < p; i += blockDim.x) buf[i] = i < m ? premax[static_cast<size_t>(q) * pm_stride + i] : 0u;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = premax[static_cast<size_t>(q) * pm_stride + i];
   __syncthreads();
-  block_sort_desc(buf, p);
+  block_topk_hist(buf, m, kPremaxMax, kp, hist, top, 512);
   if (threadIdx.x == 0) {
-    const u32 o = kp <= p ? buf[kp - 1] : 0u;
+    const u32 o = top[kp - 1];
     tauf[q] = o > 4u ? ordered_to_float(o - 4u) : __int_as_float(0xff800000);  // -inf: keep every row
   }
 }
 
-// one CTA per query: gather the per-CTA lists, sort, emit the k' best (approximate score, local id)
+// one CTA per query: gather the per-CTA lists and select the k' best (approximate score, local id)
 __global__ void __launch_bounds__(1024) wide_select_kernel(const u64* __restrict__ glists, const u32* __restrict__ gcnt,
                                                            int n_ctas, int N, int kp, float* __restrict__ Dp,
                                                            long long* __restrict__ Ip, u32* __restrict__ ovf) {
   extern __shared__ __align__(16) unsigned char sel_smem[];
   u64* buf = reinterpret_cast<u64*>(sel_smem);
+  __shared__ u64 top[512];
+  __shared__ u32 hist[kSelBins + 4];
   __shared__ u32 s_cnt;
   const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) s_cnt = 0;
@@ -297,12 +299,8 @@ __global__ void __launch_bounds__(1024) wide_select_kernel(const u64* __restrict
     if (tid == 0) ovf[q] = 1u;
     total = kGatherCap;
   }
-  int p = 2;
-  while (p < static_cast<int>(total) || p < kp) p <<= 1;
-  for (int i = total + tid; i < p; i += blockDim.x) buf[i] = 0;
-  __syncthreads();
-  block_sort_desc(buf, p);
-  block_emit_keys(buf, kp, Dp + static_cast<size_t>(q) * kp, Ip + static_cast<size_t>(q) * kp, 0);
+  block_topk_hist(buf, static_cast<int>(total), kGatherCap, kp, hist, top, 512);
+  block_emit_keys(top, kp, Dp + static_cast<size_t>(q) * kp, Ip + static_cast<size_t>(q) * kp, 0);
 }
 
 template <int N, int SUB>
