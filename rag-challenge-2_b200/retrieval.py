@@ -230,6 +230,20 @@ def _load_report_cached(document_path: Path, index_path: Path, device: int):
     return document, vector_db
 
 
+def _resolve_devices(device):
+    if isinstance(device, str):
+        if device != "auto":
+            raise ValueError("device must be a GPU ordinal, a list of ordinals or 'auto'")
+        from . import _lib
+
+        return list(range(max(1, _lib.device_count())))
+    if isinstance(device, (list, tuple)):
+        if not device:
+            raise ValueError("device list is empty")
+        return [int(d) for d in device]
+    return [int(device)]
+
+
 def _page_text_lookup(pages):
     """page number -> first page dict with that number (reference does a linear next(...) scan per
     hit, :1145; same result)."""
@@ -355,7 +369,10 @@ class VectorRetriever:
         self.vector_db_dir = Path(vector_db_dir)
         self.documents_dir = Path(documents_dir)
         self.subset_path = subset_path
-        self.device = device
+        # device: one GPU ordinal, a list of ordinals, or "auto" (every visible GPU).  Report i (sorted by
+        # file stem, so J2020..J2025 are stable) lives on devices[i % len(devices)]: one year-DB per GPU.
+        self.devices = _resolve_devices(device)
+        self.device = self.devices[0]
         self.year_lookup = _load_year_lookup(subset_path) if subset_path else {}
         self.all_dbs = self._load_dbs()
         dim = self.all_dbs[0]["vector_db"].d if self.all_dbs else 1024
@@ -369,6 +386,27 @@ class VectorRetriever:
         self.max_hops = max_hops
         self.neighbor_k = neighbor_k
 
+    @classmethod
+    def from_reports(cls, all_dbs, qwen=None, llm=None, use_hyde=False, use_multi_query=False, parallel_workers=8,
+                     multi_query_methods=None, retrieval_method="basic", max_hops=4, neighbor_k=30):
+        """A retriever over reports that are already resident: all_dbs = [{"name", "vector_db", "document"}]
+        (the structure `_load_dbs` builds and callers mutate, reference :529-534).  Used for corpora generated
+        or sharded straight into HBM."""
+        self = cls.__new__(cls)
+        self.vector_db_dir = self.documents_dir = self.subset_path = None
+        self.devices = sorted({getattr(r["vector_db"], "device", 0) for r in all_dbs}) or [0]
+        self.device = self.devices[0]
+        self.year_lookup = {}
+        self.all_dbs = list(all_dbs)
+        dim = self.all_dbs[0]["vector_db"].d if self.all_dbs else 1024
+        self.qwen = qwen if qwen is not None else _default_qwen(dim)
+        self.llm = llm
+        self.use_hyde, self.use_multi_query = use_hyde, use_multi_query
+        self.parallel_workers = max(1, parallel_workers)
+        self.multi_query_methods = multi_query_methods or {"synonym": True, "subquestion": True, "variant": True}
+        self.retrieval_method, self.max_hops, self.neighbor_k = retrieval_method, max_hops, neighbor_k
+        return self
+
     def _load_year_lookup(self) -> dict:
         return _load_year_lookup(self.subset_path)
 
@@ -377,13 +415,16 @@ class VectorRetriever:
         whose JSON or index cannot be read is logged and skipped."""
         all_dbs = []
         index_files = {p.stem: p for p in self.vector_db_dir.glob("*.faiss")}
-        for document_path in self.documents_dir.glob("*.json"):
+        document_paths = list(self.documents_dir.glob("*.json"))
+        placement = {p.stem: self.devices[i % len(self.devices)]
+                     for i, p in enumerate(sorted(document_paths, key=lambda p: p.stem))}
+        for document_path in document_paths:
             stem = document_path.stem
             if stem not in index_files:
                 _log.warning(f"No matching vector DB found for document {document_path.name}")
                 continue
             try:
-                document, vector_db = _load_report_cached(document_path, index_files[stem], self.device)
+                document, vector_db = _load_report_cached(document_path, index_files[stem], placement[stem])
             except Exception as e:  # noqa: BLE001
                 _log.error(f"Error loading report {document_path.name}: {e}")
                 continue
@@ -599,7 +640,12 @@ class VectorRetriever:
         "algorithm_specific_results"} exactly as the reference's per-task return value (:1444-1473)."""
         document, vector_db = report["document"], report["vector_db"]
         chunks = document["content"]["chunks"]
-        pages = _page_text_lookup(document["content"]["pages"])
+        # page lookup built once per resident report (rebuilt if the caller swapped the pages list)
+        cached = report.get("_page_lookup")
+        if cached is None or cached[0] != id(document["content"]["pages"]):
+            cached = report["_page_lookup"] = (id(document["content"]["pages"]),
+                                               _page_text_lookup(document["content"]["pages"]))
+        pages = cached[1]
         sha1 = document["metainfo"]["sha1_name"]
         actual_top_n = min(top_n, len(chunks))
         if actual_top_n == 0:
@@ -719,6 +765,75 @@ class VectorRetriever:
                                  use_multi_query: bool = None, progress_callback=None,
                                  selected_years: List[int] = None, multi_query_config: Optional[Dict[str, bool]] = None,
                                  retrieval_method: str = "basic", max_hops: int = 2, neighbor_k: int = 10):
+        plan = self._prepare(company_name, query, use_hyde, use_multi_query, progress_callback, selected_years,
+                             multi_query_config, retrieval_method, max_hops, neighbor_k)
+        if progress_callback:
+            progress_callback("🔎 向量检索中...", 45)
+        t0 = time.time()
+        per_report = self._search_reports(plan["reports"], [plan["query_items"]] * len(plan["reports"]), top_n,
+                                          return_parent_pages, plan["retrieval_method"], plan["max_hops"],
+                                          plan["neighbor_k"])
+        plan["timing"]["vector_search"] = time.time() - t0
+        return self._finalize(plan, per_report, top_n, progress_callback)
+
+    def retrieve_batch(self, company_name: str, queries: List[str], top_n: int = 3, return_parent_pages: bool = False,
+                       use_hyde: bool = None, use_multi_query: bool = None, selected_years=None,
+                       multi_query_config: Optional[Dict[str, bool]] = None, retrieval_method: str = "basic",
+                       max_hops: int = 2, neighbor_k: int = 10) -> List[Dict]:
+        """A whole question batch (the reference loops over questions, src/questions_processing.py:1104-1138,
+        and re-creates the retriever per question).  Returns [retrieve_by_company_name(q) for q in queries],
+        but every report is searched ONCE with the embeddings of all the questions routed to it (one
+        tensor-core batch per year-DB, the year-DBs on their own GPUs in parallel).  `selected_years` is one
+        list for the batch, or a list with one entry (list or None) per question."""
+        per_question_years = (isinstance(selected_years, (list, tuple)) and len(selected_years) == len(queries)
+                              and all(y is None or isinstance(y, (list, tuple)) for y in selected_years))
+        plans = []
+        for i, query in enumerate(queries):
+            years = selected_years[i] if per_question_years else selected_years
+            plans.append(self._prepare(company_name, query, use_hyde, use_multi_query, None, years, multi_query_config,
+                                       retrieval_method, max_hops, neighbor_k))
+        if any(p["retrieval_method"] in ("ssg", "triangulation", "hybrid_expansion") for p in plans):
+            # graph walks are sequential per (question, report): no cross-question batching
+            out = []
+            for p in plans:
+                t0 = time.time()
+                per_report = self._search_reports(p["reports"], [p["query_items"]] * len(p["reports"]), top_n,
+                                                  return_parent_pages, p["retrieval_method"], p["max_hops"],
+                                                  p["neighbor_k"])
+                p["timing"]["vector_search"] = time.time() - t0
+                out.append(self._finalize(p, per_report, top_n, None))
+            return out
+        # group the (question, expansion) embeddings by report
+        reports, items, owners = [], [], []   # owners[r] = [(plan index, n_items)]
+        slot = {}
+        for pi, p in enumerate(plans):
+            for report in p["reports"]:
+                r = slot.get(id(report))
+                if r is None:
+                    r = slot[id(report)] = len(reports)
+                    reports.append(report)
+                    items.append([])
+                    owners.append([])
+                items[r].extend(p["query_items"])
+                owners[r].append((pi, len(p["query_items"])))
+        t0 = time.time()
+        searched = self._search_reports(reports, items, top_n, return_parent_pages, "basic", max_hops, neighbor_k)
+        elapsed = time.time() - t0
+        per_plan = [[] for _ in plans]
+        for r, res in enumerate(searched):
+            pos = 0
+            for pi, cnt in owners[r]:
+                per_plan[pi].append(None if res is None else res[pos: pos + cnt])
+                pos += cnt
+        out = []
+        for p, per_report in zip(plans, per_plan):
+            p["timing"]["vector_search"] = elapsed / max(1, len(plans))
+            out.append(self._finalize(p, per_report, top_n, None))
+        return out
+
+    def _prepare(self, company_name, query, use_hyde, use_multi_query, progress_callback, selected_years,
+                 multi_query_config, retrieval_method, max_hops, neighbor_k):
+        """Routing, expansion and embedding of one question (reference :813-1101)."""
         timing_info = {"hyde_expansion": 0.0, "multi_query_expansion": 0.0, "embedding_generation": 0.0,
                        "vector_search": 0.0}
         expansion_texts = {"hyde_text": None, "multi_query_texts": [], "glossary_context": None,
@@ -753,22 +868,44 @@ class VectorRetriever:
         timing_info["embedding_generation"] = time.time() - t0
         if not query_embeddings:
             raise ValueError("Failed to generate embeddings for all queries.")
+        return {"reports": matching_reports, "query_items": list(query_embeddings.items()), "timing": timing_info,
+                "expansion_texts": expansion_texts, "retrieval_method": retrieval_method, "max_hops": max_hops,
+                "neighbor_k": neighbor_k}
 
-        if progress_callback:
-            progress_callback("🔎 向量检索中...", 45)
-        query_items = list(query_embeddings.items())
+    def _search_reports(self, reports, items_per_report, top_n, return_parent_pages, retrieval_method, max_hops,
+                        neighbor_k):
+        """_search_report for every report; reports on different GPUs run concurrently on a thread pool
+        (ctypes releases the GIL during the search — the reference's ThreadPoolExecutor fan-out, :1498-1504,
+        at report granularity).  Returns per report the (query_text, result) list, or None if it failed."""
+        def one(args):
+            report, query_items = args
+            try:
+                return self._search_report(report, query_items, top_n, return_parent_pages, retrieval_method,
+                                           max_hops, neighbor_k)
+            except Exception as e:  # noqa: BLE001 - a failed report must not fail the retrieval (:1441-1442)
+                self._safe_print(f"[ERROR] Vector search failed in report {report.get('name')}: {e}")
+                return None
+
+        work = list(zip(reports, items_per_report))
+        gpus = {getattr(r["vector_db"], "device", 0) for r in reports}
+        workers = min(self.parallel_workers, len(work), max(1, len(gpus)))
+        if workers <= 1:
+            return [one(w) for w in work]
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            return list(pool.map(one, work))  # report order, not completion order
+
+    def _finalize(self, plan, per_report, top_n, progress_callback):
+        """Aggregation over reports and queries, fusion, sort, cut (reference :1552-1819)."""
+        retrieval_method, max_hops, neighbor_k = plan["retrieval_method"], plan["max_hops"], plan["neighbor_k"]
         aggregated = {}
         traversal_details = []
         algo = {"ssg_new_chunks": [], "triangulation_new_chunks": [], "basic_count": 0,
                 "ssg_stats": {"total_expanded": 0, "new_only": 0, "in_basic_top50": 0},
                 "triangulation_stats": {"total_expanded": 0, "new_only": 0, "in_basic_top50": 0}}
-        t0 = time.time()
-        for report in matching_reports:
-            try:
-                per_query = self._search_report(report, query_items, top_n, return_parent_pages, retrieval_method,
-                                                max_hops, neighbor_k)
-            except Exception as e:  # noqa: BLE001 - a failed report must not fail the retrieval (:1441-1442)
-                self._safe_print(f"[ERROR] Vector search failed in report {report.get('name')}: {e}")
+        for per_query in per_report:
+            if per_query is None:
                 continue
             for query_text, result in per_query:
                 if not result:
@@ -788,7 +925,6 @@ class VectorRetriever:
                 else:
                     hits = result
                 self._aggregate(aggregated, hits, query_text)
-        timing_info["vector_search"] = time.time() - t0
 
         final_results = [self._final_record(info) for info in aggregated.values()]
         final_results = sorted(final_results, key=lambda x: x["vector_similarity"], reverse=True)
@@ -811,7 +947,7 @@ class VectorRetriever:
                 "ssg_new_chunks": algo["ssg_new_chunks"],
                 "triangulation_new_chunks": algo["triangulation_new_chunks"],
                 "ssg_stats": algo["ssg_stats"], "triangulation_stats": algo["triangulation_stats"]}
-        return {"results": final_results, "timing": timing_info, "expansion_texts": expansion_texts,
+        return {"results": final_results, "timing": plan["timing"], "expansion_texts": plan["expansion_texts"],
                 "retrieval_details": retrieval_details, "initial_retrieval_results": all_initial_results,
                 "algorithm_contribution": algorithm_contribution}
 

@@ -154,3 +154,59 @@ def bm25_idf_from_df(df, corpus_size, epsilon=0.25):
     eps = epsilon * average_idf
     idf[present & (idf < 0)] = eps
     return idf, average_idf
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic year databases (BASELINE config 2: J2020..J2025, one per GPU)
+# ------------------------------------------------------------------------------------------------
+class _LazySeq:
+    """Sequence of n records produced on demand (a 2M-chunk report as 2M dicts would cost GBs of host RAM)."""
+
+    def __init__(self, n, make):
+        self._n, self._make = int(n), make
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._make(i)
+
+    def __iter__(self):
+        return (self._make(i) for i in range(self._n))
+
+
+class _LazyPages(dict):
+    """page number -> page record, materialised on first use (what retrieval._page_text_lookup returns)."""
+
+    def __init__(self, n_pages, make):
+        super().__init__()
+        self._n, self._make = int(n_pages), make
+
+    def __missing__(self, page_no):
+        if not 1 <= int(page_no) <= self._n:
+            raise KeyError(page_no)
+        rec = self[page_no] = self._make(int(page_no))
+        return rec
+
+
+def synthetic_year_report(name, company, n_chunks, vector_db, chunks_per_page=8):
+    """A report dict {"name", "vector_db", "document"} in the chunked-report schema whose
+    chunk / page records are generated on demand: chunk i sits on page i // chunks_per_page + 1."""
+    n_pages = (n_chunks + chunks_per_page - 1) // chunks_per_page
+
+    def chunk(i):
+        return {"page": i // chunks_per_page + 1, "length_tokens": 300, "text": f"{name} chunk {i}", "id": i,
+                "type": "content"}
+
+    def page(p):
+        return {"page": p, "text": f"{name} page {p}"}
+
+    document = {"metainfo": {"sha1_name": name, "company_name": company, "pages_amount": n_pages},
+                "content": {"pages": _LazySeq(n_pages, lambda j: page(j + 1)), "chunks": _LazySeq(n_chunks, chunk)}}
+    return {"name": name, "vector_db": vector_db, "document": document,
+            "_page_lookup": (id(document["content"]["pages"]), _LazyPages(n_pages, page))}

@@ -119,3 +119,80 @@ def test_resident_cache_shares_reports(env):
     ia = {db["name"]: db["vector_db"] for db in a.all_dbs}
     ib = {db["name"]: db["vector_db"] for db in b.all_dbs}
     assert all(ia[k] is ib[k] for k in ia)   # one resident index per report per process
+
+
+def _assert_same_retrieval(got, want):
+    """Equal up to the oracle index's own batch-size noise: numpy's fp32 GEMV (one query) and GEMM (a batch)
+    differ in the last bit, which can flip a score's 4th decimal; everything else must be identical."""
+    got, want = gu.canon_result(got), gu.canon_result(want)
+    assert got.keys() == want.keys()
+    for key in got:
+        if key not in ("results", "initial_retrieval_results"):
+            assert got[key] == want[key], key
+            continue
+        assert len(got[key]) == len(want[key])
+
+        def ident(rec):
+            return json.dumps({k: v for k, v in rec.items() if k not in ("vector_similarity", "max_original_similarity")},
+                              sort_keys=True, ensure_ascii=False)
+
+        g, w = sorted(got[key], key=ident), sorted(want[key], key=ident)
+        for a, b in zip(g, w):
+            assert ident(a) == ident(b)
+            for f in ("vector_similarity", "max_original_similarity"):
+                assert abs(a[f] - b[f]) <= 1.5e-4 * max(1.0, a["hit_count"]), (f, a[f], b[f])
+        vals = [rec["vector_similarity"] for rec in got[key]]
+        assert all(x >= y for x, y in zip(vals, vals[1:]))
+
+
+def test_retrieve_batch_equals_per_question_calls(env):
+    """retrieve_batch (one batched search per report for the whole question batch) must return exactly
+    what per-question retrieve_by_company_name calls return — same records, order and scores."""
+    R, paths, golden = env
+    qs = list(corpus.QUESTIONS) * 2
+    years = [None, [2024], [2023, 2024, 2025], [1999], [2022], None, [2020, 2021], [2025]][: len(qs)]
+    years += [None] * (len(qs) - len(years))
+    r = R.VectorRetriever(paths["vector_db_dir"], paths["documents_dir"], subset_path=paths["subset_path"],
+                          qwen=stubs.ScriptedQwen())
+    for kw in (dict(use_hyde=False, use_multi_query=False),
+               dict(use_hyde=True, use_multi_query=True, multi_query_config=cases.MQ_ALL, return_parent_pages=True)):
+        got = r.retrieve_batch(corpus.COMPANY, qs, top_n=10, selected_years=years, **kw)
+        assert len(got) == len(qs)
+        for q, y, g in zip(qs, years, got):
+            want = r.retrieve_by_company_name(corpus.COMPANY, q, top_n=10, selected_years=y, **kw)
+            _assert_same_retrieval(g, want)
+    # one year list for the whole batch, and a graph method (falls back to the per-question loop)
+    got = r.retrieve_batch(corpus.COMPANY, qs[:3], top_n=5, selected_years=[2023, 2024], use_hyde=False,
+                           use_multi_query=False, retrieval_method="ssg", max_hops=3, neighbor_k=8)
+    for q, g in zip(qs[:3], got):
+        want = r.retrieve_by_company_name(corpus.COMPANY, q, top_n=5, selected_years=[2023, 2024], use_hyde=False,
+                                          use_multi_query=False, retrieval_method="ssg", max_hops=3, neighbor_k=8)
+        assert gu.canon_result(g) == gu.canon_result(want)
+    with pytest.raises(ValueError, match="No report found"):
+        r.retrieve_batch("nobody", qs[:2], top_n=3, use_hyde=False, use_multi_query=False)
+
+
+def test_device_placement_round_robin(env):
+    """device=[...]: report i (sorted by stem) is loaded on devices[i % n] — one year-DB per GPU."""
+    R, paths, golden = env
+    seen = {}
+    orig = R.flat_index.read_index
+
+    def spy(path, device=0):
+        seen[path.stem if hasattr(path, "stem") else str(path)] = device
+        return orig(path, device=device)
+
+    mp = pytest.MonkeyPatch()
+    mp.setattr(R.flat_index, "read_index", spy)
+    R.clear_resident_cache()
+    try:
+        r = R.VectorRetriever(paths["vector_db_dir"], paths["documents_dir"], subset_path=paths["subset_path"],
+                              qwen=stubs.ScriptedQwen(), device=[0, 1, 2])
+        stems = sorted(seen)
+        assert [seen[s] for s in stems] == [i % 3 for i in range(len(stems))]
+        assert r.devices == [0, 1, 2] and r.device == 0
+    finally:
+        mp.undo()
+        R.clear_resident_cache()
+    with pytest.raises(ValueError):
+        R.VectorRetriever(paths["vector_db_dir"], paths["documents_dir"], device=[])

@@ -99,3 +99,28 @@ def test_retrieve_all_and_threads(env):
         outs = list(ex.map(run, names))
     for name, got in zip(names, outs):
         assert_records_close(got["results"], gu.canon_result(golden["vector"][name])["results"])
+
+
+def test_retrieve_batch_on_resident_year_dbs(b2r):
+    """Config-2 shape at CI size: six synthetic year-DBs resident in HBM (lazy chunk / page records), a
+    question batch routed by year; retrieve_batch (one tensor-core batch per DB) == per-question calls."""
+    import torch
+
+    from rag_challenge_2_b200 import retrieval, synth
+
+    years = [2020, 2021, 2022, 2023, 2024, 2025]
+    reports = []
+    for i, y in enumerate(years):
+        lo = i * 4 * synth.ROW_BLOCK
+        rows = synth.dense_rows_torch(lo, lo + 20000 + 3000 * i, 1024, torch.device("cuda", 0))
+        reports.append(synth.synthetic_year_report(f"J{y}", "金盘科技", rows.shape[0], b2r.FlatIPIndex.from_device_tensor(rows)))
+    r = retrieval.VectorRetriever.from_reports(reports, qwen=retrieval.HashEmbedder(1024))
+    qs = [f"{years[i % 6]}年的第{i}个指标" for i in range(40)]
+    sel = [None if i % 3 == 0 else ([2024] if i % 3 == 1 else [2023, 2024, 2025]) for i in range(40)]
+    got = r.retrieve_batch("金盘科技", qs, top_n=30, selected_years=sel, use_hyde=False, use_multi_query=False)
+    for q, y, g in zip(qs, sel, got):
+        want = r.retrieve_by_company_name("金盘科技", q, top_n=30, selected_years=y, use_hyde=False, use_multi_query=False)
+        assert_records_close(g["results"], want["results"])
+        n_dbs = 6 if y is None else len(y)
+        assert len(g["initial_retrieval_results"]) == 30 * n_dbs
+        assert {rec["source_sha1"] for rec in g["results"]} <= {f"J{v}" for v in (y or years)}
