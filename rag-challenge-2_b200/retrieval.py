@@ -548,6 +548,94 @@ class VectorRetriever:
         details["total_hops"] = len(details["hops"])
         return {"results": results, "traversal_details": details}
 
+    def _walks_lockstep(self, vector_db, walks, max_hops=4, neighbor_k=30):
+        """Many greedy walks over one report, advanced one hop at a time (next-row f3).
+
+        walks: [{"kind": "ssg" | "triangulation", "anchor_id", "anchor_vec", "query_vec" (triangulation)}].
+        Returns, per walk, exactly what _ssg_search / _triangulation_search return.  The walks are
+        independent, so hop h of all live walks is ONE batched search (k = neighbor_k + 1) plus ONE
+        batched row gather, instead of one search and up to neighbor_k + 1 reconstruct round trips per
+        walk and hop (reference :622-631, :730-738 — hybrid_expansion runs 30 walks per query and report)."""
+        states = []
+        for w in walks:
+            aid, avec = int(w["anchor_id"]), w["anchor_vec"]
+            if w["kind"] == "ssg":
+                states.append({"kind": "ssg", "visited": {aid}, "results": [(1.0, aid)], "cur_idx": aid, "cur_vec": avec,
+                               "previous": 1.0, "alive": True,
+                               "details": {"anchor": {"idx": aid, "score": None}, "hops": [], "path": [aid],
+                                           "total_hops": 0, "total_discovered": 1}})
+            else:
+                q = w["query_vec"].flatten()
+                anchor_sim = float(np.dot(q, avec.flatten()))
+                states.append({"kind": "triangulation", "q": q, "visited": {aid}, "results": [(anchor_sim, aid)],
+                               "cur_idx": aid, "cur_vec": avec, "alive": True,
+                               "details": {"anchor": {"idx": aid, "score": anchor_sim}, "hops": [], "path": [aid],
+                                           "total_hops": 0}})
+        for hop in range(1, max_hops + 1):
+            live = [st for st in states if st["alive"]]
+            if not live:
+                break
+            X = np.stack([np.asarray(st["cur_vec"], dtype=np.float32).reshape(-1) for st in live])
+            _, I = vector_db.search(x=X, k=neighbor_k + 1)
+            neigh = [[int(i) for i in I[r] if int(i) != -1 and int(i) not in st["visited"]] for r, st in enumerate(live)]
+            need = sorted({i for ids in neigh for i in ids})
+            vecs = {}
+            if need:
+                rows = vector_db.reconstruct_batch(np.asarray(need, dtype=np.int64))
+                vecs = {i: rows[j] for j, i in enumerate(need)}
+            for st, ids in zip(live, neigh):
+                cur = st["cur_vec"].flatten()
+                candidates = []
+                if st["kind"] == "ssg":
+                    for idx in ids:
+                        candidates.append({"idx": idx, "score": float(np.dot(cur, vecs[idx].flatten())), "selected": False})
+                    if not candidates:
+                        st["alive"] = False
+                        continue
+                    candidates.sort(key=lambda c: c["score"], reverse=True)
+                    best = candidates[0]
+                    if best["score"] <= st["previous"]:
+                        st["alive"] = False
+                        continue
+                    best["selected"] = True
+                    st["details"]["hops"].append({"hop_number": hop, "current_chunk": st["cur_idx"],
+                                                  "candidates": candidates[:10], "selected_idx": best["idx"],
+                                                  "selected_score": best["score"]})
+                    st["visited"].add(best["idx"])
+                    st["details"]["path"].append(best["idx"])
+                    st["cur_idx"], st["cur_vec"] = best["idx"], vecs[best["idx"]]
+                    st["results"].append((best["score"], best["idx"]))
+                    st["previous"] = best["score"]
+                    st["details"]["total_discovered"] += 1
+                else:
+                    q = st["q"]
+                    for idx in ids:
+                        cand = vecs[idx].flatten()
+                        centroid = (q + cur + cand) / 3.0
+                        dist = float(np.linalg.norm(centroid - q))
+                        candidates.append({"idx": idx, "query_to_candidate": float(np.dot(q, cand)),
+                                           "centroid_score": 1.0 / (1.0 + dist), "centroid_distance": dist,
+                                           "selected": False})
+                    if not candidates:
+                        st["alive"] = False
+                        continue
+                    candidates.sort(key=lambda c: c["centroid_score"], reverse=True)
+                    best = candidates[0]
+                    best["selected"] = True
+                    st["details"]["hops"].append({"hop_number": hop, "current_chunk": st["cur_idx"],
+                                                  "candidates": candidates[:10], "selected_idx": best["idx"],
+                                                  "centroid_score": best["centroid_score"],
+                                                  "selection_reason": "质心距离最优"})
+                    st["visited"].add(best["idx"])
+                    st["details"]["path"].append(best["idx"])
+                    st["cur_idx"], st["cur_vec"] = best["idx"], vecs[best["idx"]]
+                    st["results"].append((best["centroid_score"], best["idx"]))
+        out = []
+        for st in states:
+            st["details"]["total_hops"] = len(st["details"]["hops"])
+            out.append({"results": st["results"], "traversal_details": st["details"]})
+        return out
+
     # ---- query expansion (reference :892-1047) ------------------------------------------------------
     def _expand_queries(self, query, use_hyde, use_multi_query, multi_query_config, timing, expansion_texts,
                         progress_callback):
@@ -673,6 +761,151 @@ class VectorRetriever:
                 out.append((q, hits))
             return out
 
+        if getattr(self, "batched_expansion", True):
+            try:
+                return self._search_report_walks_lockstep(report, query_items, return_parent_pages, retrieval_method,
+                                                          max_hops, neighbor_k)
+            except Exception as e:  # noqa: BLE001 - e.g. an index object without reconstruct_batch
+                self._safe_print(f"[WARNING] batched expansion failed in report {report.get('name')} ({e}); "
+                                 "walking sequentially")
+        return self._search_report_walks_sequential(report, query_items, return_parent_pages, retrieval_method,
+                                                    max_hops, neighbor_k)
+
+    def _search_report_walks_lockstep(self, report, query_items, return_parent_pages, retrieval_method, max_hops,
+                                      neighbor_k):
+        """ssg / triangulation / hybrid_expansion for all queries of one report with batched GPU calls:
+        one anchor (or top-50) search for all queries, one row gather for all anchors, then every walk of
+        every query in lockstep (_walks_lockstep).  Produces the per-query values of the sequential code."""
+        document, vector_db = report["document"], report["vector_db"]
+        chunks = document["content"]["chunks"]
+        pages = report["_page_lookup"][1]
+        sha1 = document["metainfo"]["sha1_name"]
+        X = np.concatenate([e for _, e in query_items], axis=0)
+        nq = len(query_items)
+        out = [None] * nq
+
+        def exp_hits(qi, exp, source):
+            emb = query_items[qi][1]
+            got = []
+            for score, idx in exp.get("results", []):
+                if idx == -1:
+                    continue
+                sim = self._query_similarity_vec(emb, idx, score, row_of)
+                got.append((self._hit(sha1, chunks, pages, idx, sim, source, return_parent_pages), score))
+            return got
+
+        row_of = {}   # id -> stored row, filled by the batched gathers below
+
+        def gather(ids):
+            need = sorted({int(i) for i in ids if int(i) not in row_of})
+            if need:
+                rows = vector_db.reconstruct_batch(np.asarray(need, dtype=np.int64))
+                for j, i in enumerate(need):
+                    row_of[i] = rows[j]
+
+        if retrieval_method in ("ssg", "triangulation"):
+            D, I = vector_db.search(x=X, k=1)
+            live = [qi for qi in range(nq) if len(D[qi]) > 0 and int(I[qi][0]) != -1]
+            for qi in range(nq):
+                if qi not in live:
+                    out[qi] = (query_items[qi][0], [])
+            gather(int(I[qi][0]) for qi in live)
+            walks = [{"kind": retrieval_method, "anchor_id": int(I[qi][0]), "anchor_vec": row_of[int(I[qi][0])],
+                      "query_vec": query_items[qi][1]} for qi in live]
+            exps = self._walks_lockstep(vector_db, walks, max_hops=max_hops, neighbor_k=neighbor_k)
+            gather(idx for exp in exps for _, idx in exp["results"])
+            for qi, exp in zip(live, exps):
+                q = query_items[qi][0]
+                hits = []
+                details = exp["traversal_details"]
+                details["anchor"]["score"] = float(D[qi][0])
+                try:
+                    hits = [h for h, _ in exp_hits(qi, exp, retrieval_method)]
+                except Exception as e:  # noqa: BLE001
+                    self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
+                out[qi] = (q, {"hits": hits, "traversal_details": details})
+            return out
+
+        # hybrid_expansion: basic top-50, SSG from the top 10, triangulation from the top 20 (:1258-1418)
+        D, I = vector_db.search(x=X, k=min(50, len(chunks)))
+        per_q = []
+        walks, owner = [], []
+        for qi, (q, emb) in enumerate(query_items):
+            hits, basic_results, basic_keys = [], [], set()
+            failed = None
+            try:
+                for distance, index in zip(D[qi], I[qi]):
+                    h = self._hit(sha1, chunks, pages, int(index), round(float(distance) * 1.0, 4), "basic",
+                                  return_parent_pages)
+                    basic_results.append((h[0], h[1], h[2], h[3], sha1, int(index)))
+                    basic_keys.add(h[0])
+                    hits.append(h)
+            except Exception as e:  # noqa: BLE001
+                failed = e
+                self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
+            per_q.append({"hits": hits, "basic": basic_results, "keys": basic_keys, "failed": failed})
+        gather(b[5] for st in per_q if st["failed"] is None for b in st["basic"][:20])
+        for qi, st in enumerate(per_q):
+            if st["failed"] is not None:
+                continue
+            for limit, source in ((10, "ssg"), (20, "triangulation")):
+                for key, page_id, text, sim0, _sha, idx in st["basic"][:limit]:
+                    walks.append({"kind": source, "anchor_id": idx, "anchor_vec": row_of[idx],
+                                  "query_vec": query_items[qi][1]})
+                    owner.append((qi, source, page_id))
+        exps = self._walks_lockstep(vector_db, walks, max_hops=max_hops, neighbor_k=neighbor_k) if walks else []
+        gather(idx for exp in exps for _, idx in exp["results"])
+        stats = [{"ssg_new": [], "tri_new": [], "ssg_total": 0, "ssg_new_only": 0, "tri_total": 0, "tri_new_only": 0}
+                 for _ in range(nq)]
+        for (qi, source, page_id), exp in zip(owner, exps):
+            st, acc = per_q[qi], stats[qi]
+            if st["failed"] is not None:
+                continue
+            try:
+                for h, score in exp_hits(qi, exp, source):
+                    st["hits"].append(h)
+                    is_new = h[0] not in st["keys"]
+                    rec = {"key": h[0], "page": h[1], "text": h[2], "vector_similarity": h[3], "source_sha1": sha1,
+                           "anchor_page": page_id, "score": score}
+                    if source == "ssg":
+                        acc["ssg_total"] += 1
+                        if is_new:
+                            acc["ssg_new"].append(rec)
+                            acc["ssg_new_only"] += 1
+                    else:
+                        acc["tri_total"] += 1
+                        if is_new:
+                            acc["tri_new"].append(rec)
+                            acc["tri_new_only"] += 1
+            except Exception as e:  # noqa: BLE001 - the reference abandons the rest of this (query, report) task
+                st["failed"] = e
+                q = query_items[qi][0]
+                self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
+        for qi, (q, _) in enumerate(query_items):
+            st, acc = per_q[qi], stats[qi]
+            out[qi] = (q, {"hits": st["hits"], "algorithm_specific_results": {
+                "ssg_new_chunks": acc["ssg_new"], "triangulation_new_chunks": acc["tri_new"],
+                "basic_count": len(st["basic"]),
+                "ssg_stats": {"total_expanded": acc["ssg_total"], "new_only": acc["ssg_new_only"],
+                              "in_basic_top50": acc["ssg_total"] - acc["ssg_new_only"]},
+                "triangulation_stats": {"total_expanded": acc["tri_total"], "new_only": acc["tri_new_only"],
+                                        "in_basic_top50": acc["tri_total"] - acc["tri_new_only"]}}})
+        return out
+
+    def _query_similarity_vec(self, embedding_array, idx, fallback_score, row_of):
+        vec = row_of.get(int(idx))
+        if vec is not None:
+            return round(float(np.dot(embedding_array.flatten(), vec.flatten())) * 1.0, 4)
+        return round(float(fallback_score) * 1.0, 4)
+
+    def _search_report_walks_sequential(self, report, query_items, return_parent_pages, retrieval_method, max_hops,
+                                        neighbor_k):
+        """One walk at a time, as the reference does (kept as the fallback of the lockstep path)."""
+        document, vector_db = report["document"], report["vector_db"]
+        chunks = document["content"]["chunks"]
+        pages = report["_page_lookup"][1]
+        sha1 = document["metainfo"]["sha1_name"]
+        out = []
         for qi, (q, emb) in enumerate(query_items):
             hits, trav = [], []
             ssg_new, tri_new, basic_results = [], [], []

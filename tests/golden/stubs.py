@@ -88,8 +88,11 @@ class OracleFlatIndex:
         self.ntotal, self.d = self.rows.shape
 
     def search(self, x, k):
+        # one query at a time: numpy's fp32 GEMV and GEMM differ in the last bit, and the golden outputs were
+        # produced by the reference, which always searches a single query (src/retrieval.py:1140)
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, self.d)
-        return oracle.flat_ip_search_ref(self.rows, x, k)
+        parts = [oracle.flat_ip_search_ref(self.rows, x[i: i + 1], k) for i in range(x.shape[0])]
+        return np.concatenate([p[0] for p in parts], axis=0), np.concatenate([p[1] for p in parts], axis=0)
 
     def reconstruct(self, i):
         i = int(i)

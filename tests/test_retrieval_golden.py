@@ -196,3 +196,32 @@ def test_device_placement_round_robin(env):
         R.clear_resident_cache()
     with pytest.raises(ValueError):
         R.VectorRetriever(paths["vector_db_dir"], paths["documents_dir"], device=[])
+
+
+def test_graph_expansions_use_batched_calls(env):
+    """hybrid_expansion walks 30 anchors per (query, report): in lockstep that is 1 + max_hops batched searches
+    and a few batched gathers per report, and no per-candidate reconstruct round trips — with the reference's
+    records (the golden comparison above runs through the same path)."""
+    R, paths, golden = env
+    r = R.VectorRetriever(paths["vector_db_dir"], paths["documents_dir"], subset_path=paths["subset_path"],
+                          qwen=stubs.ScriptedQwen())
+    calls = {"search": [], "reconstruct": 0, "reconstruct_batch": 0}
+    cls = type(r.all_dbs[0]["vector_db"])
+    orig = cls.search, cls.reconstruct, cls.reconstruct_batch
+    mp = pytest.MonkeyPatch()
+    mp.setattr(cls, "search", lambda self, x, k: (calls["search"].append(len(x)), orig[0](self, x, k))[1])
+    mp.setattr(cls, "reconstruct", lambda self, i: (calls.__setitem__("reconstruct", calls["reconstruct"] + 1), orig[1](self, i))[1])
+    mp.setattr(cls, "reconstruct_batch",
+               lambda self, ids: (calls.__setitem__("reconstruct_batch", calls["reconstruct_batch"] + 1), orig[2](self, ids))[1])
+    try:
+        kw = dict(cases.VECTOR_CASES["hybrid_expansion"])
+        got = r.retrieve_by_company_name(**kw)
+    finally:
+        mp.undo()
+    want = gu.canon_result(golden["vector"]["hybrid_expansion"])
+    assert gu.canon_result(got)["results"] == want["results"]
+    n_reports = 1                                   # selected_years=[2024]
+    assert calls["reconstruct"] == 0
+    assert len(calls["search"]) <= n_reports * (1 + kw["max_hops"])
+    assert max(calls["search"]) >= 20               # the walks advance together
+    assert calls["reconstruct_batch"] <= n_reports * (2 + kw["max_hops"])
