@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--cpu-docs", type=int, default=50_000, help="documents of the CPU-baseline BM25 sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run BM25 after the scan instead of under it")
+    ap.add_argument("--bm25-first", action="store_true", help="enqueue BM25 (side stream) before the scan (experiment)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU result exchange: one fused kernel over NVLink peer memory, or NCCL all-gather + merges")
     return ap.parse_args()
@@ -250,6 +251,8 @@ def run_b200(args):
         exchange = "nccl" if world > 1 else "none"
         index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap)
 
+    index.searcher.scan_first = not args.bm25_first
+
     # ---- queries (rank 0 decides, everyone gets the same) --------------------------------------------
     pool = max(args.pool, args.nq)
     q_pool = synth.dense_queries_torch(pool, args.dim, dev, rows if rank == 0 else None)
@@ -339,7 +342,8 @@ def run_b200(args):
     # tensor-core path (K2); local shard only, CUDA events, a few iterations each
     extras = {}
     index.searcher.local_dense = inner_dense
-    for name, nqx, iters in (("dense_single_query", 1, 20), ("dense_batch64_tensor_core", 64, 5)):
+    for name, nqx, iters in (("dense_single_query", 1, 20), ("dense_batch64_tensor_core", 64, 5),
+                             ("dense_batch128_tensor_core", 128, 5)):
         qx = q_pool[:nqx].contiguous() if pool >= nqx else q_pool.repeat((nqx + pool - 1) // pool, 1)[:nqx].contiguous()
         for _ in range(2):
             flat.search_dev(qx, args.k)

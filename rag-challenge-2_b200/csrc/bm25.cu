@@ -340,6 +340,7 @@ static int bm25_launch_t(b2r_bm25* h, const Bm25Plan& p, Bm25Args<W> a, int nq_l
   a.weight = static_cast<const W*>(h->weight);
   auto kern = bm25_kernel<W>;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   dim3 grid(p.grid_x, nq_launch);
   kern<<<grid, kBm25Warps * 32, p.smem, stream>>>(a);
   B2R_CUDA(cudaGetLastError());

@@ -480,10 +480,12 @@ static int launch_tma_cw(const ScanPlan& p, const ScanArgs& a, cudaStream_t stre
   if (p.cw == 8) {
     auto kern = flat_scan_tma_kernel<DV, NQ, 8>;
     B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<p.grid, p.threads, p.smem, stream>>>(a);
   } else {
     auto kern = flat_scan_tma_kernel<DV, NQ, 4>;
     B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+    B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<p.grid, p.threads, p.smem, stream>>>(a);
   }
   B2R_CUDA(cudaGetLastError());
@@ -515,6 +517,7 @@ template <int NQ>
 static int launch_generic_nq(const ScanPlan& p, const ScanArgs& a, cudaStream_t stream) {
   auto kern = flat_scan_generic_kernel<NQ, 8>;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   kern<<<p.grid, p.threads, p.smem, stream>>>(a);
   B2R_CUDA(cudaGetLastError());
   return B2R_OK;

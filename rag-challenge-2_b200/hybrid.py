@@ -128,6 +128,7 @@ class ShardedSearcher:
         self._merge = merge or merge_topk
         self._fuse = fuse or hybrid_fuse
         self.side_stream = None  # set to a torch.cuda.Stream to overlap BM25 with the dense scan
+        self.scan_first = True   # enqueue the scan before the side-stream BM25 (see search_hybrid)
         self.peer_exchange = None  # set to a PeerExchange to replace all-gather + merges + fusion by one kernel
         self.launches = 0      # kernels of this library enqueued by the last call
         self.collectives = 0   # collectives enqueued by the last call
@@ -183,14 +184,24 @@ class ShardedSearcher:
         self.launches = self.collectives = 0
         side = self.side_stream
         if side is not None:
-            # BM25 is latency-bound and small (its CTAs co-reside with the scan's on every SM):
-            # enqueue it on a side stream so it runs under the HBM-bound scan
+            # BM25 is latency-bound and small: it runs on a side stream under the HBM-bound scan.  The scan
+            # is enqueued FIRST so that its persistent CTAs (one per SM, statically assigned tiles) are all
+            # resident before BM25's CTAs fill the remaining shared memory; the other order lets two BM25
+            # CTAs land on one SM, delays that SM's scan CTA and with it the whole scan (measured: +80 us).
             main = torch.cuda.current_stream(q.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                S, J = self.local_bm25(term_ids, term_offsets, k)
-            D, I = self.local_dense(q, k)
-            self.launches += self._last_dense_launches()
+            if self.scan_first:
+                ready = main.record_event()
+                D, I = self.local_dense(q, k)
+                self.launches += self._last_dense_launches()
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    S, J = self.local_bm25(term_ids, term_offsets, k)
+            else:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    S, J = self.local_bm25(term_ids, term_offsets, k)
+                D, I = self.local_dense(q, k)
+                self.launches += self._last_dense_launches()
             main.wait_stream(side)
             for t in (S, J):
                 t.record_stream(main)
