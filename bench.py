@@ -41,8 +41,12 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=1_000_000, help="rows of the CPU-baseline dense sample")
     ap.add_argument("--cpu-docs", type=int, default=50_000, help="documents of the CPU-baseline BM25 sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="run BM25 after the scan instead of under it")
-    ap.add_argument("--bm25-first", action="store_true", help="enqueue BM25 (side stream) before the scan (experiment)")
+    ap.add_argument("--no-overlap", action="store_true", help="run BM25 after the scan instead of beside it")
+    ap.add_argument("--overlap", default="pdl", choices=["pdl", "streams"],
+                    help="how BM25 runs beside the scan: programmatic dependent launch (one stream) or two streams")
+    ap.add_argument("--no-scan-priority", action="store_true", help="scan on the caller's stream instead of a high-priority one (experiment)")
+    ap.add_argument("--no-bm25-events", action="store_true", help="do not time the BM25 kernel inside the step (experiment)")
+    ap.add_argument("--tunable", action="append", default=[], help="library tunable key=value (experiments)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU result exchange: one fused kernel over NVLink peer memory, or NCCL all-gather + merges")
     return ap.parse_args()
@@ -194,7 +198,7 @@ def workload_config(args, world):
     return {"workload": f"hybrid top-{args.k}: flat IP over {args.rows} x {args.dim} fp32 + BM25Okapi over {args.rows} "
                         f"chunks (vocab {args.vocab}, Zipf) + fusion; {args.nq} query/step",
             "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "k": args.k, "queries_per_step": args.nq,
-            "sharding": f"rows/{world}", "bm25_overlapped_with_scan": not args.no_overlap, "l2": "inputs (rows + postings) far larger than the 126 MB L2; no flush needed"}
+            "sharding": f"rows/{world}", "bm25_overlapped_with_scan": (False if args.no_overlap else args.overlap), "l2": "inputs (rows + postings) far larger than the 126 MB L2; no flush needed"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -212,6 +216,9 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    for kv in args.tunable:
+        key, v = kv.split("=")
+        pkg._lib.tunable_set(key, int(v))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (there is no CPU fallback; use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
@@ -241,17 +248,18 @@ def run_b200(args):
     exchange = args.exchange
     if world > 1 and exchange == "peer":
         try:
-            index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap, exchange="peer")
+            index = hybrid.HybridIndex(flat, bm25, lo, overlap=(None if args.no_overlap else args.overlap), exchange="peer")
         except Exception as e:  # noqa: BLE001 - symmetric memory needs P2P / IPC support on the box
             if rank == 0:
                 print(f"[bench] peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
             exchange = "nccl"
-            index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap)
+            index = hybrid.HybridIndex(flat, bm25, lo, overlap=(None if args.no_overlap else args.overlap))
     else:
         exchange = "nccl" if world > 1 else "none"
-        index = hybrid.HybridIndex(flat, bm25, lo, overlap=not args.no_overlap)
+        index = hybrid.HybridIndex(flat, bm25, lo, overlap=(None if args.no_overlap else args.overlap))
 
-    index.searcher.scan_first = not args.bm25_first
+    if args.no_scan_priority:
+        index.searcher.scan_stream = None
 
     # ---- queries (rank 0 decides, everyone gets the same) --------------------------------------------
     pool = max(args.pool, args.nq)
@@ -278,16 +286,38 @@ def run_b200(args):
     scan_events = []
     inner_dense = index.searcher.local_dense
 
+    pdl = (not args.no_overlap) and args.overlap == "pdl"
+
     def timed_dense(q, k):
+        # pdl: no stream operation may sit between the scan and the BM25 launch (it would serialise them), so
+        # the closing event is recorded after BM25: the interval is the scan with BM25 running beside it
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         out = inner_dense(q, k)
-        b.record()
+        if not pdl:
+            b.record()
         scan_events.append((a, b))
         return out
 
     timed_dense.last_launches = inner_dense.last_launches
     index.searcher.local_dense = timed_dense
+    bm25_events = []
+    inner_bm25 = index.searcher.local_bm25
+
+    def timed_bm25(t, o, k, **kw):  # events on the stream BM25 is enqueued on
+        if pdl:
+            out = inner_bm25(t, o, k, **kw)
+            scan_events[-1][1].record()
+            return out
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = inner_bm25(t, o, k, **kw)
+        b.record()
+        bm25_events.append((a, b))
+        return out
+
+    if pdl or not args.no_bm25_events:
+        index.searcher.local_bm25 = timed_bm25
 
     def sync_all():
         torch.cuda.synchronize()
@@ -305,6 +335,7 @@ def run_b200(args):
         index.search_hybrid_dev(q, t, o, args.k)
     sync_all()
     scan_events.clear()
+    bm25_events.clear()
     launches = 0
     collectives = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -320,6 +351,7 @@ def run_b200(args):
     t_wall1 = time.time()
     ms_total = e0.elapsed_time(e1)
     scan_ms = sum(a.elapsed_time(b) for a, b in scan_events) / max(1, len(scan_events))
+    bm25_ms = sum(a.elapsed_time(b) for a, b in bm25_events) / max(1, len(bm25_events))
     top1 = O[:, 0].tolist()
 
     # ---- e2e: host buffers in, host buffers out, through the public API ---------------------------------
@@ -342,6 +374,7 @@ def run_b200(args):
     # tensor-core path (K2); local shard only, CUDA events, a few iterations each
     extras = {}
     index.searcher.local_dense = inner_dense
+    index.searcher.local_bm25 = inner_bm25
     for name, nqx, iters in (("dense_single_query", 1, 20), ("dense_batch64_tensor_core", 64, 5),
                              ("dense_batch128_tensor_core", 128, 5)):
         qx = q_pool[:nqx].contiguous() if pool >= nqx else q_pool.repeat((nqx + pool - 1) // pool, 1)[:nqx].contiguous()
@@ -379,10 +412,12 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "flat_scan_tma_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(hi - lo, args.dim),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": scan_ms, "frac_of_8TBps_nominal": achieved / 8000.0,
+                         "kernel_ms": scan_ms, "kernel_ms_note": ("scan with the BM25 kernel running beside it (events around the pair)"
+                                                                   if pdl else "events around the scan launch"),
+                         "frac_of_8TBps_nominal": achieved / 8000.0,
                          "share_of_step": scan_ms * max(1, -(-args.nq // 4)) / (ms_total / args.steps)},
             "clocks": sampler.summary(t_wall0, t_wall1),
-            "bm25": {"postings_local": n_post, "bytes_per_posting": 4 + wbits // 8},
+            "bm25": {"postings_local": n_post, "bytes_per_posting": 4 + wbits // 8, "kernel_ms_in_step": bm25_ms},
             "top1_last_step": top1,
             "extras": extras,
         }

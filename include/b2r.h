@@ -132,6 +132,15 @@ int b2r_bm25_topk_host(b2r_bm25* h, const int32_t* term_ids, const int32_t* term
 int b2r_bm25_topk_dev(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* term_offsets_dev,
                       const int32_t* term_offsets_host, int nq, int k, double* S_dev,
                       int64_t* I_dev, int64_t id_offset, void* stream);
+/* Same, with launch flags.  B2R_LAUNCH_OVERLAP_PREVIOUS: the kernel is launched with programmatic stream
+ * serialization, so it may run BESIDE the previous kernel of `stream` once all CTAs of that kernel are
+ * running (the flat scan kernels issue griddepcontrol.launch_dependents at their start; any other kernel
+ * releases it when it exits, i.e. ordinary stream order).  Only for work that does not read what the previous
+ * kernel writes — the hybrid path launches BM25 this way right behind the dense scan. */
+#define B2R_LAUNCH_OVERLAP_PREVIOUS 1u
+int b2r_bm25_topk_dev_ex(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* term_offsets_dev,
+                         const int32_t* term_offsets_host, int nq, int k, double* S_dev,
+                         int64_t* I_dev, int64_t id_offset, void* stream, unsigned flags);
 int b2r_bm25_destroy(b2r_bm25* h);
 
 /* ---- dense + BM25 fusion ------------------------------------------------------------------- */

@@ -62,6 +62,7 @@ SIGNATURES = {
     "b2r_bm25_scores_host": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "b2r_bm25_topk_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b2r_bm25_topk_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp]),
+    "b2r_bm25_topk_dev_ex": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_uint]),
     "b2r_bm25_destroy": (C.c_int, [_vp]),
     "b2r_cosine_stats_dev": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int64, C.c_int64, _vp, _vp, C.c_int, C.c_int,
                                        _vp, _vp, C.c_int, _vp]),

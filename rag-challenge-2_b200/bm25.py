@@ -179,8 +179,9 @@ class BM25Okapi:
                                                 _lib.ptr(I)))
         return S, I
 
-    def topk_dev(self, term_ids, term_offsets, k, S=None, I=None, id_offset=0, stream=None):
-        """Resident batch: term_ids / term_offsets are int32 CUDA tensors; returns CUDA tensors."""
+    def topk_dev(self, term_ids, term_offsets, k, S=None, I=None, id_offset=0, stream=None, overlap_previous=False):
+        """Resident batch: term_ids / term_offsets are int32 CUDA tensors; returns CUDA tensors.
+        overlap_previous: launch beside the previous kernel of the stream (B2R_LAUNCH_OVERLAP_PREVIOUS)."""
         import torch
 
         nq = int(term_offsets.shape[0]) - 1
@@ -190,10 +191,10 @@ class BM25Okapi:
             I = torch.empty((nq, k), dtype=torch.int64, device=term_ids.device)
         if stream is None:
             stream = torch.cuda.current_stream(term_ids.device).cuda_stream
-        _lib.check(self._lib.b2r_bm25_topk_dev(self._h, C.c_void_p(term_ids.data_ptr()),
-                                               C.c_void_p(term_offsets.data_ptr()), None, nq, int(k),
-                                               C.c_void_p(S.data_ptr()), C.c_void_p(I.data_ptr()), int(id_offset),
-                                               C.c_void_p(stream)))
+        _lib.check(self._lib.b2r_bm25_topk_dev_ex(self._h, C.c_void_p(term_ids.data_ptr()),
+                                                  C.c_void_p(term_offsets.data_ptr()), None, nq, int(k),
+                                                  C.c_void_p(S.data_ptr()), C.c_void_p(I.data_ptr()), int(id_offset),
+                                                  C.c_void_p(stream), 1 if overlap_previous else 0))
         return S, I
 
     def get_top_n(self, query, documents, n=5):

@@ -336,20 +336,39 @@ static int bm25_plan(const b2r_bm25* h, int k, Bm25Plan* p) {
 }
 
 template <class W>
-static int bm25_launch_t(b2r_bm25* h, const Bm25Plan& p, Bm25Args<W> a, int nq_launch, cudaStream_t stream) {
+static int bm25_launch_t(b2r_bm25* h, const Bm25Plan& p, Bm25Args<W> a, int nq_launch, cudaStream_t stream,
+                         bool overlap_prev) {
   a.weight = static_cast<const W*>(h->weight);
   auto kern = bm25_kernel<W>;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   dim3 grid(p.grid_x, nq_launch);
-  kern<<<grid, kBm25Warps * 32, p.smem, stream>>>(a);
+  if (overlap_prev) {
+    // programmatic stream serialization: this grid may start as soon as every CTA of the previous kernel in
+    // the stream has executed griddepcontrol.launch_dependents (or exited).  The kernel never waits on the
+    // previous grid (it reads nothing that grid writes); the next ordinary launch waits for both.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kBm25Warps * 32);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2R_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  } else {
+    kern<<<grid, kBm25Warps * 32, p.smem, stream>>>(a);
+  }
   B2R_CUDA(cudaGetLastError());
   return B2R_OK;
 }
 
 // shared by topk (dense == nullptr) and scores (dense != nullptr, one query)
 static int bm25_run(b2r_bm25* h, const int* term_ids_dev, const int* term_offsets_dev, int nq, int k, double* S_dev,
-                    long long* I_dev, long long id_offset, double* dense_dev, cudaStream_t stream) {
+                    long long* I_dev, long long id_offset, double* dense_dev, cudaStream_t stream,
+                    bool overlap_prev = false) {
   launch_counter() = 0;
   Bm25Plan p;
   int rc = bm25_plan(h, k, &p);
@@ -387,9 +406,9 @@ static int bm25_run(b2r_bm25* h, const int* term_ids_dev, const int* term_offset
     if (h->weight_bits == 64) {
       Bm25Args<double> ad;
       memcpy(&ad, &a, sizeof(a));  // identical layout: only the weight pointer type differs
-      rc = bm25_launch_t<double>(h, p, ad, nql, stream);
+      rc = bm25_launch_t<double>(h, p, ad, nql, stream, overlap_prev && q0 == 0);
     } else {
-      rc = bm25_launch_t<float>(h, p, a, nql, stream);
+      rc = bm25_launch_t<float>(h, p, a, nql, stream, overlap_prev && q0 == 0);
     }
     if (rc) return rc;
     ++launch_counter();
@@ -519,6 +538,13 @@ static int bm25_check_terms(const b2r_bm25* h, const int32_t* term_ids, int n) {
 int b2r_bm25_topk_dev(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* term_offsets_dev,
                       const int32_t* term_offsets_host, int nq, int k, double* S_dev, int64_t* I_dev, int64_t id_offset,
                       void* stream) {
+  return b2r_bm25_topk_dev_ex(h, term_ids_dev, term_offsets_dev, term_offsets_host, nq, k, S_dev, I_dev, id_offset, stream,
+                              0u);
+}
+
+int b2r_bm25_topk_dev_ex(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* term_offsets_dev,
+                         const int32_t* term_offsets_host, int nq, int k, double* S_dev, int64_t* I_dev,
+                         int64_t id_offset, void* stream, unsigned flags) {
   (void)term_offsets_host;
   if (!h) return fail(B2R_ERR_INVALID, "b2r_bm25_topk: NULL handle");
   if (nq < 0 || k < 1) return fail(B2R_ERR_INVALID, "b2r_bm25_topk: need nq >= 0 and k >= 1");
@@ -528,7 +554,7 @@ int b2r_bm25_topk_dev(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* t
   DeviceGuard g(h->device);
   if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_bm25_topk: cudaSetDevice failed");
   return bm25_run(h, term_ids_dev, term_offsets_dev, nq, k, S_dev, reinterpret_cast<long long*>(I_dev), id_offset,
-                  nullptr, static_cast<cudaStream_t>(stream));
+                  nullptr, static_cast<cudaStream_t>(stream), (flags & B2R_LAUNCH_OVERLAP_PREVIOUS) != 0u);
 }
 
 int b2r_bm25_topk_host(b2r_bm25* h, const int32_t* term_ids, const int32_t* term_offsets, int nq, int k, double* S,

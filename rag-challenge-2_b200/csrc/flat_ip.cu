@@ -105,6 +105,10 @@ __device__ __forceinline__ void scan_epilogue(const ScanArgs& a, u64* cand, int 
 template <int DV, int NQ, int CW>
 __global__ void __launch_bounds__((CW + 1) * 32) flat_scan_tma_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // Programmatic dependent launch: a kernel enqueued behind this one with B2R_LAUNCH_OVERLAP_PREVIOUS (the
+  // hybrid path's BM25) may start once every CTA of this grid is running — i.e. beside the scan, but only
+  // after all of its persistent CTAs hold their SM.  No effect on ordinary launches.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int d = DV * 128;
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__((CW + 1) * 32) flat_scan_tma_kernel(const Scan
 template <int NQ, int NW>
 __global__ void __launch_bounds__(NW * 32) flat_scan_generic_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // see flat_scan_tma_kernel
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int d = a.d;

@@ -127,8 +127,10 @@ class ShardedSearcher:
         self._gather = gather or self._dist_gather
         self._merge = merge or merge_topk
         self._fuse = fuse or hybrid_fuse
-        self.side_stream = None  # set to a torch.cuda.Stream to overlap BM25 with the dense scan
-        self.scan_first = True   # enqueue the scan before the side-stream BM25 (see search_hybrid)
+        self.overlap = None      # "pdl": BM25 beside the scan by programmatic dependent launch (one stream);
+                                 # "streams": side stream + high-priority scan stream; None: one after the other
+        self.side_stream = None  # "streams" mode: a torch.cuda.Stream for BM25
+        self.scan_stream = None  # high-priority stream for the scan while BM25 runs beside it (see search_hybrid)
         self.peer_exchange = None  # set to a PeerExchange to replace all-gather + merges + fusion by one kernel
         self.launches = 0      # kernels of this library enqueued by the last call
         self.collectives = 0   # collectives enqueued by the last call
@@ -182,26 +184,36 @@ class ShardedSearcher:
         import torch
 
         self.launches = self.collectives = 0
-        side = self.side_stream
-        if side is not None:
-            # BM25 is latency-bound and small: it runs on a side stream under the HBM-bound scan.  The scan
-            # is enqueued FIRST so that its persistent CTAs (one per SM, statically assigned tiles) are all
-            # resident before BM25's CTAs fill the remaining shared memory; the other order lets two BM25
-            # CTAs land on one SM, delays that SM's scan CTA and with it the whole scan (measured: +80 us).
+        side = self.side_stream if self.overlap == "streams" else None
+        if self.overlap == "pdl":
+            # BM25 is latency-bound and small, the scan HBM-bound: BM25 is launched right behind the scan with
+            # programmatic stream serialization, so it runs BESIDE the scan — but only once every persistent
+            # scan CTA (one per SM, statically assigned tiles) holds its SM.  With two streams both kernels
+            # become runnable at the same instant, two BM25 CTAs can take an SM before its scan CTA arrives,
+            # and that CTA — hence the whole scan — is delayed by a BM25 lifetime (measured: +70 us per step).
+            D, I = self.local_dense(q, k)
+            self.launches += self._last_dense_launches()
+            S, J = self.local_bm25(term_ids, term_offsets, k, overlap_previous=True)
+        elif side is not None:
+            # two-stream variant: BM25 on a side stream, the scan on a high-priority stream so that the block
+            # scheduler places its CTAs first (helps, but less reliably than the dependent launch)
             main = torch.cuda.current_stream(q.device)
-            if self.scan_first:
-                ready = main.record_event()
-                D, I = self.local_dense(q, k)
-                self.launches += self._last_dense_launches()
-                side.wait_event(ready)
-                with torch.cuda.stream(side):
-                    S, J = self.local_bm25(term_ids, term_offsets, k)
+            ready = main.record_event()
+            scan = self.scan_stream
+            if scan is not None:
+                scan.wait_event(ready)
+                with torch.cuda.stream(scan):
+                    D, I = self.local_dense(q, k)
             else:
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    S, J = self.local_bm25(term_ids, term_offsets, k)
                 D, I = self.local_dense(q, k)
-                self.launches += self._last_dense_launches()
+            self.launches += self._last_dense_launches()
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                S, J = self.local_bm25(term_ids, term_offsets, k)
+            if scan is not None:
+                main.wait_stream(scan)
+                for t in (D, I):
+                    t.record_stream(main)
             main.wait_stream(side)
             for t in (S, J):
                 t.record_stream(main)
@@ -236,7 +248,7 @@ class HybridIndex:
     `flat` is a FlatIPIndex over this rank's rows, `bm25` a BM25Okapi over the same chunks (built
     with corpus-global idf / avgdl), `offset` the global id of local row 0."""
 
-    def __init__(self, flat, bm25=None, offset=0, group=None, world_size=None, overlap=True, exchange="nccl"):
+    def __init__(self, flat, bm25=None, offset=0, group=None, world_size=None, overlap="pdl", exchange="nccl"):
         self.flat, self.bm25, self.offset = flat, bm25, int(offset)
 
         def local_dense(q, k):
@@ -244,15 +256,21 @@ class HybridIndex:
 
         local_dense.last_launches = flat.last_launch_count
 
-        def local_bm25(tids, toffs, k):
-            return bm25.topk_dev(tids, toffs, k, id_offset=self.offset)
+        def local_bm25(tids, toffs, k, overlap_previous=False):
+            return bm25.topk_dev(tids, toffs, k, id_offset=self.offset, overlap_previous=overlap_previous)
 
         self.searcher = ShardedSearcher(local_dense, local_bm25 if bm25 is not None else None, group=group,
                                         world_size=world_size)
-        if bm25 is not None and overlap:
+        if overlap is True:
+            overlap = "pdl"
+        if bm25 is not None and overlap in ("pdl", "streams"):
+            self.searcher.overlap = overlap
+        if bm25 is not None and overlap == "streams":
             import torch
 
-            self.searcher.side_stream = torch.cuda.Stream(device=torch.device("cuda", flat.device))
+            dev = torch.device("cuda", flat.device)
+            self.searcher.side_stream = torch.cuda.Stream(device=dev)
+            self.searcher.scan_stream = torch.cuda.Stream(device=dev, priority=-1)
         if exchange == "peer" and self.searcher.world_size > 1 and bm25 is not None:
             import torch
 
