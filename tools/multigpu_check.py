@@ -52,6 +52,14 @@ for it in range(5):  # several steps: exercises the parity double-buffering and 
     F2, O2 = nccl.search_hybrid_dev(q, tids, toffs, k)
     torch.cuda.synchronize()
     ok &= bool(torch.equal(O1, O2) and torch.equal(F1, F2))
+# single queries: the SIMT scan with BM25 launched beside it (programmatic dependent launch) + the exchange
+t1 = torch.from_numpy(np.asarray(toks[0], np.int32)).to(dev)
+o1 = torch.tensor([0, len(toks[0])], dtype=torch.int32, device=dev)
+for it in range(4):
+    Fa, Oa = peer.search_hybrid_dev(q[:1], t1, o1, k)
+    Fb, Ob = nccl.search_hybrid_dev(q[:1], t1, o1, k)
+    torch.cuda.synchronize()
+    ok &= bool(torch.equal(Oa, Ob) and torch.equal(Fa, Fb) and torch.equal(Oa[0], O1[0]) and torch.equal(Fa[0], F1[0]))
 Fh, Oh = peer.search_hybrid(q.cpu().numpy(), toks, k)  # host API on every rank (SPMD)
 ok &= bool(np.array_equal(Oh, O1.cpu().numpy()) and np.array_equal(Fh, F1.cpu().numpy()))
 if rank == 0:
