@@ -166,6 +166,24 @@ int b2r_hybrid_exchange_fuse_dev(const float* D, const int64_t* I, const double*
                                  int nq, int k, void* const* peer_bufs, int rank, int world, int nq_max,
                                  int k_max, uint32_t step, float* F, int64_t* O, void* stream);
 
+/* ---- one hybrid step behind one call (host buffers) ------------------------------------------- */
+/* What the drop-in does per question on one index: q[nq,d] + token ids in, fused top-k out.  Replaces the
+ * Python sequence index.search -> bm25.get_scores -> sorted(...)[:top_n] (src/retrieval.py:262-295,1140-1157)
+ * plus the fusion above.  The context owns a stream and pinned / device staging (grown on demand); steps on one
+ * context are serialised — create one context per host thread.  Inside: ONE pinned host->device copy of the
+ * packed inputs, the dense scan, BM25 launched beside it (B2R_LAUNCH_OVERLAP_PREVIOUS), the fusion kernel — or,
+ * when world > 1, the one-kernel exchange + merge + fusion over peer_bufs (see above; `step` as there) — the
+ * device->host copies of F / O and one stream synchronisation.  id_offset: global id of local row / doc 0. */
+typedef struct b2r_hybrid_ctx b2r_hybrid_ctx;
+int b2r_hybrid_ctx_create(int device, b2r_hybrid_ctx** out);
+int b2r_hybrid_ctx_destroy(b2r_hybrid_ctx* ctx);
+/* bytes moved host->device and device->host by the last step on this context (bench accounting) */
+int b2r_hybrid_ctx_bytes(const b2r_hybrid_ctx* ctx, size_t* h2d, size_t* d2h);
+int b2r_hybrid_search_host(b2r_hybrid_ctx* ctx, b2r_flat* flat, b2r_bm25* bm25, const float* q, int nq, int d,
+                           const int32_t* term_ids, const int32_t* term_offsets, int k, int64_t id_offset,
+                           void* const* peer_bufs, int rank, int world, int nq_max, int k_max, uint32_t step,
+                           float* F, int64_t* O);
+
 /* ---- N x N cosine analysis ---------------------------------------------------------------- */
 /* compute_cosine_similarity_matrix + off-diagonal statistics
  *                             semantic_similarity_analysis/generate_similarity_matrix.py:84-98,162-171

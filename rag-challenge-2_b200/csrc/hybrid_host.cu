@@ -1,0 +1,158 @@
+// hybrid_host.cu — one hybrid query step behind ONE C call with host buffers.
+//
+// The call a user of the drop-in makes per question is "embedding + tokens in, fused top-k out".  Driving the
+// three device entry points from Python costs ~90 us of interpreter / ctypes / torch time per step, which is
+// 10 % of a step on a 1.25M-row shard; this entry point does the whole step from C: one pinned host->device
+// copy of the packed inputs, dense scan, BM25 launched beside it (programmatic dependent launch), fusion (or
+// the one-kernel NVLink exchange + merge + fusion when peer buffers are given) storing its 12 * nq * k result
+// bytes straight into mapped pinned host memory, one stream synchronisation.  It replaces, for the single-index case, the Python loop over
+// index.search / bm25.get_scores / sorted(...)[:top_n] of src/retrieval.py:262-295,1140-1157.
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "b2r_common.cuh"
+
+struct b2r_hybrid_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  unsigned char* in_pin = nullptr;
+  unsigned char* in_dev = nullptr;
+  size_t in_cap = 0;
+  unsigned char* out_pin = nullptr;  // mapped pinned host memory: the fusion kernel stores F / O straight into it
+  unsigned char* out_pin_dev = nullptr;  // device alias of out_pin
+  unsigned char* out_dev = nullptr;  // intermediate lists [I int64][S double][J int64][D float]
+  size_t out_cap = 0;                // in (nq * k) units
+  std::mutex mu;                     // one step at a time per context (create one context per host thread)
+  size_t last_h2d = 0, last_d2h = 0;
+};
+
+using namespace b2r;
+
+static int ctx_reserve(b2r_hybrid_ctx* c, size_t in_bytes, size_t nk) {
+  if (c->in_cap < in_bytes) {
+    const size_t cap = std::max<size_t>(in_bytes, 1 << 16);
+    if (c->in_pin) cudaFreeHost(c->in_pin);
+    if (c->in_dev) cudaFree(c->in_dev);
+    c->in_pin = c->in_dev = nullptr;
+    c->in_cap = 0;
+    B2R_CUDA(cudaMallocHost(&c->in_pin, cap));
+    B2R_CUDA(cudaMalloc(&c->in_dev, cap));
+    c->in_cap = cap;
+  }
+  if (c->out_cap < nk) {
+    const size_t cap = std::max<size_t>(nk, 4096);
+    if (c->out_pin) cudaFreeHost(c->out_pin);
+    if (c->out_dev) cudaFree(c->out_dev);
+    c->out_pin = c->out_dev = nullptr;
+    c->out_cap = 0;
+    B2R_CUDA(cudaHostAlloc(&c->out_pin, cap * 12, cudaHostAllocMapped));
+    B2R_CUDA(cudaHostGetDevicePointer(&c->out_pin_dev, c->out_pin, 0));
+    B2R_CUDA(cudaMalloc(&c->out_dev, cap * 28));
+    c->out_cap = cap;
+  }
+  return B2R_OK;
+}
+
+extern "C" {
+
+int b2r_hybrid_ctx_create(int device, b2r_hybrid_ctx** out) {
+  if (!out) return fail(B2R_ERR_INVALID, "b2r_hybrid_ctx_create: out is NULL");
+  *out = nullptr;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_hybrid_ctx_create: cudaSetDevice failed");
+  b2r_hybrid_ctx* c = new b2r_hybrid_ctx();
+  c->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(B2R_ERR_CUDA, std::string("b2r_hybrid_ctx_create: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return B2R_OK;
+}
+
+int b2r_hybrid_ctx_destroy(b2r_hybrid_ctx* c) {
+  if (!c) return B2R_OK;
+  DeviceGuard g(c->device);
+  if (c->stream) {
+    cudaStreamSynchronize(c->stream);
+    cudaStreamDestroy(c->stream);
+  }
+  if (c->in_pin) cudaFreeHost(c->in_pin);
+  if (c->in_dev) cudaFree(c->in_dev);
+  if (c->out_pin) cudaFreeHost(c->out_pin);
+  if (c->out_dev) cudaFree(c->out_dev);
+  delete c;
+  return B2R_OK;
+}
+
+int b2r_hybrid_ctx_bytes(const b2r_hybrid_ctx* c, size_t* h2d, size_t* d2h) {
+  if (!c) return fail(B2R_ERR_INVALID, "b2r_hybrid_ctx_bytes: NULL context");
+  if (h2d) *h2d = c->last_h2d;
+  if (d2h) *d2h = c->last_d2h;
+  return B2R_OK;
+}
+
+int b2r_hybrid_search_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, const float* q, int nq, int d,
+                           const int32_t* term_ids, const int32_t* term_offsets, int k, int64_t id_offset,
+                           void* const* peer_bufs, int rank, int world, int nq_max, int k_max, uint32_t step, float* F,
+                           int64_t* O) {
+  if (!c || !flat || !bm25) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: NULL handle");
+  if (nq < 1 || d < 1 || k < 1 || k > B2R_MAX_K) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: bad sizes");
+  if (!q || !term_offsets || !F || !O) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: NULL buffer");
+  int fd = 0;
+  int rc = b2r_flat_dim(flat, &fd);
+  if (rc) return rc;
+  if (fd != d) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: query width does not match the index");
+  const int n_terms = term_offsets[nq];
+  if (term_offsets[0] != 0 || n_terms < 0 || (n_terms > 0 && !term_ids)) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: bad term offsets");
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_hybrid_search_host: cudaSetDevice failed");
+  std::lock_guard<std::mutex> lock(c->mu);
+  const size_t qb = static_cast<size_t>(nq) * d * 4, ob = (static_cast<size_t>(nq) + 1) * 4;
+  const size_t tb = static_cast<size_t>(std::max(n_terms, 1)) * 4;
+  const size_t in_bytes = qb + ob + tb;
+  const size_t nk = static_cast<size_t>(nq) * k;
+  rc = ctx_reserve(c, in_bytes, nk);
+  if (rc) return rc;
+  memcpy(c->in_pin, q, qb);
+  memcpy(c->in_pin + qb, term_offsets, ob);
+  if (n_terms) memcpy(c->in_pin + qb + ob, term_ids, static_cast<size_t>(n_terms) * 4);
+  const size_t h2d = qb + ob + static_cast<size_t>(n_terms) * 4;
+  B2R_CUDA(cudaMemcpyAsync(c->in_dev, c->in_pin, h2d, cudaMemcpyHostToDevice, c->stream));
+  const float* q_dev = reinterpret_cast<const float*>(c->in_dev);
+  const int32_t* offs_dev = reinterpret_cast<const int32_t*>(c->in_dev + qb);
+  const int32_t* tids_dev = reinterpret_cast<const int32_t*>(c->in_dev + qb + ob);
+  // results: the fusion kernel writes O[nq*k] int64 and F[nq*k] float directly into mapped pinned host memory
+  // (12 * nq * k bytes of posted PCIe writes instead of two device->host copy operations)
+  int64_t* O_dev = reinterpret_cast<int64_t*>(c->out_pin_dev);
+  float* F_dev = reinterpret_cast<float*>(c->out_pin_dev + nk * 8);
+  unsigned char* mid = c->out_dev;
+  int64_t* I_dev = reinterpret_cast<int64_t*>(mid);
+  double* S_dev = reinterpret_cast<double*>(mid + c->out_cap * 8);
+  int64_t* J_dev = reinterpret_cast<int64_t*>(mid + c->out_cap * 16);
+  float* D_dev = reinterpret_cast<float*>(mid + c->out_cap * 24);
+  rc = b2r_flat_search_dev(flat, q_dev, nq, k, D_dev, I_dev, id_offset, c->stream);
+  if (rc) return rc;
+  rc = b2r_bm25_topk_dev_ex(bm25, tids_dev, offs_dev, nullptr, nq, k, S_dev, J_dev, id_offset, c->stream,
+                            B2R_LAUNCH_OVERLAP_PREVIOUS);
+  if (rc) return rc;
+  if (world > 1) {
+    if (!peer_bufs) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: world > 1 needs the peer buffers");
+    rc = b2r_hybrid_exchange_fuse_dev(D_dev, I_dev, S_dev, J_dev, nq, k, peer_bufs, rank, world, nq_max, k_max, step, F_dev,
+                                      O_dev, c->stream);
+  } else {
+    rc = b2r_hybrid_fuse_dev(D_dev, I_dev, S_dev, J_dev, nq, k, k, k, F_dev, O_dev, nullptr, c->stream);
+  }
+  if (rc) return rc;
+  B2R_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(O, c->out_pin, nk * 8);
+  memcpy(F, c->out_pin + nk * 8, nk * 4);
+  c->last_h2d = h2d;
+  c->last_d2h = nk * 12;
+  return B2R_OK;
+}
+
+}  // extern "C"

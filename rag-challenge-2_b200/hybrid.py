@@ -276,6 +276,7 @@ class HybridIndex:
 
             self.searcher.peer_exchange = PeerExchange(torch.device("cuda", flat.device), group)
         self._pinned = {}
+        self._ctx = None   # b2r_hybrid_ctx of the one-call host step
 
     # resident API -----------------------------------------------------------------------------------
     def search_dev(self, q, k):
@@ -305,8 +306,64 @@ class HybridIndex:
 
     def search_hybrid(self, x, queries_term_ids, k):
         """x float32[nq,d] (host), queries_term_ids: list of int term-id lists -> (F, O) numpy.
-        One packed host->device copy from pinned memory, the resident search, pinned device->host
-        copies of the result, one stream synchronisation.  Records the bytes moved each way."""
+        One packed host->device copy from pinned memory, the resident search, pinned device->host copies of the
+        result, one stream synchronisation.  Records the bytes moved each way.  With one rank, or with the
+        peer-memory exchange, the whole step is ONE C call (b2r_hybrid_search_host); the NCCL exchange keeps the
+        step in Python (torch.distributed owns the collective)."""
+        import numpy as np
+
+        s = self.searcher
+        if self.bm25 is not None and (s.world_size == 1 or s.peer_exchange is not None):
+            return self._search_hybrid_c(x, queries_term_ids, k)
+        return self._search_hybrid_py(x, queries_term_ids, k)
+
+    def _search_hybrid_c(self, x, queries_term_ids, k):
+        import numpy as np
+
+        lib = _lib.load()
+        if self._ctx is None:
+            h = C.c_void_p()
+            _lib.check(lib.b2r_hybrid_ctx_create(int(self.flat.device), C.byref(h)))
+            self._ctx = h
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        nq, d = x.shape
+        offs = np.zeros(nq + 1, dtype=np.int32)
+        np.cumsum([len(t) for t in queries_term_ids], out=offs[1:])
+        tids = (np.concatenate([np.asarray(t, np.int32) for t in queries_term_ids]) if offs[-1]
+                else np.zeros(1, np.int32)).astype(np.int32, copy=False)
+        F = np.empty((nq, k), dtype=np.float32)
+        O = np.empty((nq, k), dtype=np.int64)
+        s = self.searcher
+        px = s.peer_exchange
+        if px is not None:
+            import torch
+
+            torch.cuda.current_stream(torch.device("cuda", self.flat.device)).synchronize()  # order after resident steps
+            px.step += 1
+            arr = (C.c_void_p * len(px.ptrs))(*[C.c_void_p(int(p)) for p in px.ptrs])
+            args = (arr, px.rank, px.world, px.nq_max, px.k_max, px.step)
+        else:
+            args = (None, 0, 1, 0, 0, 0)
+        self.bm25._ensure_built()
+        _lib.check(lib.b2r_hybrid_search_host(self._ctx, self.flat._h, self.bm25._h, _lib.ptr(x), nq, d, _lib.ptr(tids),
+                                              _lib.ptr(offs), int(k), self.offset, *args, _lib.ptr(F), _lib.ptr(O)))
+        h2d, d2h = C.c_size_t(0), C.c_size_t(0)
+        lib.b2r_hybrid_ctx_bytes(self._ctx, C.byref(h2d), C.byref(d2h))
+        self.last_h2d_bytes, self.last_d2h_bytes = int(h2d.value), int(d2h.value)
+        return F, O
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None:
+            _lib.load().b2r_hybrid_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _search_hybrid_py(self, x, queries_term_ids, k):
         import numpy as np
         import torch
 

@@ -138,6 +138,19 @@ def test_sharded_dense_and_hybrid_match_unsharded(b2r):
     # and the host-facing call agrees with the resident one
     Fh, Oh = whole.search_hybrid(q.cpu().numpy(), queries, k)
     assert np.array_equal(Oh, O0.cpu().numpy()) and np.array_equal(Fh, F0.cpu().numpy())
+    # the one-call C step (b2r_hybrid_search_host) == the Python-driven host step, also one query at a time
+    # (SIMT scan with BM25 launched beside it by programmatic dependent launch)
+    Fp, Op = whole._search_hybrid_py(q.cpu().numpy(), queries, k)
+    assert np.array_equal(Op, Oh) and np.array_equal(Fp, Fh)
+    qh = q.cpu().numpy()
+    for rep in range(3):
+        for i in range(len(queries)):
+            F1q, O1q = whole.search_hybrid(qh[i: i + 1], [queries[i]], k)
+            assert np.array_equal(O1q[0], Oh[i])
+            assert np.allclose(F1q[0], Fh[i], rtol=2e-6, atol=1e-7)   # K1 vs K2 summation order
+    assert whole.last_h2d_bytes == 4 * 1024 + 8 + 4 * len(queries[-1]) and whole.last_d2h_bytes == 12 * k
+    Fe, Oe = whole.search_hybrid(qh[:2], [[], queries[1]], k)          # a query without known tokens
+    assert np.array_equal(Oe[1], Oh[1])
 
 
 @pytest.mark.parametrize("world,k,step", [(1, 30, 1), (3, 30, 2), (8, 30, 5), (8, 100, 8), (4, 7, 3)])
