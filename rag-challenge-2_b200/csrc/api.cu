@@ -43,7 +43,9 @@ static std::map<std::string, int>& tunables() {
       {"gemm.mode", 0},            // 0: tf32 candidates + exact fp32 rescoring (verified); 3: 3xTF32 only
       {"gemm.no_verify", 0},       // 1: skip the 3xTF32 redo pass of unproven queries
       {"select.buf_cap", 0},       // cap on the final-select scratch (keys); small values force the fallback
-      {"bm25.block_docs", 0},      // documents per CTA in the BM25 kernel
+      {"bm25.block_docs", 0},      // documents per CTA in the doc-block BM25 kernel (bm25.v1)
+      {"bm25.debug_skip", 0},      // perf experiments (wrong results): 1 no select, 2 no accumulate, 4 no merge
+      {"bm25.v1", 0},              // 1: use the doc-block kernel (binary searches, per-token barriers) instead of the streaming one
   };
   return t;
 }

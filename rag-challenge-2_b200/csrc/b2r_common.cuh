@@ -292,6 +292,7 @@ __device__ __forceinline__ void block_select_lists(const K* __restrict__ src, in
 // ----------------------------------------------------------------------------------------------
 static const int kSelBins = 2048;
 
+__device__ __forceinline__ u32 key_score_bits(u128 k) { return static_cast<u32>(k >> 96); }
 __device__ __forceinline__ u32 key_score_bits(u64 k) { return static_cast<u32>(k >> 32); }
 __device__ __forceinline__ u32 key_score_bits(u32 k) { return k; }
 

@@ -235,6 +235,549 @@ __global__ void __launch_bounds__(kBm25Warps * 32) bm25_kernel(const Bm25Args<W>
   }
 }
 
+
+// mbarrier wait with a watchdog: a pipeline bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_wd(u64* bar, u32 parity) {
+  const u32 addr = smem_u32(bar);
+  for (u32 spins = 0;; ++spins) {
+    u32 done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins == (1u << 27)) __trap();
+  }
+}
+
+// barrier over the 256 consumer threads of the streaming kernel (the producer warp never joins)
+__device__ __forceinline__ void named_bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// bitonic sort (descending) by the 256 consumer threads; n is a power of two
+template <class K>
+__device__ __forceinline__ void consumer_sort_desc(K* a, int n, int ct) {
+  for (int ls = 1; (1 << ls) <= n; ++ls) {
+    for (int lj = ls - 1; lj >= 0; --lj) {
+      const int stride = 1 << lj;
+      for (int t = ct; t < (n >> 1); t += 256) {
+        const int i = ((t >> lj) << (lj + 1)) | (t & (stride - 1));
+        const bool up = ((i >> ls) & 1) != 0;
+        cmpxchg_desc(a, i, i | stride, up);
+      }
+      named_bar_sync_256();
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// K4s: streaming BM25 kernel (default).  Same arithmetic and results as bm25_kernel above; organised like
+// the flat scan: persistent CTAs, one producer warp driving the bulk-copy engine, eight consumer warps.
+//
+//   work item = (query, block of kStreamBlk = 4096 documents); CTA c takes items c, c + grid, ...
+//   producer   per item and token: segment bounds from the block index skip[term][block] (built once per
+//              index; no binary search on the query path), then 16-byte aligned bulk copies of the segment's
+//              (doc id, weight) arrays into a ring of 1024-posting stages.  It runs ahead of the consumers
+//              across item boundaries, so the index / term-table latency is hidden behind their work.
+//   consumers  acc[doc] += idf * w for the postings of a stage (documents are unique within a token, tokens are
+//              separated by a named barrier: float64 sums in the reference's order, no atomics), then the
+//              fused select over the 4096 accumulators: candidates are the documents with score >= the query's
+//              global threshold tau_g (k-th best score any finished block has published), reduced to the best k
+//              by a histogram select on the ordered score bits (equal scores: ascending id), sorted, written to
+//              the per-(query, block) list; bm25_merge_kernel (one CTA per query) merges the lists.
+// Shared memory: 32 KiB accumulators + 6 x 8 KiB (12 KiB with float64 weights) ring + 8 KiB histogram + 8 KiB
+// list = 97 KiB, two CTAs per SM.
+// Algorithmic bytes per query: sum_t df_t * (4 + sizeof(weight)); the block index adds 8 B per (token, block).
+// ----------------------------------------------------------------------------------------------
+static const int kStreamBlk = 4096;       // documents per work item (block index granularity)
+static const int kStreamChunk = 1024;     // postings per ring stage
+static const int kStreamStages = 6;
+static const int kStreamSelCap = 512;     // candidate list (u128 keys)
+static const int kStreamMaxK = 384;       // k + 64 spill keys must fit the list
+static const int kStreamThreads = 9 * 32; // 8 consumer warps + producer warp
+
+template <class W>
+struct Bm25StreamArgs {
+  const long long* indptr;
+  const int* doc_ids;
+  const W* weight;
+  const double* idf;
+  const u32* skip;          // [V][n_blocks + 1] first posting (relative to indptr[t]) with doc >= b * kStreamBlk; may be NULL
+  long long n_docs;
+  int n_blocks;
+  const int* term_ids;
+  const int* term_offsets;
+  int q_base, nq_launch;
+  int k;
+  u128* partial;            // [nq_launch][n_blocks][k]
+  u64* tau_g;               // [nq_launch]
+  double* dense;            // non-NULL: write the scores of query q_base densely, skip the select
+  int debug_skip;           // perf experiments only (wrong results): 1 no select, 2 no accumulate
+};
+
+struct StreamMeta {
+  long long p_begin, p_end;  // valid posting range of this token inside the item's block
+  long long base;            // posting index of element 0 of the stage (16-byte aligned start)
+  double idf;
+  int count;                 // elements in the stage
+  int flags;                 // 1: last stage of the token, 2: last stage of the item
+};
+
+template <class W>
+__global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25StreamArgs<W> a) {
+  extern __shared__ __align__(128) unsigned char stream_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kStageBytes = kStreamChunk * (4 + static_cast<int>(sizeof(W)));
+  double* acc = reinterpret_cast<double*>(stream_smem);                                   // [kStreamBlk]
+  unsigned char* ring = stream_smem + kStreamBlk * sizeof(double);                        // [stages][ids | weights]
+  StreamMeta* meta = reinterpret_cast<StreamMeta*>(ring + kStreamStages * kStageBytes);  // [stages]
+  u64* full = reinterpret_cast<u64*>(meta + kStreamStages);
+  u64* empty = full + kStreamStages;
+  u64* ctl = empty + kStreamStages;                                                    // [8] select control words
+  u32* hist = reinterpret_cast<u32*>(ctl + 8);                                         // [kSelBins]
+  u128* sel = reinterpret_cast<u128*>(
+      (reinterpret_cast<uintptr_t>(hist + kSelBins) + 15) & ~static_cast<uintptr_t>(15));  // [kStreamSelCap]
+
+  if (tid == 0) {
+    for (int s = 0; s < kStreamStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long long n_items = static_cast<long long>(a.nq_launch) * a.n_blocks;
+  // CTA c takes items c, c + grid, ...: at any time the whole grid works on one or two queries, so a query's
+  // threshold tau_g saturates within its first wave of blocks and the remaining blocks select next to nothing
+  const long long item_lo = blockIdx.x, item_hi = n_items, item_step = gridDim.x;
+
+  if (warp == 8) {
+    // ======================= producer warp =======================
+    // The token table of the current query (term, list start, idf) stays in registers from item to item; only
+    // the two block-index entries per token change, and those of the NEXT item are loaded while this item's
+    // copies are being issued.
+    const u64 policy = l2_policy_evict_first();
+    int s = 0;
+    u32 ph = 0;
+    int cur_q = -1, t0 = 0, t1 = 0;
+    int term = 0;          // lane-held token table (first 32 tokens of the query)
+    long long ib = 0, ie = 0;
+    double idfv = 0.0;
+    u32 nx0 = 0, nx1 = 0;  // prefetched block-index entries of the next item (lane-held)
+    bool have_next = false;
+    for (long long item = item_lo; item < item_hi; item += item_step) {
+      const int ql = static_cast<int>(item / a.n_blocks);
+      const int b = static_cast<int>(item - static_cast<long long>(ql) * a.n_blocks);
+      const long long lo = static_cast<long long>(b) * kStreamBlk;
+      const long long hi = min(a.n_docs, lo + kStreamBlk);
+      if (ql != cur_q) {
+        cur_q = ql;
+        const int qi = a.q_base + ql;
+        t0 = a.term_offsets[qi];
+        t1 = a.term_offsets[qi + 1];
+        if (t0 + lane < t1) {
+          term = a.term_ids[t0 + lane];
+          ib = a.indptr[term];
+          ie = a.indptr[term + 1];
+          idfv = a.idf[term];
+        }
+        have_next = false;
+      }
+      if (t1 == t0) {  // a query without known tokens: one empty stage closes the item
+        if (lane == 0) {
+          mbar_wait_wd(&empty[s], ph ^ 1u);
+          meta[s].count = 0;
+          meta[s].p_begin = meta[s].p_end = meta[s].base = 0;
+          meta[s].idf = 0.0;
+          meta[s].flags = 3;
+          mbar_arrive(&full[s]);
+        }
+        if (++s == kStreamStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+        continue;
+      }
+      for (int tb = t0; tb < t1; tb += 32) {
+        const int j = tb + lane;
+        long long p0 = 0, p1 = 0;
+        double tidf = 0.0;
+        if (j < t1) {
+          int tt = term;
+          long long tib = ib, tie = ie;
+          tidf = idfv;
+          if (tb != t0) {  // queries longer than 32 tokens: later rounds are fetched on the fly
+            tt = a.term_ids[j];
+            tib = a.indptr[tt];
+            tie = a.indptr[tt + 1];
+            tidf = a.idf[tt];
+          }
+          if (a.skip) {
+            u32 e0, e1;
+            if (tb == t0 && have_next) {
+              e0 = nx0;
+              e1 = nx1;
+            } else {
+              const u32* row = a.skip + static_cast<size_t>(tt) * (a.n_blocks + 1) + b;
+              e0 = row[0];
+              e1 = row[1];
+            }
+            p0 = tib + e0;
+            p1 = tib + e1;
+          } else {
+            p0 = lower_bound_i32(a.doc_ids, tib, tie, lo);
+            p1 = lower_bound_i32(a.doc_ids, p0, tie, hi);
+          }
+        }
+        if (tb == t0) {  // prefetch the next item's entries when it belongs to the same query
+          have_next = false;
+          if (a.skip && item + item_step < item_hi && b + item_step < a.n_blocks) {
+            if (t0 + lane < t1) {
+              const u32* row = a.skip + static_cast<size_t>(term) * (a.n_blocks + 1) + (b + item_step);
+              nx0 = row[0];
+              nx1 = row[1];
+            }
+            have_next = true;
+          }
+        }
+        const int nt = min(32, t1 - tb);
+        for (int u = 0; u < nt; ++u) {
+          const long long q0 = __shfl_sync(0xffffffffu, p0, u), q1 = __shfl_sync(0xffffffffu, p1, u);
+          const double qidf = __shfl_sync(0xffffffffu, tidf, u);
+          const bool last_token = (tb + u == t1 - 1);
+          // 16-byte aligned copy window [a0, a1) around [q0, q1); consumers mask by posting index
+          const long long a0 = q0 & ~3LL;
+          const long long a1 = (q1 + 3) & ~3LL;
+          long long c0 = a0;
+          do {
+            const long long c1 = min(a1, c0 + kStreamChunk);
+            const int cnt = static_cast<int>(c1 - c0);
+            const bool last_chunk = c1 >= a1;
+            if (lane == 0) {
+              mbar_wait_wd(&empty[s], ph ^ 1u);
+              StreamMeta& m = meta[s];
+              m.p_begin = q0;
+              m.p_end = q1;
+              m.base = c0;
+              m.idf = qidf;
+              m.count = cnt;
+              m.flags = (last_chunk ? 1 : 0) | ((last_chunk && last_token) ? 2 : 0);
+              unsigned char* st = ring + static_cast<size_t>(s) * kStageBytes;
+              if (cnt > 0) {
+                mbar_arrive_expect_tx(&full[s], static_cast<u32>(cnt) * (4u + static_cast<u32>(sizeof(W))));
+                bulk_g2s(st, a.doc_ids + c0, static_cast<u32>(cnt) * 4u, &full[s], policy);
+                bulk_g2s(st + kStreamChunk * 4, a.weight + c0, static_cast<u32>(cnt) * static_cast<u32>(sizeof(W)), &full[s],
+                         policy);
+              } else {
+                mbar_arrive(&full[s]);
+              }
+            }
+            if (++s == kStreamStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+            c0 = c1;
+          } while (c0 < a1);
+        }
+      }
+    }
+    return;
+  }
+
+  // ======================= consumer warps =======================
+  const int ct = tid;  // 0..255
+#pragma unroll
+  for (int i = 0; i < kStreamBlk / 256; ++i) acc[i * 256 + ct] = 0.0;
+  named_bar_sync_256();
+  int s = 0;
+  u32 ph = 0;
+  u32* s_cnt = reinterpret_cast<u32*>(ctl);        // [0] candidates, [1] selected, [2] threshold bin, [3] above
+  u64* s_mn = ctl + 2;
+  u64* s_mx = ctl + 3;
+  for (long long item = item_lo; item < item_hi; item += item_step) {
+    const int ql = static_cast<int>(item / a.n_blocks);
+    const int b = static_cast<int>(item - static_cast<long long>(ql) * a.n_blocks);
+    const long long lo = static_cast<long long>(b) * kStreamBlk;
+    const int nb = static_cast<int>(min(a.n_docs, lo + kStreamBlk) - lo);
+    // ---- accumulate: stages arrive in token order (acc is zero: cleared at start / by the previous select) ----
+    for (;;) {
+      mbar_wait_wd(&full[s], ph);
+      const StreamMeta m = meta[s];
+      const unsigned char* st = ring + static_cast<size_t>(s) * kStageBytes;
+      const int* ids = reinterpret_cast<const int*>(st);
+      const W* ws = reinterpret_cast<const W*>(st + kStreamChunk * 4);
+      for (int i = ct; i < m.count; i += 256) {
+        const long long p = m.base + i;
+        if (p >= m.p_begin && p < m.p_end && !(a.debug_skip & 2)) {
+          const int dl = ids[i] - static_cast<int>(lo);
+          // explicit rn intrinsics: no FMA contraction, numpy forms idf*w and the sum separately
+          acc[dl] = __dadd_rn(acc[dl], __dmul_rn(m.idf, static_cast<double>(ws[i])));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == kStreamStages) {
+        s = 0;
+        ph ^= 1u;
+      }
+      if (m.flags & 1) named_bar_sync_256();  // token boundary: the next token may touch the same documents
+      if (m.flags & 2) break;
+    }
+    if (a.dense) {
+      for (int i = ct; i < kStreamBlk; i += 256) {
+        if (i < nb) a.dense[lo + i] = acc[i];
+        acc[i] = 0.0;
+      }
+      named_bar_sync_256();
+      continue;
+    }
+
+    // ---- fused select: best k of this block among the documents that can still matter ----
+    const int k = a.k;
+    const u64 taug = (a.debug_skip & 1) ? ~0ull : *(reinterpret_cast<volatile u64*>(a.tau_g) + ql);
+    u64 sk[kStreamBlk / 256];
+    u32 act = 0;  // bit i: document i * 256 + ct is a live candidate
+#pragma unroll
+    for (int i = 0; i < kStreamBlk / 256; ++i) {
+      const int dcl = i * 256 + ct;
+      sk[i] = double_to_ordered(acc[dcl]);
+      acc[dcl] = 0.0;  // ready for the next item (this thread is the only reader of these entries)
+      if (dcl < nb && sk[i] >= taug) act |= 1u << i;
+    }
+    if (ct == 0) {
+      s_cnt[0] = 0;
+      s_cnt[1] = 0;
+    }
+    named_bar_sync_256();
+    {
+      const u32 c = __reduce_add_sync(0xffffffffu, static_cast<u32>(__popc(act)));
+      if (lane == 0 && c) atomicAdd(&s_cnt[0], c);
+    }
+    named_bar_sync_256();
+    u128* dst = a.partial + (static_cast<size_t>(ql) * a.n_blocks + b) * k;
+    if (s_cnt[0] == 0) {  // no document of this block can enter the query's top k (usual after the first wave)
+      for (int i = ct; i < k; i += 256) dst[i] = 0;
+      named_bar_sync_256();
+      continue;
+    }
+    int need = min(k, static_cast<int>(s_cnt[0]));
+    int live = static_cast<int>(s_cnt[0]);
+    // narrow the live set by histogram levels until what is left fits the list
+    while (live > need && live > 64) {
+      if (ct == 0) {
+        *s_mn = ~0ull;
+        *s_mx = 0ull;
+      }
+      for (int i = ct; i < kSelBins; i += 256) hist[i] = 0;
+      named_bar_sync_256();
+      u64 mn = ~0ull, mx = 0ull;
+#pragma unroll
+      for (int i = 0; i < kStreamBlk / 256; ++i) {
+        if ((act >> i) & 1u) {
+          mn = sk[i] < mn ? sk[i] : mn;
+          mx = sk[i] > mx ? sk[i] : mx;
+        }
+      }
+      // warp-reduce first: 64-bit shared-memory min / max are CAS loops and collapse under 256-way contention
+#pragma unroll
+      for (int mm = 16; mm > 0; mm >>= 1) {
+        const u64 omn = __shfl_xor_sync(0xffffffffu, mn, mm), omx = __shfl_xor_sync(0xffffffffu, mx, mm);
+        mn = omn < mn ? omn : mn;
+        mx = omx > mx ? omx : mx;
+      }
+      if (lane == 0 && mn <= mx) {
+        atomicMin(s_mn, mn);
+        atomicMax(s_mx, mx);
+      }
+      named_bar_sync_256();
+      const u64 gmn = *s_mn, range = *s_mx - gmn;
+      if (range == 0) break;  // all live scores equal: ascending id decides (below)
+      int sh = 0;
+      while ((range >> sh) >= static_cast<u64>(kSelBins)) ++sh;
+      // scores cluster in a few bins: lanes with the same bin combine their increments (one atomic per group)
+#pragma unroll
+      for (int i = 0; i < kStreamBlk / 256; ++i) {
+        const bool on = (act >> i) & 1u;
+        const u32 bin = on ? static_cast<u32>((sk[i] - gmn) >> sh) : 0xFFFFFFFFu;
+        const u32 peers = __match_any_sync(0xffffffffu, bin);
+        if (on && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<u32>(__popc(peers)));
+      }
+      named_bar_sync_256();
+      if (warp == 0) {  // bins from the top until `need` keys are covered
+        constexpr int per = kSelBins / 32;
+        const int top = kSelBins - per * lane;
+        u32 sum = 0;
+        for (int bb = top - 1; bb >= top - per; --bb) sum += hist[bb];
+        u32 incl = sum;
+#pragma unroll
+        for (int mm = 1; mm < 32; mm <<= 1) {
+          const u32 v = __shfl_up_sync(0xffffffffu, incl, mm);
+          if (lane >= mm) incl += v;
+        }
+        const u32 before = incl - sum;
+        if (before < static_cast<u32>(need) && incl >= static_cast<u32>(need)) {
+          u32 accn = before;
+          int bb = top - 1;
+          for (; bb > top - per; --bb) {
+            if (accn + hist[bb] >= static_cast<u32>(need)) break;
+            accn += hist[bb];
+          }
+          s_cnt[2] = static_cast<u32>(bb);
+          s_cnt[3] = accn;  // keys in the bins above the threshold bin
+        }
+      }
+      named_bar_sync_256();
+      const u32 bstar = s_cnt[2], above = s_cnt[3], bucket = hist[bstar];
+      // keys above the threshold bin are in the answer; the bin itself stays live
+#pragma unroll
+      for (int i = 0; i < kStreamBlk / 256; ++i) {
+        if ((act >> i) & 1u) {
+          const u32 bin = static_cast<u32>((sk[i] - gmn) >> sh);
+          if (bin > bstar) {
+            const u32 pos = atomicAdd(&s_cnt[1], 1u);
+            sel[pos] = (static_cast<u128>(sk[i]) << 64) | static_cast<u128>(0xFFFFFFFFu - static_cast<u32>(lo + i * 256 + ct));
+          }
+          if (bin != bstar) act &= ~(1u << i);
+        }
+      }
+      need -= static_cast<int>(above);
+      live = static_cast<int>(bucket);
+      named_bar_sync_256();
+    }
+    if (live > need && live > 64) {
+      // all live documents share one score: the `need` lowest ids win.  Rank = live documents before this one
+      // in id order (row i * 256 + ct): rows in order, threads in order inside a row.
+#pragma unroll
+      for (int i = 0; i < kStreamBlk / 256; ++i) {
+        if (need <= 0) break;  // uniform
+        const bool on = (act >> i) & 1u;
+        const u32 bal = __ballot_sync(0xffffffffu, on);
+        u32* wcnt = hist;  // [8] per-warp counts of this row
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        named_bar_sync_256();
+        u32 before = 0, row_total = 0;
+        for (int w = 0; w < 8; ++w) {
+          const u32 c = wcnt[w];
+          if (w < warp) before += c;
+          row_total += c;
+        }
+        const u32 rank = before + __popc(bal & ((1u << lane) - 1u));
+        if (on && rank < static_cast<u32>(need)) {
+          const u32 pos = atomicAdd(&s_cnt[1], 1u);
+          sel[pos] = (static_cast<u128>(sk[i]) << 64) | static_cast<u128>(0xFFFFFFFFu - static_cast<u32>(lo + i * 256 + ct));
+        }
+        need -= static_cast<int>(min(row_total, static_cast<u32>(need)));
+        named_bar_sync_256();
+      }
+      act = 0;
+    }
+    // what is still live (<= need, or <= 64 spill keys) joins the list; the sort settles the order
+#pragma unroll
+    for (int i = 0; i < kStreamBlk / 256; ++i) {
+      if ((act >> i) & 1u) {
+        const u32 pos = atomicAdd(&s_cnt[1], 1u);
+        sel[pos] = (static_cast<u128>(sk[i]) << 64) | static_cast<u128>(0xFFFFFFFFu - static_cast<u32>(lo + i * 256 + ct));
+      }
+    }
+    named_bar_sync_256();
+    const int n_sel = static_cast<int>(s_cnt[1]);
+    int p2 = 2;
+    while (p2 < n_sel) p2 <<= 1;
+    if (p2 > kStreamSelCap) p2 = kStreamSelCap;
+    for (int i = n_sel + ct; i < p2; i += 256) sel[i] = 0;
+    named_bar_sync_256();
+    if (p2 <= 128) {  // short list: one warp sorts it without block-wide barriers
+      if (warp == 0) warp_sort_desc(sel, p2, lane);
+      named_bar_sync_256();
+    } else {
+      consumer_sort_desc(sel, p2, ct);
+    }
+    for (int i = ct; i < k; i += 256) dst[i] = i < p2 ? sel[i] : static_cast<u128>(0);
+    if (ct == 0 && n_sel >= k) {
+      // k documents of this block score >= sel[k - 1]: nothing below it can enter the query's top k
+      atomicMax(a.tau_g + ql, static_cast<u64>(sel[k - 1] >> 64));
+    }
+    named_bar_sync_256();  // the list area is reused by the next item
+  }
+}
+
+// one CTA per query: merge the per-block lists of the streaming kernel into the query's top k, reset its threshold.
+// theta = k-th largest of the lists' best scores (k lists hold a key >= theta each, so the answer lies above it);
+// the keys above theta — a little over k of them — are gathered and the best k selected, both by histogram.
+static const int kMergeLists = 8192;   // list maxima the threshold step can take (33M documents per shard)
+static const int kMergeCap = 4096;     // gathered keys
+
+__global__ void __launch_bounds__(1024) bm25_merge_kernel(const u128* __restrict__ partial, int n_lists, int k, int q_base,
+                                                          u64* __restrict__ tau_g, double* __restrict__ S,
+                                                          long long* __restrict__ I, long long id_offset) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  u128* buf = reinterpret_cast<u128*>(merge_smem);                       // [kMergeCap]; first the u32 list maxima
+  u128* top = buf + kMergeCap;                                           // [1024]
+  u32* hist = reinterpret_cast<u32*>(top + 1024);                        // [kSelBins + 4]
+  __shared__ u64 ctl[4];
+  __shared__ u32 s_n;
+  const int ql = blockIdx.x, qi = q_base + ql, tid = threadIdx.x, nt = blockDim.x;
+  const u128* src = partial + static_cast<size_t>(ql) * n_lists * k;
+  const long long total = static_cast<long long>(n_lists) * k;
+  u32 theta = 0;
+  if (n_lists >= k && n_lists <= kMergeLists) {
+    u32* mx = reinterpret_cast<u32*>(buf);
+    u32* top32 = reinterpret_cast<u32*>(top);
+    for (int l = tid; l < n_lists; l += nt) mx[l] = key_score_bits(src[static_cast<long long>(l) * k]);
+    __syncthreads();
+    block_topk_hist(mx, n_lists, kMergeLists, k, hist, top32, 1024);
+    theta = top32[k - 1];
+    __syncthreads();
+  }
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (long long i = tid; i < total; i += nt) {
+    const u128 v = src[i];
+    if (v != 0 && key_score_bits(v) >= theta) {
+      const u32 pos = atomicAdd(&s_n, 1u);
+      if (pos < static_cast<u32>(kMergeCap)) buf[pos] = v;
+    }
+  }
+  __syncthreads();
+  const u32 n = s_n;
+  const u128* res = top;
+  if (n <= static_cast<u32>(kMergeCap)) {
+    block_topk_hist(buf, static_cast<int>(n), kMergeCap, k, hist, top, 1024);
+  } else {  // heavy ties at the threshold: the streaming select of the shared helper
+    block_select_lists(src, n_lists, k, k, buf, kMergeCap, ctl);
+    res = buf;
+  }
+  for (int i = tid; i < k; i += nt) {
+    const u128 key = res[i];
+    const size_t o = static_cast<size_t>(qi) * k + i;
+    if (key == 0) {
+      S[o] = -1.7976931348623157e308;
+      I[o] = -1;
+    } else {
+      S[o] = ordered_to_double(static_cast<u64>(key >> 64));
+      I[o] = static_cast<long long>(0xFFFFFFFFu - static_cast<u32>(key)) + id_offset;
+    }
+  }
+  if (tid == 0) tau_g[ql] = 0;
+}
+
+// block index: skip[t][b] = number of postings of term t with doc id < b * kStreamBlk
+__global__ void bm25_skip_kernel(const long long* __restrict__ indptr, const int* __restrict__ doc_ids, int n_terms,
+                                 int n_blocks, u32* __restrict__ skip) {
+  const long long total = static_cast<long long>(n_terms) * (n_blocks + 1);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / (n_blocks + 1));
+    const int b = static_cast<int>(i - static_cast<long long>(t) * (n_blocks + 1));
+    const long long ib = indptr[t], ie = indptr[t + 1];
+    skip[i] = static_cast<u32>(lower_bound_i32(doc_ids, ib, ie, static_cast<long long>(b) * kStreamBlk) - ib);
+  }
+}
+
 // build-time: weight[p] = tf*(k1+1) / (tf + k1*(1 - b + b*dl/avgdl)), numpy's operation order
 template <class W>
 __global__ void bm25_weight_kernel(const int* __restrict__ doc_ids, const int* __restrict__ tf,
@@ -269,6 +812,8 @@ struct b2r_bm25 {
   int* doc_ids = nullptr;
   void* weight = nullptr;
   double* idf = nullptr;
+  unsigned* skip = nullptr;   // block index [n_terms][n_blocks + 1] of the streaming kernel (may be absent)
+  int n_blocks = 0;           // ceil(n_docs / kStreamBlk)
   bool owns_doc_ids = true;
   int num_sms = 148;
   std::mutex mu;
@@ -365,11 +910,95 @@ static int bm25_launch_t(b2r_bm25* h, const Bm25Plan& p, Bm25Args<W> a, int nq_l
   return B2R_OK;
 }
 
+template <class W>
+static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<W> a, cudaStream_t stream, bool overlap_prev) {
+  a.weight = static_cast<const W*>(h->weight);
+  auto kern = bm25_stream_kernel<W>;
+  const size_t smem = kStreamBlk * sizeof(double) + static_cast<size_t>(kStreamStages) * kStreamChunk * (4 + sizeof(W)) +
+                      kStreamStages * sizeof(StreamMeta) + 2 * kStreamStages * 8 + 8 * 8 + kSelBins * 4 + 16 +
+                      static_cast<size_t>(kStreamSelCap) * 16;
+  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const long long n_items = static_cast<long long>(a.nq_launch) * a.n_blocks;
+  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024))));
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_items, static_cast<long long>(h->num_sms) * per_sm)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kStreamThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap_prev ? 1 : 0;  // see bm25_launch_t
+  B2R_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  B2R_CUDA(cudaGetLastError());
+  return B2R_OK;
+}
+
+static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term_offsets_dev, int nq, int k, double* S_dev,
+                           long long* I_dev, long long id_offset, double* dense_dev, cudaStream_t stream,
+                           bool overlap_prev) {
+  Bm25Ws ws;
+  int rc = bm25_get_ws(h, stream, &ws);
+  if (rc) return rc;
+  const size_t per_q = static_cast<size_t>(h->n_blocks) * k * 16;
+  long long max_q = static_cast<long long>((ws.bytes - kBm25CtlBytes) / per_q);
+  max_q = std::min<long long>(max_q, kBm25MaxQPerLaunch);
+  if (max_q < 1) return fail(B2R_ERR_UNSUPPORTED, "bm25: workspace too small for one query (corpus x k too large)");
+  for (int q0 = 0; q0 < nq; q0 += static_cast<int>(max_q)) {
+    Bm25StreamArgs<float> a;
+    a.indptr = h->indptr;
+    a.doc_ids = h->doc_ids;
+    a.weight = nullptr;
+    a.idf = h->idf;
+    a.skip = h->skip;
+    a.n_docs = h->n_docs;
+    a.n_blocks = h->n_blocks;
+    a.term_ids = term_ids_dev;
+    a.term_offsets = term_offsets_dev;
+    a.q_base = q0;
+    a.nq_launch = static_cast<int>(std::min<long long>(max_q, nq - q0));
+    a.k = k;
+    a.partial = reinterpret_cast<u128*>(ws.base + kBm25CtlBytes);
+    a.tau_g = reinterpret_cast<u64*>(ws.base + kBm25CtlBytes / 2);
+    a.dense = dense_dev;
+    a.debug_skip = tunable("bm25.debug_skip");
+    if (h->weight_bits == 64) {
+      Bm25StreamArgs<double> ad;
+      memcpy(&ad, &a, sizeof(a));  // identical layout: only the weight pointer type differs
+      rc = bm25_stream_launch<double>(h, ad, stream, overlap_prev && q0 == 0);
+    } else {
+      rc = bm25_stream_launch<float>(h, a, stream, overlap_prev && q0 == 0);
+    }
+    if (rc) return rc;
+    ++launch_counter();
+    if (!dense_dev) {
+      const int msmem = kMergeCap * 16 + 1024 * 16 + (kSelBins + 4) * 4;
+      auto mk = bm25_merge_kernel;
+      B2R_CUDA(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
+      mk<<<a.nq_launch, 1024, msmem, stream>>>(a.partial, a.n_blocks, k, q0, a.tau_g, S_dev, I_dev, id_offset);
+      B2R_CUDA(cudaGetLastError());
+      ++launch_counter();
+    }
+  }
+  return B2R_OK;
+}
+
 // shared by topk (dense == nullptr) and scores (dense != nullptr, one query)
 static int bm25_run(b2r_bm25* h, const int* term_ids_dev, const int* term_offsets_dev, int nq, int k, double* S_dev,
                     long long* I_dev, long long id_offset, double* dense_dev, cudaStream_t stream,
                     bool overlap_prev = false) {
   launch_counter() = 0;
+  // Alone, the streaming kernel is ~1.6x faster (profiles/r01_bm25.md); launched BESIDE the flat scan its busy
+  // consumer warps take more from the scan than the latency-bound doc-block kernel does, so the hybrid
+  // single-query path keeps the latter (bm25.v1 = 2 forces the streaming kernel there too).
+  const int v1 = tunable("bm25.v1");
+  const bool use_stream = v1 == 2 || (v1 == 0 && !(overlap_prev && nq <= 4));
+  if (use_stream && k <= kStreamMaxK) {
+    return bm25_run_stream(h, term_ids_dev, term_offsets_dev, nq, k, S_dev, I_dev, id_offset, dense_dev, stream, overlap_prev);
+  }
   Bm25Plan p;
   int rc = bm25_plan(h, k, &p);
   if (rc) return rc;
@@ -458,7 +1087,7 @@ int b2r_bm25_create_ex(int64_t n_docs, int32_t n_terms, const int64_t* indptr, c
   h->num_sms = prop.multiProcessorCount;
   int* tf_dev = nullptr;
   int* dl_dev = nullptr;
-  const size_t np_alloc = static_cast<size_t>(std::max<long long>(n_post, 1));
+  const size_t np_alloc = static_cast<size_t>(std::max<long long>(n_post, 1)) + 4;
   cudaError_t e = cudaMalloc(&h->indptr, (static_cast<size_t>(n_terms) + 1) * sizeof(long long));
   if (e == cudaSuccess) e = cudaMalloc(&h->idf, static_cast<size_t>(n_terms) * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&h->weight, np_alloc * (weight_bits / 8));
@@ -495,6 +1124,21 @@ int b2r_bm25_create_ex(int64_t n_docs, int32_t n_terms, const int64_t* indptr, c
   if (!inputs_on_device) {
     if (tf_dev) cudaFree(tf_dev);
     if (dl_dev) cudaFree(dl_dev);
+  }
+  if (e == cudaSuccess) {
+    // block index of the streaming kernel: 4 bytes per (term, 4096-document block); skipped when it would
+    // outweigh a quarter of the postings (huge vocabularies over huge shards fall back to binary searches)
+    h->n_blocks = static_cast<int>((n_docs + kStreamBlk - 1) / kStreamBlk);
+    const size_t skip_bytes = static_cast<size_t>(n_terms) * (static_cast<size_t>(h->n_blocks) + 1) * sizeof(unsigned);
+    const size_t post_bytes = static_cast<size_t>(n_post) * (4 + weight_bits / 8);
+    if (skip_bytes <= std::max<size_t>(static_cast<size_t>(256) << 20, post_bytes / 4)) {
+      e = cudaMalloc(&h->skip, skip_bytes);
+      if (e == cudaSuccess) {
+        bm25_skip_kernel<<<prop.multiProcessorCount * 8, 256>>>(h->indptr, h->doc_ids, n_terms, h->n_blocks, h->skip);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      }
+    }
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
@@ -640,6 +1284,7 @@ int b2r_bm25_destroy(b2r_bm25* h) {
   if (h->doc_ids) cudaFree(h->doc_ids);
   if (h->weight) cudaFree(h->weight);
   if (h->idf) cudaFree(h->idf);
+  if (h->skip) cudaFree(h->skip);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   delete h;
   return B2R_OK;
