@@ -953,7 +953,7 @@ static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term
     a.doc_ids = h->doc_ids;
     a.weight = nullptr;
     a.idf = h->idf;
-    a.skip = h->skip;
+    a.skip = tunable("bm25.no_skip") ? nullptr : h->skip;
     a.n_docs = h->n_docs;
     a.n_blocks = h->n_blocks;
     a.term_ids = term_ids_dev;

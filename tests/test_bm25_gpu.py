@@ -240,3 +240,53 @@ def test_device_built_postings_vs_csr_oracle(b2r):
     S32, I32 = idx32.topk([np.array(q, np.int32) for q in queries], 30)
     want = np.stack([bm25_scores_csr_ref(indptr, dids, tf, dl, avgdl, idf, q) for q in queries])
     oracle.assert_topk_equivalent(S32, I32, want, 30, rtol=1e-6, atol=1e-9, what="bm25 f32 dev", pad_score=PAD)
+
+
+def test_streaming_kernel_variants_agree(b2r):
+    """The streaming kernel (default), the same without its block index (binary searches in the producer) and the
+    doc-block kernel must return bit-identical scores and ids; k = 384 is the streaming kernel's largest k, 500 falls
+    back to the doc-block kernel."""
+    from rag_challenge_2_b200 import _lib
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    docs = s.token_corpus_np(30000, vocab=3000, seed=21)
+    ref = oracle.BM25OkapiRef(docs)
+    idx = BM25Okapi(docs, weight_bits=64)
+    queries = [as_tokens(q) for q in s.token_queries_np(9, vocab=3000, seed=22)]
+    queries.append([])                                   # no known token: every score 0, lowest ids win
+    queries.append(["t2999", "t2999", "nope"])           # rare term twice + unknown token
+    wants = [ref.get_scores(q) if q else np.zeros(len(docs)) for q in queries]
+    for k in (1, 30, 384, 500):
+        base = idx.topk(queries, k)
+        for qi, want in enumerate(wants):
+            top = oracle.bm25_topn_ref(want, k)
+            assert np.array_equal(base[1][qi], top), f"k={k} q{qi}"
+            assert np.array_equal(base[0][qi], want[top])
+        for key in ("bm25.no_skip", "bm25.v1"):
+            _lib.tunable_set(key, 1)
+            try:
+                S, I = idx.topk(queries, k)
+            finally:
+                _lib.tunable_set(key, 0)
+            assert np.array_equal(I, base[1]) and np.array_equal(S, base[0]), f"{key} k={k}"
+
+
+def test_streaming_kernel_heavy_ties(b2r):
+    """Thousands of documents with exactly equal scores around the k-th place (identical documents): the histogram
+    select cannot separate them by score and must fall back to ascending id, as Python's stable sort does."""
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    rng = np.random.default_rng(23)
+    proto = [["alpha", "beta", "gamma"], ["alpha", "delta"], ["beta", "beta", "epsilon", "zeta"], ["eta"]]
+    docs = [list(proto[int(i)]) for i in rng.integers(0, 4, 12000)]
+    docs[777] = ["alpha", "alpha", "alpha", "beta"]
+    ref = oracle.BM25OkapiRef(docs)
+    idx = BM25Okapi(docs, weight_bits=64)
+    for q in (["alpha"], ["beta", "zeta"], ["eta", "alpha", "nothing"], ["omega"]):
+        want = ref.get_scores(q)
+        for k in (5, 100, 300):
+            S, I = idx.topk([q], k)
+            top = oracle.bm25_topn_ref(want, k)
+            assert np.array_equal(I[0], top), (q, k)
+            assert np.array_equal(S[0], want[top])
