@@ -417,7 +417,8 @@ def run_b200(args):
                          "frac_of_8TBps_nominal": achieved / 8000.0,
                          "share_of_step": scan_ms * max(1, -(-args.nq // 4)) / (ms_total / args.steps)},
             "clocks": sampler.summary(t_wall0, t_wall1),
-            "bm25": {"postings_local": n_post, "bytes_per_posting": 4 + wbits // 8, "kernel_ms_in_step": bm25_ms},
+            "bm25": {"postings_local": n_post, "bytes_per_posting": 4 + wbits // 8,
+                     "kernel_ms_in_step": (None if pdl or not bm25_events else bm25_ms)},
             "top1_last_step": top1,
             "extras": extras,
         }

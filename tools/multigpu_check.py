@@ -17,7 +17,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-n, d, V, k, nq = 400_000, 1024, 20_000, 30, 12
+n, d, V, k, nq = 16 * synth.ROW_BLOCK - 3_000, 1024, 20_000, 30, 12  # ragged last shard, none empty up to 8 ranks
 bounds = hybrid.shard_bounds(n, world, synth.ROW_BLOCK)
 lo, hi = bounds[rank], bounds[rank + 1]
 
