@@ -39,6 +39,53 @@ def corpus_statistics(nd, corpus_size, epsilon=0.25):
     return idf, average_idf
 
 
+def token_stream_statistics(token_ids, doc_offsets, n_terms, epsilon=0.25, device=None, group=None):
+    """Tokenised corpus -> CSR postings + rank_bm25 statistics with torch ops on `device` (CUDA in the product;
+    the CPU is only used by the gloo plumbing test).  Returns dict(indptr, doc_ids, tf, doc_len tensors; idf
+    float64 numpy [n_terms] (0 for terms that never occur); avgdl; average_idf; corpus_size)."""
+    import torch
+
+    tok = torch.as_tensor(token_ids).to(device=device, dtype=torch.int64).reshape(-1)
+    offs = torch.as_tensor(doc_offsets).to(device=device, dtype=torch.int64).reshape(-1)
+    n_docs = int(offs.shape[0]) - 1
+    lens = offs[1:] - offs[:-1]
+    doc_of = torch.repeat_interleave(torch.arange(n_docs, device=tok.device), lens)
+    key, _ = torch.sort(tok * max(n_docs, 1) + doc_of)
+    uniq, counts = torch.unique_consecutive(key, return_counts=True)
+    term = uniq // max(n_docs, 1)
+    doc_ids = (uniq - term * max(n_docs, 1)).to(torch.int32)
+    df = torch.bincount(term, minlength=n_terms)
+    indptr = torch.zeros(n_terms + 1, dtype=torch.int64, device=tok.device)
+    indptr[1:] = torch.cumsum(df, 0)
+    # rank_bm25 sums the idf values in first-seen (dict insertion) order: global position of each term's first token
+    first = torch.full((n_terms,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=tok.device)
+    pos = torch.arange(tok.shape[0], dtype=torch.int64, device=tok.device)
+    totals = torch.tensor([int(tok.shape[0]), n_docs], dtype=torch.int64, device=tok.device)
+    if group is not None:
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        sizes = [torch.zeros(2, dtype=torch.int64, device=tok.device) for _ in range(world)]
+        dist.all_gather(sizes, totals, group=group)
+        pos = pos + sum(int(sz[0]) for sz in sizes[:rank])   # documents are sharded in rank order
+        totals = torch.stack(sizes).sum(0)
+    first.scatter_reduce_(0, tok, pos, reduce="amin", include_self=True)
+    if group is not None:
+        dist.all_reduce(df, group=group)
+        dist.all_reduce(first, op=dist.ReduceOp.MIN, group=group)
+    corpus_size = int(totals[1])
+    df_host = df.cpu().numpy()
+    order = np.argsort(first.cpu().numpy(), kind="stable")
+    nd = {int(t): int(df_host[t]) for t in order if df_host[t] > 0}
+    idf_map, average_idf = corpus_statistics(nd, corpus_size, epsilon)
+    idf = np.zeros(n_terms, dtype=np.float64)
+    for t, v in idf_map.items():
+        idf[t] = v
+    return {"indptr": indptr, "doc_ids": doc_ids.contiguous(), "tf": counts.to(torch.int32).contiguous(),
+            "doc_len": lens.to(torch.int32).contiguous(), "idf": idf, "avgdl": int(totals[0]) / corpus_size,
+            "average_idf": average_idf, "corpus_size": corpus_size}
+
+
 class BM25Okapi:
     """Drop-in for rank_bm25.BM25Okapi; `device` selects the GPU that holds the postings."""
 
@@ -109,6 +156,27 @@ class BM25Okapi:
         self.doc_len = None
         self._n_terms = n_terms
         self._create(n_terms, ptrs, 1 if on_dev else 0)
+        return self
+
+    @classmethod
+    def from_token_ids(cls, token_ids, doc_offsets, n_terms, k1=1.5, b=0.75, epsilon=0.25, device=0, weight_bits=32,
+                       vocab=None, group=None):
+        """Index build on the GPU from a tokenised corpus (next-row f4): `token_ids` int32[total] are the term ids
+        of all documents back to back, `doc_offsets` int64[n_docs + 1] their boundaries (numpy arrays or tensors).
+        The (term, doc) pairs are sorted and run-length counted on the device, which yields the term-major CSR
+        postings, df and doc_len; idf / avgdl follow rank_bm25 (src/ingestion.py:19-22 builds
+        BM25Okapi([chunk.split() ...]) with Python dictionaries).  With `group` (torch.distributed) the documents
+        are this rank's shard: df, the token count, the document count and the terms' first-seen order are
+        all-reduced so every shard scores exactly like the unsharded corpus."""
+        import torch
+
+        dev = torch.device("cuda", int(device))
+        stats = token_stream_statistics(token_ids, doc_offsets, n_terms, epsilon=epsilon, device=dev, group=group)
+        self = cls.from_postings(stats["indptr"], stats["doc_ids"], stats["tf"], stats["doc_len"],
+                                 torch.from_numpy(stats["idf"]).to(dev), stats["avgdl"], k1=k1, b=b, device=int(device),
+                                 weight_bits=weight_bits, vocab=vocab)
+        self.epsilon = epsilon
+        self.average_idf = stats["average_idf"]
         return self
 
     def _create(self, n_terms, ptrs, on_dev):

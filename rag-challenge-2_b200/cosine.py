@@ -101,3 +101,30 @@ def cosine_topk(rows, k, batch=4096):
             S[lo:hi, kk - 1:] = -3.4028235e38
             I[lo:hi, kk - 1:] = -1
     return S, I
+
+
+def heatmap_tiles(rows, pixels=512):
+    """Down-sampled heat map of the N x N cosine matrix (next-row f4): the reference plots the full matrix with
+    Plotly (generate_similarity_matrix.py:124-160), which at N = 200k would be a 160 GB array.  Pixel (a, b) is the
+    mean of S over rows of group a and columns of group b (groups = `pixels` contiguous row ranges).  The mean of
+    dot products is the dot product of the means, so the map is the Gram matrix of the pooled normalised rows —
+    O(N d + pixels^2 d) — corrected for the diagonal the reference forces to 1.  (The clip to [-1, 1] only touches
+    values that rounding pushed past +-1; it is applied to the pixel means.)  Returns a float32 CUDA tensor
+    [p, p] with p = min(pixels, N), and the group boundaries."""
+    import torch
+
+    n = int(rows.shape[0])
+    p = max(1, min(int(pixels), n))
+    xn = rows / (rows.norm(dim=1, keepdim=True) + 1e-8)
+    bounds = torch.div(torch.arange(p + 1, device=rows.device, dtype=torch.int64) * n, p, rounding_mode="floor")
+    sizes = (bounds[1:] - bounds[:-1]).to(torch.float64)
+    group = torch.bucketize(torch.arange(n, device=rows.device), bounds[1:], right=True)
+    pooled = torch.zeros((p, rows.shape[1]), dtype=torch.float64, device=rows.device)
+    pooled.index_add_(0, group, xn.to(torch.float64))
+    gram = pooled @ pooled.T                                   # sums over the tile: a plain p x p GEMM
+    # diagonal tiles: the reference overwrites S[i, i] (= |xn_i|^2) with 1
+    self_dot = torch.zeros(p, dtype=torch.float64, device=rows.device)
+    self_dot.index_add_(0, group, (xn.to(torch.float64) ** 2).sum(1))
+    gram[torch.arange(p), torch.arange(p)] += sizes - self_dot
+    tiles = gram / (sizes[:, None] * sizes[None, :])
+    return tiles.clamp_(-1.0, 1.0).to(torch.float32), bounds

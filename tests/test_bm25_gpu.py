@@ -290,3 +290,25 @@ def test_streaming_kernel_heavy_ties(b2r):
             top = oracle.bm25_topn_ref(want, k)
             assert np.array_equal(I[0], top), (q, k)
             assert np.array_equal(S[0], want[top])
+
+
+def test_index_build_from_token_ids_on_gpu(b2r):
+    """BM25Okapi.from_token_ids (sort + run-length count of (term, doc) pairs on the device) == the dictionary build
+    of BM25Okapi(corpus): same scores to the last bit, same top-k."""
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    docs = s.token_corpus_np(6000, vocab=1500, seed=31)
+    host = BM25Okapi(docs, weight_bits=64)
+    vocab = host._vocab
+    tok = np.array([vocab[w] for d in docs for w in d], np.int32)
+    offs = np.zeros(len(docs) + 1, np.int64)
+    np.cumsum([len(d) for d in docs], out=offs[1:])
+    dev = BM25Okapi.from_token_ids(tok, offs, len(vocab), weight_bits=64, vocab=vocab)
+    assert dev.corpus_size == host.corpus_size and dev.avgdl == host.avgdl and dev.average_idf == host.average_idf
+    queries = [as_tokens(q) for q in s.token_queries_np(6, vocab=1500, seed=32)]
+    for q in queries[:3]:
+        assert np.array_equal(dev.get_scores(q), host.get_scores(q))
+    S0, I0 = host.topk(queries, 30)
+    S1, I1 = dev.topk(queries, 30)
+    assert np.array_equal(I0, I1) and np.array_equal(S0, S1)

@@ -65,3 +65,23 @@ def test_topk_neighbours(b2r):
     assert I[50, 0] == 100 and I[100, 0] == 50
     assert not np.any(I == np.arange(4000)[:, None])
     oracle.assert_topk_equivalent(S, I, sim, 10, rtol=1e-5, atol=2e-6, what="cosine top-k")
+
+
+def test_heatmap_tiles_match_tile_means_of_the_matrix(b2r):
+    """Down-sampled heat map (Gram matrix of pooled normalised rows) == tile means of the reference's full matrix
+    (diagonal forced to 1, clipped), which only fits in memory at test size."""
+    import torch
+
+    from rag_challenge_2_b200 import cosine
+
+    rng = np.random.default_rng(71)
+    x = (rng.standard_normal((1003, 256)) * rng.uniform(0.5, 2.0, (1003, 1))).astype(np.float32)
+    x[500] = x[20] * 3.0                                      # a duplicate direction: an off-diagonal 1.0
+    S = oracle.cosine_matrix_ref(x).astype(np.float64)
+    for p in (1, 7, 64, 5000):
+        tiles, bounds = cosine.heatmap_tiles(torch.from_numpy(x).cuda(), p)
+        bounds = bounds.cpu().numpy()
+        pp = tiles.shape[0]
+        assert pp == min(p, 1003) and bounds[0] == 0 and bounds[-1] == 1003
+        want = np.array([[S[bounds[a]:bounds[a + 1], bounds[b]:bounds[b + 1]].mean() for b in range(pp)] for a in range(pp)])
+        assert np.allclose(tiles.cpu().numpy(), want, rtol=1e-5, atol=2e-6), p

@@ -109,3 +109,58 @@ def test_shard_bounds():
     assert shard_bounds(10, 4) == [0, 3, 6, 9, 10]
     assert shard_bounds(5, 8) == [0, 1, 2, 3, 4, 5, 5, 5, 5]
     assert shard_bounds(1000, 1, 128) == [0, 1000]
+
+
+def _token_corpus(n=1200, V=300, seed=5):
+    rng = np.random.default_rng(seed)
+    docs = [[int(t) for t in rng.integers(0, V, int(rng.integers(3, 25)))] for _ in range(n)]
+    docs[7] = [V - 1] * 4                     # a term that first appears early and only on rank 0
+    offs = np.zeros(n + 1, np.int64)
+    np.cumsum([len(d) for d in docs], out=offs[1:])
+    return docs, np.concatenate([np.asarray(d, np.int32) for d in docs]), offs
+
+
+def _stats_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rag_challenge_2_b200.bm25 import token_stream_statistics
+
+    docs, tok, offs = _token_corpus()
+    cut = [0, 700, len(docs)]
+    lo, hi = cut[rank], cut[rank + 1]
+    st = token_stream_statistics(tok[offs[lo]: offs[hi]], offs[lo: hi + 1] - offs[lo], 300, device=torch.device("cpu"),
+                                 group=dist.group.WORLD)
+    np.savez(os.path.join(out_dir, f"s{rank}.npz"), idf=st["idf"], avgdl=st["avgdl"], average_idf=st["average_idf"],
+             corpus_size=st["corpus_size"], indptr=st["indptr"].numpy(), doc_ids=st["doc_ids"].numpy(), tf=st["tf"].numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_token_stream_statistics_sharded_world2_gloo(tmp_path):
+    """BM25 index build from a token stream: a 2-way document shard (df, token / document counts and the terms'
+    first-seen order all-reduced) must produce the corpus-global idf / avgdl of the unsharded build, which in turn
+    equals rank_bm25's dictionary arithmetic (corpus_statistics) bit for bit."""
+    from rag_challenge_2_b200.bm25 import corpus_statistics, token_stream_statistics
+
+    mp.spawn(_stats_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    docs, tok, offs = _token_corpus()
+    whole = token_stream_statistics(tok, offs, 300, device=torch.device("cpu"))
+    nd = {}
+    for d in docs:
+        for w in dict.fromkeys(d):
+            nd[w] = nd.get(w, 0) + 1
+    idf, avg = corpus_statistics(nd, len(docs))
+    assert whole["average_idf"] == avg and whole["avgdl"] == sum(map(len, docs)) / len(docs)
+    assert all(whole["idf"][w] == v for w, v in idf.items())
+    s0, s1 = np.load(tmp_path / "s0.npz"), np.load(tmp_path / "s1.npz")
+    for s in (s0, s1):
+        assert np.array_equal(s["idf"], whole["idf"]) and float(s["avgdl"]) == whole["avgdl"]
+        assert float(s["average_idf"]) == whole["average_idf"] and int(s["corpus_size"]) == len(docs)
+    # the shards' postings are the whole corpus' postings split by document range
+    assert int(s0["indptr"][-1]) + int(s1["indptr"][-1]) == int(whole["indptr"][-1])
+    t = 17
+    a, b = int(whole["indptr"][t]), int(whole["indptr"][t + 1])
+    got = np.concatenate([s0["doc_ids"][s0["indptr"][t]: s0["indptr"][t + 1]],
+                          s1["doc_ids"][s1["indptr"][t]: s1["indptr"][t + 1]] + 700])
+    assert np.array_equal(got, whole["doc_ids"].numpy()[a:b])
