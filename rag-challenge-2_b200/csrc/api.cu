@@ -34,8 +34,9 @@ static std::map<std::string, int>& tunables() {
       {"flat.force_generic", 0},   // 1: use the non-TMA kernel even for templated widths
       {"flat.no_gemm", 0},         // 1: never use the tensor-core batch kernel
       {"flat.gemm_min_nq", 0},     // smallest batch that goes to the tensor-core kernel (default 5)
-      {"flat.gemm_max_n", 0},      // queries per tensor-core pass (default 128)
+      {"flat.gemm_max_n", 0},      // queries per tensor-core pass (default 256)
       {"gemm.stages", 0},          // depth of the tensor-core kernel's TMA ring
+      {"gemm.no_pair", 0},         // 1: at most 128 queries per pass (no CTA-pair kernel)
       {"gemm.no_wide", 0},         // 1: candidate pass keeps lists in shared memory (<= 64 queries / pass) instead of thresholds
       {"gemm.wide_sub", 0},        // 128-row sub-tiles per tile of the threshold candidate pass (1 or 2; default by width)
       {"gemm.tile256", 0},         // 1: candidate pass scores 256 rows per query slab (experimental)

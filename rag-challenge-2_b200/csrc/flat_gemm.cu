@@ -39,7 +39,7 @@
 namespace b2r {
 
 static const int kGemmThreads = 320;
-static const int kGemmMaxBatch = 128;  // queries per gemm_search_chunk call
+static const int kGemmMaxBatch = 256;  // queries per gemm_search_chunk call (CTA-pair candidate pass)
 
 // csrc/flat_gemm_wide.cu
 bool wide_path_supported(long long n, int d, int kp);
@@ -720,7 +720,7 @@ static int list_scan_max_batch(int ksel) {
 // largest batch gemm_search_chunk accepts
 int gemm_max_batch(int k) {
   (void)k;
-  return kGemmMaxBatch;
+  return tunable("gemm.no_pair") ? 128 : kGemmMaxBatch;
 }
 
 int gemm_max_row_norm2(const float* rows, long long n, int d, float* out_dev, cudaStream_t stream) {

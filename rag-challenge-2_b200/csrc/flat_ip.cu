@@ -399,7 +399,8 @@ struct Workspace {
   size_t bytes = 0;
 };
 
-static const size_t kPartialBytes = static_cast<size_t>(kMaxNQ) * kMaxGrid * B2R_MAX_K * sizeof(u64);
+// per-CTA partial lists of the scans; also the candidate lists of the tensor-core passes (148 CTAs x 256 queries x 128 keys)
+static const size_t kPartialBytes = static_cast<size_t>(2) * kMaxNQ * kMaxGrid * B2R_MAX_K * sizeof(u64);
 
 // csrc/flat_gemm.cu (tensor-core path; its scratch follows the partial lists in the workspace)
 bool gemm_path_supported(int d, int k);
@@ -652,7 +653,7 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
   int gemm_min = tunable("flat.gemm_min_nq");
   if (gemm_min <= 0) gemm_min = h->n >= 32768 ? 3 : 5;
   int gemm_max = tunable("flat.gemm_max_n");
-  if (gemm_max <= 0 || gemm_max > 128) gemm_max = 128;
+  if (gemm_max <= 0 || gemm_max > 256) gemm_max = 256;
   const bool use_gemm = nq >= gemm_min && gemm_path_supported(h->d, k) && !tunable("flat.force_generic") &&
                         !tunable("flat.no_gemm") && h->n >= 128;
   if (use_gemm) {

@@ -124,6 +124,91 @@ __device__ __forceinline__ u64 make_kmajor_sw128_desc(u32 smem_addr) {
 __host__ __device__ constexpr u32 make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<u32>(n >> 3) << 17) | (static_cast<u32>(kTileM >> 4) << 24);
 }
+
+// ---------------- CTA pair (cta_group::2): two SMs of a TPC execute one M = 256 MMA ----------------
+__device__ __forceinline__ u32 cluster_ctarank() {
+  u32 r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D tensor copy into THIS CTA's shared memory whose completion bytes are counted on the LEADER CTA's mbarrier
+// (bit 24 of a shared::cluster address selects the odd CTA of the pair: clearing it addresses CTA 0's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, u64* bar,
+                                                 u64 policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tc_alloc_pair(u32* slot, u32 ncols) {  // the same warp of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc_pair(u32 taddr, u32 ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem, 128 rows in each CTA] * B[smem, N/2 rows in each CTA]^T; leader CTA, one thread
+__device__ __forceinline__ void tc_mma_tf32_pair(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in both CTAs once the previously issued MMAs have completed
+__device__ __forceinline__ void tc_commit_pair(u64* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<unsigned short>(3))
+      : "memory");
+}
+// arrive on the mbarrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(u64* bar, u32 rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// wait with cluster-scope acquire (the arrivals come from the peer CTA) and a watchdog
+__device__ __forceinline__ void mbar_wait_cluster_tag(u64* bar, u32 parity, int tag) {
+  const u32 addr = smem_u32(bar);
+  for (u32 spins = 0;; ++spins) {
+    u32 done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spins == (1u << 26)) {
+      printf("b2r flat_gemm pair: barrier wait stuck: tag %d block %d thread %d parity %u\n", tag, blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M (128 or 256), N
+__host__ __device__ constexpr u32 make_idesc_tf32_mn(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<u32>(n >> 3) << 17) | (static_cast<u32>(m >> 4) << 24);
+}
+
 #endif  // __CUDACC__
 
 // host: 2-D tensor map over a row-major float32 matrix [outer, inner], {box_inner x box_outer} boxes, SWIZZLE_128B

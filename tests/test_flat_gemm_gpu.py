@@ -199,3 +199,42 @@ def test_wide_other_widths(b2r, d):
     index = b2r.FlatIPIndex(d)
     index.add(xb)
     check(index, xb, queries_for(xb, 70, 69), 10)
+
+
+@pytest.mark.parametrize("nq,sub", [(129, 0), (256, 0), (257, 0), (600, 0), (200, 2)])
+def test_cta_pair_pass(b2r, nq, sub):
+    """More than 128 queries: the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 queries per pass), in both of its
+    TMEM layouts (one sub-tile double-buffered / two sub-tiles single-buffered); same parity bar, and the same answers as
+    with the pair kernel disabled."""
+    from rag_challenge_2_b200 import _lib
+
+    xb = unit_rows(90001, 1024, 81)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    xq = queries_for(xb, nq, 82 + nq)
+    _lib.tunable_set("gemm.wide_sub", sub)
+    try:
+        D1, I1 = check(index, xb, xq, 30)
+    finally:
+        _lib.tunable_set("gemm.wide_sub", 0)
+    _lib.tunable_set("gemm.no_pair", 1)
+    try:
+        D2, I2 = index.search(xq, 30)
+    finally:
+        _lib.tunable_set("gemm.no_pair", 0)
+    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+
+
+def test_cta_pair_other_widths_and_overflow(b2r):
+    for d in (64, 2048):
+        xb = unit_rows(30000, d, 83)
+        index = b2r.FlatIPIndex(d)
+        index.add(xb)
+        check(index, xb, queries_for(xb, 150, 84), 10)
+    # adversarial row order: thresholds sampled from the first tiles are too low, lists overflow, redo pass answers
+    xb = unit_rows(40000, 1024, 85)
+    q = unit_rows(3, 1024, 86)
+    xb = np.ascontiguousarray(xb[np.argsort(xb @ q[0])])
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    check(index, xb, np.concatenate([q, queries_for(xb, 140, 87)]), 30)
