@@ -370,13 +370,13 @@ def run_b200(args):
     h2d, d2h = index.last_h2d_bytes, index.last_d2h_bytes
     sampler.stop()
 
-    # ---- explanatory extras (not the metric): dense-only single query, and a 64-query dense batch on the
-    # tensor-core path (K2); local shard only, CUDA events, a few iterations each
+    # ---- explanatory extras (not the metric): dense-only single query, and dense batches on the tensor-core
+    # path (K2; 256 queries: the CTA-pair kernel); local shard only, CUDA events, a few iterations each
     extras = {}
     index.searcher.local_dense = inner_dense
     index.searcher.local_bm25 = inner_bm25
     for name, nqx, iters in (("dense_single_query", 1, 20), ("dense_batch64_tensor_core", 64, 5),
-                             ("dense_batch128_tensor_core", 128, 5)):
+                             ("dense_batch128_tensor_core", 128, 5), ("dense_batch256_tensor_core_cta_pairs", 256, 5)):
         qx = q_pool[:nqx].contiguous() if pool >= nqx else q_pool.repeat((nqx + pool - 1) // pool, 1)[:nqx].contiguous()
         for _ in range(2):
             flat.search_dev(qx, args.k)
