@@ -836,8 +836,16 @@ __global__ void cosine_double_hist_kernel(u64* hist, int n_bins) {
   if (i < n_bins) hist[i] *= 2ull;
 }
 
+// csrc/cosine_pair.cu
+bool cosine_pair_supported(long long n, int d, int n_bins, int num_sms);
+int cosine_stats_run_pair(const float* rows_dev, long long n, int d, long long col_begin, long long col_end,
+                          double* stats_dev, u64* hist_dev, int n_bins, int num_sms, cudaStream_t stream);
+
 int cosine_stats_run(const float* rows_dev, long long n, int d, long long col_begin, long long col_end,
                      double* stats_dev, u64* hist_dev, int n_bins, int num_sms, cudaStream_t stream) {
+  if (cosine_pair_supported(n, d, n_bins, num_sms)) {
+    return cosine_stats_run_pair(rows_dev, n, d, col_begin, col_end, stats_dev, hist_dev, n_bins, num_sms, stream);
+  }
   constexpr int N = 64;
   float* xn = nullptr;
   unsigned char* scratch = nullptr;

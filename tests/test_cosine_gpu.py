@@ -85,3 +85,35 @@ def test_heatmap_tiles_match_tile_means_of_the_matrix(b2r):
         assert pp == min(p, 1003) and bounds[0] == 0 and bounds[-1] == 1003
         want = np.array([[S[bounds[a]:bounds[a + 1], bounds[b]:bounds[b + 1]].mean() for b in range(pp)] for a in range(pp)])
         assert np.allclose(tiles.cpu().numpy(), want, rtol=1e-5, atol=2e-6), p
+
+
+@pytest.mark.parametrize("n,d", [(4096, 64), (4500, 1024), (6001, 96)])
+def test_stats_cta_pair_kernel(b2r, n, d):
+    """n >= 4096: the CTA-pair 3xTF32 kernel (csrc/cosine_pair.cu); same bar, and the same numbers as the single-CTA
+    kernel up to fp32 accumulation order."""
+    import torch
+
+    from rag_challenge_2_b200 import _lib, cosine
+
+    rng = np.random.default_rng(n + d)
+    x = rng.standard_normal((n, d)).astype(np.float32) + 0.5 * rng.standard_normal((1, d)).astype(np.float32)
+    x *= rng.uniform(0.5, 2.0, (n, 1)).astype(np.float32)
+    x[7] = 3.0 * x[3]
+    x[n - 1] = -2.0 * x[n - 5]
+    rows = torch.from_numpy(x).cuda()
+    got = cosine.cosine_stats(rows)
+    compare(x, got)
+    _lib.tunable_set("cosine.no_pair", 1)
+    try:
+        old = cosine.cosine_stats(rows)
+    finally:
+        _lib.tunable_set("cosine.no_pair", 0)
+    assert got["count"] == old["count"] and got["max_similarity"] == old["max_similarity"]
+    assert abs(got["avg_similarity"] - old["avg_similarity"]) <= 1e-6 * abs(old["avg_similarity"]) + 1e-9
+    # column shards at boundaries that are not multiples of the 128-column tile
+    parts = [cosine.cosine_stats(rows, lo, hi, finalize=False) for lo, hi in ((0, 1000), (1000, 4097 if n > 4097 else 3000), (4097 if n > 4097 else 3000, n))]
+    stats = sum(p[0].cpu().numpy()[[0, 1, 4]] for p in parts)
+    hist = sum(p[1].cpu().numpy() for p in parts)
+    merged = cosine.finalize_stats(np.array([stats[0], stats[1], min(float(p[0][2]) for p in parts),
+                                             max(float(p[0][3]) for p in parts), stats[2], 0.0]), hist)
+    compare(x, merged)

@@ -14,14 +14,17 @@ d = 1024
 g = torch.Generator(device="cuda").manual_seed(777)
 x = torch.randn((n, d), generator=g, device="cuda") * (0.5 + 1.5 * torch.rand((n, 1), generator=g, device="cuda"))
 x = x.contiguous()
-cosine.cosine_stats(x[:4096].contiguous())
+cosine.cosine_stats(x[:8192].contiguous())
 torch.cuda.synchronize()
-t0 = time.time()
-st = cosine.cosine_stats(x)
-torch.cuda.synchronize()
-dt = time.time() - t0
+times = []
+for _ in range(2):          # the first full-size call pays the allocator (2 x 0.8 GB of split operands)
+    t0 = time.time()
+    st = cosine.cosine_stats(x)
+    torch.cuda.synchronize()
+    times.append(time.time() - t0)
+dt = min(times)
 flops = 2.0 * n * n * d / 2  # symmetry: upper triangle only
-print(json.dumps({"n": n, "d": d, "seconds": round(dt, 3), "tflops_useful_fp32_equiv": round(flops / dt / 1e12, 1),
+print(json.dumps({"n": n, "d": d, "seconds": round(dt, 3), "seconds_each_call": [round(t, 3) for t in times], "tflops_useful_fp32_equiv": round(flops / dt / 1e12, 1),
                   "tensor_tflops_issued_3xtf32": round(3 * flops / dt / 1e12, 1), "stats": st}))
 t0 = time.time()
 S, I = cosine.cosine_topk(x[: min(n, 50_000)].contiguous(), 30)
