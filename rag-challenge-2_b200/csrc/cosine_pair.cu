@@ -20,7 +20,7 @@
 
 namespace b2r {
 
-static const int kCosThreads = 192;
+static const int kCosThreads = 320;   // producer, MMA, 8 epilogue warps (two per TMEM lane quadrant)
 static const int kCosN = 128;        // columns per tile
 static const int kCosSuper = 2048;   // rows / columns of an L2 super-tile
 static const int kCosStages = 3;
@@ -92,7 +92,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
       mbar_init(&empty[s], 1);
     }
     mbar_init(tm_full, 1);
-    mbar_init(tm_empty, 8);
+    mbar_init(tm_empty, 16);  // eight epilogue warps of each CTA
     mbar_fence_init();
   }
   for (int i = tid; i < a.n_bins; i += blockDim.x) hist_s[i] = 0;
@@ -168,21 +168,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
     }
   } else {
     // ======================= epilogue warps (both CTAs): statistics of the tile =======================
+    // Warps 2-9: warp w reads TMEM lane quadrant w % 4 (a hardware rule) and one half of the 128 columns, so two
+    // warps share a quadrant.  Per 16-column chunk the sum and the sum of squares are formed in fp32 and added to the
+    // float64 totals once; interior tiles (every row below every column, all inside the matrix and the column range)
+    // skip the per-element masks.
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;  // 0: columns 0-63, 1: columns 64-127
     u32 ph_t = 0;
     double st_sum = 0.0, st_sq = 0.0;
     unsigned long long st_cnt = 0;
     float st_min = 3.4028235e38f, st_max = -3.4028235e38f;
     const float scale = 0.5f * static_cast<float>(a.n_bins);
+    const int last_bin = a.n_bins - 1;
     for (long long t = pair; t < a.n_tiles; t += n_pairs) {
       const int2 rc = a.tiles[t];
-      const long long row = static_cast<long long>(rc.x) * (2 * kTileM) + static_cast<long long>(rank) * kTileM + quad * 32 + lane;
+      const long long row_base = static_cast<long long>(rc.x) * (2 * kTileM);
+      const long long row = row_base + static_cast<long long>(rank) * kTileM + quad * 32 + lane;
       const long long col_base = static_cast<long long>(rc.y) * N;
+      const bool interior = row_base + 2 * kTileM - 1 < col_base && col_base + N <= a.n && col_base >= a.col_lo &&
+                            col_base + N <= a.col_hi;
       mbar_wait_cluster_tag(tm_full, ph_t, 700);
       tc_fence_after();
-      const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16);
+      const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(half * (N / 2));
 #pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 16) {
+      for (int c0 = 0; c0 < N / 2; c0 += 16) {
         float m0[16], m1[16], s0[16], s1[16];
         tc_ld16(taddr + c0, m0);
         tc_ld16(taddr + 2 * N + c0, s0);
@@ -191,31 +200,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
           tc_ld16(taddr + 3 * N + c0, s1);
         }
         tc_wait_ld();
-        if (c0 + 16 >= N) {  // the whole tile has been read
+        if (c0 + 16 >= N / 2) {  // this warp has read its part of the tile
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tm_empty, 0);
         }
+        float csum = 0.f, csq = 0.f;
+        int ccnt = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const long long col = col_base + c0 + i;
-          if (row < a.n && col < a.n && row < col && col >= a.col_lo && col < a.col_hi) {
+          const long long col = col_base + half * (N / 2) + c0 + i;
+          if (interior || (row < a.n && col < a.n && row < col && col >= a.col_lo && col < a.col_hi)) {
             const float sc = (n_slabs > 1) ? (m0[i] + m1[i]) + (s0[i] + s1[i]) : m0[i] + s0[i];
             const float v = fminf(1.0f, fmaxf(-1.0f, sc));
-            st_sum += static_cast<double>(v);
-            st_sq += static_cast<double>(v) * static_cast<double>(v);
+            csum += v;
+            csq = fmaf(v, v, csq);
             st_min = fminf(st_min, v);
             st_max = fmaxf(st_max, v);
-            ++st_cnt;
-            int bin = static_cast<int>((v + 1.0f) * scale);
-            bin = bin >= a.n_bins ? a.n_bins - 1 : bin;
+            ++ccnt;
+            const int bin = min(static_cast<int>((v + 1.0f) * scale), last_bin);
             atomicAdd(&hist_s[bin], 1u);
           }
         }
+        st_sum += static_cast<double>(csum);
+        st_sq += static_cast<double>(csq);
+        st_cnt += static_cast<unsigned long long>(ccnt);
       }
       ph_t ^= 1u;
     }
-    named_bar_sync(1, 128);
+    named_bar_sync(1, 256);
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
       st_sum += __shfl_xor_sync(0xffffffffu, st_sum, m);
@@ -231,7 +244,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
       atomicMin(a.minmax + 0, float_to_ordered(st_min));
       atomicMax(a.minmax + 1, float_to_ordered(st_max));
     }
-    for (int b = tid - 64; b < a.n_bins; b += 128) {
+    for (int b = tid - 64; b < a.n_bins; b += 256) {
       const u32 h = hist_s[b];
       if (h) atomicAdd(a.hist + b, static_cast<u64>(h));
     }
