@@ -2,7 +2,8 @@
 //
 // Replaces index.search(x[nq, d], k) for query batches (the multi-query fan-out of
 // src/retrieval.py:1475-1504 and 127-question batches): every row tile is read from HBM once and
-// scored against up to N = 64 queries.
+// scored against up to N = 64 queries by the kernels of this file (list-keeping select; the 3xTF32 redo / k > 64 path
+// and the small-index path) and against up to 256 by the threshold candidate passes of flat_gemm_wide.cu.
 //
 //   S[128 rows, N queries] = A[128, d] * B[N, d]^T          per row tile, accumulated over d in TMEM
 //

@@ -1,4 +1,5 @@
-// flat_gemm_wide.cu — K2 candidate pass, threshold form: up to 128 queries per pass over the rows.
+// flat_gemm_wide.cu — K2 candidate pass, threshold form: up to 128 queries per pass over the rows on one CTA per SM,
+// up to 256 on CTA pairs (flat_gemm_pair_kernel, below).
 //
 // Same job as the TERMS = 1 pass of flat_gemm.cu (approximate tf32 scores select k' candidates per
 // query, exact fp32 rescoring and the completeness proof follow), but the select epilogue no longer
@@ -541,8 +542,6 @@ bool wide_path_supported(long long n, int d, int kp) {
   return d % kSlabK == 0 && d >= kSlabK && kp <= kListCap && n >= 16384 && !tunable("gemm.no_wide");
 }
 
-// Candidate pass for nq <= 128 queries: fills Dp / Ip [nq][kp] (approximate scores, local ids) and ovf[nq].
-// B: scratch for the query operand (128 * d floats); glists: partial-list scratch of glists_bytes.
 template <int SUB, int BUFS>
 static int pair_launch(const CUtensorMap& ma, const CUtensorMap& mb, const WideArgs& a, int grid, size_t smem,
                        cudaStream_t stream) {

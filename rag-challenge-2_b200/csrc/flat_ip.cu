@@ -646,7 +646,7 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
   int rc = get_workspace(h, stream, &ws);
   if (rc) return rc;
   int done = 0;
-  // batches go to the tensor cores (K2): one pass over the rows per <= 128 queries
+  // batches go to the tensor cores (K2): one pass over the rows per <= 256 queries
   // smallest batch that goes to the tensor cores: 5 on report-sized indexes, 3 from 32k rows on, where one
   // tensor-core pass beats a 4-query SIMT pass (profiles/r01_small_index_sweep.json: 200k rows, 4 queries SIMT
   // 365 us vs 5 queries on the tensor path 241 us; equal at 10k rows)
