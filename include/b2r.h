@@ -78,6 +78,11 @@ int b2r_flat_search_dev(b2r_flat* h, const float* q_dev, int nq, int k, float* D
  * generate_similarity_matrix.py:61.  out is host float32[m,d]; any id outside [0,ntotal)
  * fails with B2R_ERR_INVALID (faiss raises; the reference catches it, :574-576). */
 int b2r_flat_reconstruct(b2r_flat* h, const int64_t* ids, int m, float* out);
+/* Optional: keep a bfloat16 copy of the rows (+50 % memory) for the tensor-core candidate pass of batches of more
+ * than 128 queries — half the bytes per row and twice the MMA rate.  Results stay exact: the candidates (128 per query)
+ * are rescored in fp32 and the answer is only accepted when the bf16 error bound proves the candidate set complete;
+ * otherwise the query is redone with 3xTF32.  The copy is (re)built lazily by the next batched search. */
+int b2r_flat_set_candidate_bf16(b2r_flat* h, int enable);
 int b2r_flat_destroy(b2r_flat* h);
 /* Number of kernel launches the last search on this thread enqueued (bench accounting). */
 int b2r_last_launch_count(void);

@@ -44,9 +44,10 @@ static const int kGemmMaxBatch = 256;  // queries per gemm_search_chunk call (CT
 
 // csrc/flat_gemm_wide.cu
 bool wide_path_supported(long long n, int d, int kp);
-int wide_candidates(const float* rows, long long n, int d, const float* q_dev, int nq, int kp, float* B, float* tauf,
-                    u32* premax, u32* gcnt, u32* ovf, u64* glists, size_t glists_bytes, float* Dp, long long* Ip,
-                    int num_sms, cudaStream_t stream, int* launches);
+int wide_candidates(const float* rows, const void* rows_bf16, long long n, int d, const float* q_dev, int nq, int kp,
+                    float* B, float* tauf, u32* premax, u32* gcnt, u32* ovf, u64* glists, size_t glists_bytes, float* Dp,
+                    long long* Ip, int num_sms, cudaStream_t stream, int* launches);
+bool wide_uses_bf16(const void* rows_bf16, int d, int nq);
 static const int kLoStages = 4;
 
 struct GemmArgs {
@@ -515,7 +516,8 @@ __global__ void __launch_bounds__(512) gemm_rescore_kernel(const float* __restri
                                                            const long long* __restrict__ Ip, int kp, int k,
                                                            const float* __restrict__ max_norm2, float* __restrict__ D,
                                                            long long* __restrict__ I, long long id_offset,
-                                                           u32* __restrict__ redo, const u32* __restrict__ ovf) {
+                                                           u32* __restrict__ redo, const u32* __restrict__ ovf,
+                                                           float operand_err) {
   __shared__ u64 keys[256];
   __shared__ float s_qn2;
   const int qi = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -579,8 +581,9 @@ __global__ void __launch_bounds__(512) gemm_rescore_kernel(const float* __restri
     u32 need_redo = 0;
     const bool list_full = cand[kp - 1] >= 0;  // fewer than k' rows in the shard: every row was rescored
     if (list_full) {
-      // operand truncation 2^-9 (+6 %) plus the truncating fp32 accumulation of a length-d chain, d * 2^-24
-      const float rel = 0.001953125f * 1.0625f + static_cast<float>(d) * 5.9604645e-8f;
+      // operand error (tf32 truncation 2^-9, bf16 rounding 2^-8; +6 %) plus the truncating fp32 accumulation of a
+      // length-d chain, d * 2^-24
+      const float rel = operand_err * 1.0625f + static_cast<float>(d) * 5.9604645e-8f;
       const float bound = rel * sqrtf(s_qn2) * sqrtf(*max_norm2) + 1e-6f;
       const u64 kth = keys[k - 1];
       const float exact_kth = kth ? key_score(kth) : -3.4028235e38f;
@@ -619,6 +622,21 @@ int make_map_2d(CUtensorMap* map, const float* base, unsigned long long inner, u
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B2R_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return B2R_OK;
+}
+
+int make_map_2d_bf16(CUtensorMap* map, const void* base, unsigned long long inner, unsigned long long outer,
+                     unsigned box_inner, unsigned box_outer) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode_fn();
+  if (!enc) return fail(B2R_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B2R_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed with code " + std::to_string(r));
   return B2R_OK;
 }
 
@@ -744,9 +762,9 @@ size_t gemm_scratch_bytes() { return kScrEnd + 1024; }
 
 // Scores `nq` (<= kGemmMaxBatch) queries against the whole shard.  scratch: gemm_scratch_bytes() of device
 // memory; partial: list scratch of partial_bytes (>= 64 * grid * 128 keys).
-int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
-                      long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial, size_t partial_bytes,
-                      const float* max_norm2_dev, int num_sms, cudaStream_t stream, int* launches) {
+int gemm_search_chunk(const float* rows, const void* rows_bf16, long long n, int d, const float* q_dev, int nq, int k,
+                      float* D_dev, long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial,
+                      size_t partial_bytes, const float* max_norm2_dev, int num_sms, cudaStream_t stream, int* launches) {
   float* bsplit = reinterpret_cast<float*>(scratch);
   float* Dp = reinterpret_cast<float*>(scratch + kScrDp);
   long long* Ip = reinterpret_cast<long long*>(scratch + kScrIp);
@@ -768,11 +786,16 @@ int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev,
     }
     return B2R_OK;
   }
-  const int kp = std::min(128, std::max(64, 2 * k));
+  int kp = std::min(128, std::max(64, 2 * k));
   const bool wide = wide_path_supported(n, d, kp);
+  // bf16 candidate pass (opt-in copy of the rows, batches of more than 128 queries): twice the operand error, so twice
+  // the candidates for the completeness proof
+  const bool bf16 = wide && wide_uses_bf16(rows_bf16, d, nq);
+  if (bf16) kp = 128;
+  const float operand_err = bf16 ? 0.00390625f : 0.001953125f;
   if (wide) {
-    rc = wide_candidates(rows, n, d, q_dev, nq, kp, bsplit, tauf, premax, gcnt, ovf, partial, partial_bytes, Dp, Ip,
-                         num_sms, stream, launches);
+    rc = wide_candidates(rows, bf16 ? rows_bf16 : nullptr, n, d, q_dev, nq, kp, bsplit, tauf, premax, gcnt, ovf, partial,
+                         partial_bytes, Dp, Ip, num_sms, stream, launches);
     if (rc) return rc;
   } else {
     const int step = list_scan_max_batch(kp);
@@ -785,7 +808,7 @@ int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev,
     }
   }
   gemm_rescore_kernel<<<nq, 512, 0, stream>>>(rows, d, q_dev, Dp, Ip, kp, k, max_norm2_dev, D_dev, I_dev, id_offset, redo,
-                                              wide ? ovf : nullptr);
+                                              wide ? ovf : nullptr, operand_err);
   B2R_CUDA(cudaGetLastError());
   *launches += 1;
   if (!tunable("gemm.no_verify")) {

@@ -28,6 +28,8 @@
 // two tiles in flight: 2 * SUB * N TMEM columns (512 at N = 128, SUB = 2).
 //
 // L2 traffic per byte of A: N / (SUB * 128) bytes of B — 0.5 at N = 128 with 256-row tiles.
+#include <cuda_bf16.h>
+
 #include <algorithm>
 
 #include "tc_ptx.cuh"
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(kWideThreads, 1)
 // commits are multicast to both CTAs' `empty` / `tm_full` barriers, and the epilogue warps of both CTAs arrive
 // on the leader's `tm_empty`.  TMEM: SUB x 256 columns per tile x BUFS tiles = 512 columns.
 // ---------------------------------------------------------------------------------------------
-template <int SUB, int BUFS>
+template <int SUB, int BUFS, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWideThreads, 1)
     flat_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                           const WideArgs a) {
@@ -273,8 +275,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWideThreads, 1)
   constexpr u32 kTileCols = SUB * N;
   constexpr u32 kTmemCols = BUFS * kTileCols;
   static_assert(kTmemCols == 512, "the pair kernel uses all of TMEM");
+  // a K-slab is one 128-byte swizzle row: 32 floats (tf32 MMAs on the fp32 rows) or 64 bf16 (the optional bf16 copy)
+  constexpr int kSlabElems = BF16 ? 64 : kSlabK;
   const int R = a.stages;
-  const int n_slabs = a.d / kSlabK;
+  const int n_slabs = a.d / kSlabElems;
   const bool pre = a.premax != nullptr;
   const u32 rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -327,9 +331,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWideThreads, 1)
           if (leader) mbar_arrive_expect_tx(&full[s], 2u * kStage);  // bytes of both CTAs land on this barrier
 #pragma unroll
           for (int sub = 0; sub < SUB; ++sub) {
-            tma_load_2d_pair(st + sub * kSubBytes, &map_a, sl * kSlabK, row0 + sub * kTileM, &full[s], pol_a);
+            tma_load_2d_pair(st + sub * kSubBytes, &map_a, sl * kSlabElems, row0 + sub * kTileM, &full[s], pol_a);
           }
-          tma_load_2d_pair(st + kABytes, &map_b, sl * kSlabK, static_cast<int>(rank) * NH, &full[s], pol_b);
+          tma_load_2d_pair(st + kABytes, &map_b, sl * kSlabElems, static_cast<int>(rank) * NH, &full[s], pol_b);
           if (++s == R) {
             s = 0;
             ph ^= 1u;
@@ -340,7 +344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWideThreads, 1)
   } else if (warp == 1) {
     // ======================= MMA issuer (leader CTA only) =======================
     if (lane == 0 && leader) {
-      constexpr u32 idesc = make_idesc_tf32_mn(2 * kTileM, N);
+      constexpr u32 idesc = BF16 ? make_idesc_bf16_mn(2 * kTileM, N) : make_idesc_tf32_mn(2 * kTileM, N);
       int s = 0, buf = 0, j = 0;
       u32 ph_s = 0, ph_buf[2] = {0, 0};
       for (long long t = pair; t < n_tiles && j < a.tile_limit; t += n_pairs, ++j) {
@@ -359,7 +363,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWideThreads, 1)
 #pragma unroll
             for (int kk = 0; kk < kSlabK / 8; ++kk) {
               const u64 adv = static_cast<u64>(kk * 8 * 4 >> 4);
-              tc_mma_tf32_pair(d_acc, d_a + adv, d_b + adv, idesc, (sl == 0 && kk == 0) ? 0u : 1u);
+              if (BF16) tc_mma_bf16_pair(d_acc, d_a + adv, d_b + adv, idesc, (sl == 0 && kk == 0) ? 0u : 1u);
+              else tc_mma_tf32_pair(d_acc, d_a + adv, d_b + adv, idesc, (sl == 0 && kk == 0) ? 0u : 1u);
             }
           }
           tc_commit_pair(&empty[s]);
@@ -463,6 +468,36 @@ __global__ void wide_prep_kernel(const float* __restrict__ q, int nq, int N, int
   for (long long i = i0; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) B[i] = i < live ? q[i] : 0.f;
 }
 
+// bf16 variant of the query operand (round to nearest even, as the rows' copy)
+__global__ void wide_prep_bf16_kernel(const float* __restrict__ q, int nq, int N, int d, unsigned short* __restrict__ B,
+                                      u32* __restrict__ ovf) {
+  const long long total = static_cast<long long>(N) * d;
+  const long long live = static_cast<long long>(nq) * d;
+  const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i0 < N) ovf[i0] = 0;
+  for (long long i = i0; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    B[i] = i < live ? __bfloat16_as_ushort(__float2bfloat16_rn(q[i])) : static_cast<unsigned short>(0);
+  }
+}
+
+// rows -> bf16 copy (the optional candidate-pass operand), n * d elements
+__global__ void rows_to_bf16_kernel(const float* __restrict__ x, long long total, unsigned short* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    out[i] = __bfloat16_as_ushort(__float2bfloat16_rn(x[i]));
+  }
+}
+
+int rows_to_bf16(const float* rows, long long n, int d, void* out, int num_sms, cudaStream_t stream) {
+  rows_to_bf16_kernel<<<num_sms * 16, 256, 0, stream>>>(rows, n * d, static_cast<unsigned short*>(out));
+  B2R_CUDA(cudaGetLastError());
+  return B2R_OK;
+}
+
+bool wide_uses_bf16(const void* rows_bf16, int d, int nq) {
+  return rows_bf16 != nullptr && nq > 128 && d % 64 == 0 && !tunable("gemm.no_pair") && !tunable("gemm.no_bf16");
+}
+
 // one CTA per query: tau = k'-th largest group maximum, 4 ulps lower (insurance; costs nothing)
 __global__ void __launch_bounds__(1024) wide_tau_kernel(const u32* __restrict__ premax, int pm_stride, int m, int kp,
                                                         float* __restrict__ tauf) {
@@ -542,10 +577,10 @@ bool wide_path_supported(long long n, int d, int kp) {
   return d % kSlabK == 0 && d >= kSlabK && kp <= kListCap && n >= 16384 && !tunable("gemm.no_wide");
 }
 
-template <int SUB, int BUFS>
+template <int SUB, int BUFS, bool BF16>
 static int pair_launch(const CUtensorMap& ma, const CUtensorMap& mb, const WideArgs& a, int grid, size_t smem,
                        cudaStream_t stream) {
-  auto kern = flat_gemm_pair_kernel<SUB, BUFS>;
+  auto kern = flat_gemm_pair_kernel<SUB, BUFS, BF16>;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<grid, kWideThreads, smem, stream>>>(ma, mb, a);  // cluster shape (2, 1, 1) is part of the kernel
   B2R_CUDA(cudaGetLastError());
@@ -554,10 +589,12 @@ static int pair_launch(const CUtensorMap& ma, const CUtensorMap& mb, const WideA
 
 // Candidate pass for nq <= 256 queries: fills Dp / Ip [nq][kp] (approximate scores, local ids) and ovf[nq].
 // B: scratch for the query operand (256 * d floats); glists: partial-list scratch of glists_bytes.
-int wide_candidates(const float* rows, long long n, int d, const float* q_dev, int nq, int kp, float* B, float* tauf,
-                    u32* premax, u32* gcnt, u32* ovf, u64* glists, size_t glists_bytes, float* Dp, long long* Ip,
-                    int num_sms, cudaStream_t stream, int* launches) {
+// rows_bf16 != NULL (pair path only): the candidate pass reads the bf16 copy of the rows instead.
+int wide_candidates(const float* rows, const void* rows_bf16, long long n, int d, const float* q_dev, int nq, int kp,
+                    float* B, float* tauf, u32* premax, u32* gcnt, u32* ovf, u64* glists, size_t glists_bytes, float* Dp,
+                    long long* Ip, int num_sms, cudaStream_t stream, int* launches) {
   const bool pair = nq > 128;
+  const bool bf16 = pair && rows_bf16 != nullptr;
   const int N = pair ? 256 : (nq <= 16 ? 16 : (nq <= 32 ? 32 : (nq <= 64 ? 64 : 128)));
   // 128-row sub-tiles per CTA and tile: 2 for the 64 / 128-query kernels (halves the L2 re-reads of the query operand);
   // the pair kernel runs faster with one sub-tile and two tiles in flight (3.64 vs 4.31 ms per 256 queries at 4M rows)
@@ -581,13 +618,21 @@ int wide_candidates(const float* rows, long long n, int d, const float* q_dev, i
   const int m = grid * static_cast<int>(pre_tiles) * sub * 4;
   if (m > kPremaxMax) return fail(B2R_ERR_UNSUPPORTED, "wide_candidates: too many CTAs for the threshold sample");
 
-  wide_prep_kernel<<<128, 256, 0, stream>>>(q_dev, nq, N, d, B, ovf);
+  if (bf16) wide_prep_bf16_kernel<<<128, 256, 0, stream>>>(q_dev, nq, N, d, reinterpret_cast<unsigned short*>(B), ovf);
+  else wide_prep_kernel<<<128, 256, 0, stream>>>(q_dev, nq, N, d, B, ovf);
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemsetAsync(premax, 0, static_cast<size_t>(nq) * m * sizeof(u32), stream));
   CUtensorMap ma, mb;
-  int rc = make_map_2d(&ma, rows, static_cast<unsigned long long>(d), static_cast<unsigned long long>(n), kSlabK, kTileM);
-  if (rc) return rc;
-  rc = make_map_2d(&mb, B, static_cast<unsigned long long>(d), static_cast<unsigned long long>(N), kSlabK, pair ? 128 : N);
+  int rc;
+  if (bf16) {
+    rc = make_map_2d_bf16(&ma, rows_bf16, static_cast<unsigned long long>(d), static_cast<unsigned long long>(n), 64, kTileM);
+    if (rc) return rc;
+    rc = make_map_2d_bf16(&mb, B, static_cast<unsigned long long>(d), static_cast<unsigned long long>(N), 64, 128);
+  } else {
+    rc = make_map_2d(&ma, rows, static_cast<unsigned long long>(d), static_cast<unsigned long long>(n), kSlabK, kTileM);
+    if (rc) return rc;
+    rc = make_map_2d(&mb, B, static_cast<unsigned long long>(d), static_cast<unsigned long long>(N), kSlabK, pair ? 128 : N);
+  }
   if (rc) return rc;
   const size_t stage = static_cast<size_t>(sub * kTileM) * kSlabK * 4 + static_cast<size_t>(pair ? 128 : N) * kSlabK * 4;
   const size_t fixed = 32 * 8 + static_cast<size_t>(N) * 8 + 64 + 1024;
@@ -612,7 +657,12 @@ int wide_candidates(const float* rows, long long n, int d, const float* q_dev, i
   const bool single_buf = sub == 2;  // pair kernel: 2 sub-tiles x 256 columns fill TMEM, one tile in flight
   auto scan = [&](const WideArgs& wa) {
     if (!pair) return wide_dispatch(N, sub, ma, mb, wa, grid, smem, stream);
-    return single_buf ? pair_launch<2, 1>(ma, mb, wa, grid, smem, stream) : pair_launch<1, 2>(ma, mb, wa, grid, smem, stream);
+    if (bf16) {
+      return single_buf ? pair_launch<2, 1, true>(ma, mb, wa, grid, smem, stream)
+                        : pair_launch<1, 2, true>(ma, mb, wa, grid, smem, stream);
+    }
+    return single_buf ? pair_launch<2, 1, false>(ma, mb, wa, grid, smem, stream)
+                      : pair_launch<1, 2, false>(ma, mb, wa, grid, smem, stream);
   };
   rc = scan(a);
   if (rc) return rc;

@@ -407,9 +407,11 @@ bool gemm_path_supported(int d, int k);
 int gemm_max_batch(int k);
 size_t gemm_scratch_bytes();
 int gemm_max_row_norm2(const float* rows, long long n, int d, float* out_dev, cudaStream_t stream);
-int gemm_search_chunk(const float* rows, long long n, int d, const float* q_dev, int nq, int k, float* D_dev,
-                      long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial, size_t partial_bytes,
-                      const float* max_norm2_dev, int num_sms, cudaStream_t stream, int* launches);
+int gemm_search_chunk(const float* rows, const void* rows_bf16, long long n, int d, const float* q_dev, int nq, int k,
+                      float* D_dev, long long* I_dev, long long id_offset, unsigned char* scratch, u64* partial,
+                      size_t partial_bytes, const float* max_norm2_dev, int num_sms, cudaStream_t stream, int* launches);
+// csrc/flat_gemm_wide.cu
+int rows_to_bf16(const float* rows, long long n, int d, void* out, int num_sms, cudaStream_t stream);
 
 static size_t workspace_bytes() { return 256 + kPartialBytes + gemm_scratch_bytes(); }
 
@@ -441,6 +443,9 @@ struct b2r_flat {
   std::vector<HostCtx*> all_ctx;
   float* max_norm2 = nullptr;      // device scalar: max |row|^2 (error bound of the tf32 candidate pass)
   long long max_norm2_rows = -1;   // number of rows it was computed for
+  bool want_bf16 = false;          // b2r_flat_set_candidate_bf16: keep a bf16 copy of the rows for the candidate pass
+  void* rows_bf16 = nullptr;
+  long long bf16_rows = -1;        // number of rows the copy covers
 };
 
 namespace b2r {
@@ -472,6 +477,21 @@ static int ensure_row_norm(b2r_flat* h, cudaStream_t stream) {
     B2R_CUDA(cudaStreamSynchronize(stream));
     h->max_norm2_rows = h->n;
   }
+  return B2R_OK;
+}
+
+// bf16 copy of the rows (optional), rebuilt when the index has grown
+static int ensure_bf16(b2r_flat* h, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->want_bf16 || h->bf16_rows == h->n) return B2R_OK;
+  if (h->rows_bf16) cudaFree(h->rows_bf16);
+  h->rows_bf16 = nullptr;
+  h->bf16_rows = -1;
+  B2R_CUDA(cudaMalloc(&h->rows_bf16, static_cast<size_t>(h->n) * h->d * 2));
+  int rc = rows_to_bf16(h->rows, h->n, h->d, h->rows_bf16, h->num_sms, stream);
+  if (rc) return rc;
+  B2R_CUDA(cudaStreamSynchronize(stream));
+  h->bf16_rows = h->n;
   return B2R_OK;
 }
 
@@ -660,11 +680,14 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
     gemm_max = std::min(gemm_max, gemm_max_batch(k));
     rc = ensure_row_norm(h, stream);
     if (rc) return rc;
+    rc = ensure_bf16(h, stream);
+    if (rc) return rc;
   }
   while (use_gemm && nq - done >= gemm_min) {
     const int chunk = std::min(nq - done, gemm_max);
     int launches = 0;
-    rc = gemm_search_chunk(h->rows, h->n, h->d, q_dev + static_cast<size_t>(done) * h->d, chunk, k,
+    rc = gemm_search_chunk(h->rows, h->bf16_rows == h->n ? h->rows_bf16 : nullptr, h->n, h->d,
+                           q_dev + static_cast<size_t>(done) * h->d, chunk, k,
                            D_dev + static_cast<size_t>(done) * k,
                            reinterpret_cast<long long*>(I_dev) + static_cast<size_t>(done) * k, id_offset,
                            ws.base + 256 + kPartialBytes, reinterpret_cast<u64*>(ws.base + 256), kPartialBytes, h->max_norm2,
@@ -932,10 +955,25 @@ int b2r_flat_reconstruct(b2r_flat* h, const int64_t* ids, int m, float* out) {
   return rc;
 }
 
+int b2r_flat_set_candidate_bf16(b2r_flat* h, int enable) {
+  if (!h) return fail(B2R_ERR_INVALID, "b2r_flat_set_candidate_bf16: NULL handle");
+  DeviceGuard g(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->want_bf16 = enable != 0;
+  if (!h->want_bf16 && h->rows_bf16) {
+    cudaDeviceSynchronize();
+    cudaFree(h->rows_bf16);
+    h->rows_bf16 = nullptr;
+    h->bf16_rows = -1;
+  }
+  return B2R_OK;
+}
+
 int b2r_flat_destroy(b2r_flat* h) {
   if (!h) return B2R_OK;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
+  if (h->rows_bf16) cudaFree(h->rows_bf16);
   for (HostCtx* c : h->all_ctx) {
     if (c->q_dev) cudaFree(c->q_dev);
     if (c->q_pin) cudaFreeHost(c->q_pin);

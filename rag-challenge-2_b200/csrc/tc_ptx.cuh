@@ -164,6 +164,17 @@ __device__ __forceinline__ void tc_mma_tf32_pair(u32 tmem_d, u64 desc_a, u64 des
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with bf16 operands (kind::f16, K = 16 per instruction)
+__device__ __forceinline__ void tc_mma_bf16_pair(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on the mbarrier at this shared-memory offset in both CTAs once the previously issued MMAs have completed
 __device__ __forceinline__ void tc_commit_pair(u64* bar) {
   asm volatile(
@@ -204,6 +215,10 @@ __device__ __forceinline__ void mbar_wait_cluster_tag(u64* bar, u32 parity, int 
     }
   }
 }
+// instruction descriptor: D fp32, A/B bf16, both K-major
+__host__ __device__ constexpr u32 make_idesc_bf16_mn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<u32>(n >> 3) << 17) | (static_cast<u32>(m >> 4) << 24);
+}
 // instruction descriptor: D fp32, A/B tf32, both K-major, M (128 or 256), N
 __host__ __device__ constexpr u32 make_idesc_tf32_mn(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<u32>(n >> 3) << 17) | (static_cast<u32>(m >> 4) << 24);
@@ -214,5 +229,8 @@ __host__ __device__ constexpr u32 make_idesc_tf32_mn(int m, int n) {
 // host: 2-D tensor map over a row-major float32 matrix [outer, inner], {box_inner x box_outer} boxes, SWIZZLE_128B
 int make_map_2d(CUtensorMap* map, const float* base, unsigned long long inner, unsigned long long outer,
                 unsigned box_inner, unsigned box_outer);
+// same over a bfloat16 matrix (box_inner = 64 elements = one 128-byte swizzle row)
+int make_map_2d_bf16(CUtensorMap* map, const void* base, unsigned long long inner, unsigned long long outer,
+                     unsigned box_inner, unsigned box_outer);
 
 }  // namespace b2r

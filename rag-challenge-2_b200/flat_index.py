@@ -121,6 +121,11 @@ class FlatIPIndex:
         )
         return D, I
 
+    def enable_bf16_candidates(self, enable=True):
+        """Keep a bf16 copy of the rows for the candidate pass of batches of more than 128 queries (exact results:
+        fp32 rescoring + completeness proof, see b2r_flat_set_candidate_bf16)."""
+        _lib.check(self._lib.b2r_flat_set_candidate_bf16(self._h, 1 if enable else 0))
+
     def last_launch_count(self):
         return int(self._lib.b2r_last_launch_count())
 

@@ -238,3 +238,35 @@ def test_cta_pair_other_widths_and_overflow(b2r):
     index = b2r.FlatIPIndex(1024)
     index.add(xb)
     check(index, xb, np.concatenate([q, queries_for(xb, 140, 87)]), 30)
+
+
+@pytest.mark.parametrize("nq,d", [(256, 1024), (300, 1024), (200, 192)])
+def test_bf16_candidate_pass(b2r, nq, d):
+    """Opt-in bf16 copy of the rows for the candidate pass of large batches: the answers stay exact (fp32 rescoring,
+    completeness proof with the bf16 bound, 3xTF32 redo) and equal the tf32 path's."""
+    from rag_challenge_2_b200 import _lib
+
+    xb = unit_rows(60001, d, 91)
+    index = b2r.FlatIPIndex(d)
+    index.add(xb)
+    xq = queries_for(xb, nq, 92 + nq)
+    D0, I0 = check(index, xb, xq, 30)
+    index.enable_bf16_candidates()
+    D1, I1 = check(index, xb, xq, 30)
+    assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+    index.add(unit_rows(5000, d, 93))                      # growing the index rebuilds the copy
+    xb2 = np.concatenate([xb, unit_rows(5000, d, 93)])
+    check(index, xb2, xq, 30)
+    # crowded scores: the bf16 bound cannot prove completeness, the redo pass must answer
+    base = unit_rows(4, d, 94)
+    rng = np.random.default_rng(95)
+    crowd = np.repeat(base, 3000, axis=0) + 1e-4 * rng.standard_normal((12000, d)).astype(np.float32) / np.sqrt(d)
+    xb3 = np.concatenate([crowd, unit_rows(20000, d, 96)]).astype(np.float32)
+    idx3 = b2r.FlatIPIndex(d)
+    idx3.add(xb3)
+    idx3.enable_bf16_candidates()
+    check(idx3, xb3, np.concatenate([base, queries_for(xb3, 140, 97)]), 30)
+    index.enable_bf16_candidates(False)
+    D2, I2 = index.search(xq, 30)
+    _lib.tunable_set("gemm.no_pair", 0)
+    assert I2.shape == (nq, 30)

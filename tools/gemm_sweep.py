@@ -12,11 +12,17 @@ from rag_challenge_2_b200 import _lib, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 nqs = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 16, 32, 64, 128, 256, 1024]
+use_bf16 = False
 for kv in sys.argv[3:]:
     key, v = kv.split("=")
-    _lib.tunable_set(key, int(v))
+    if key == "bf16":
+        use_bf16 = bool(int(v))
+    else:
+        _lib.tunable_set(key, int(v))
 rows = synth.dense_rows_torch(0, n, 1024, "cuda")
 index = pkg.FlatIPIndex.from_device_tensor(rows)
+if use_bf16:
+    index.enable_bf16_candidates()
 out = []
 for nq in nqs:
     q = synth.dense_queries_torch(nq, 1024, "cuda", rows)
