@@ -503,6 +503,9 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
     const int b = static_cast<int>(item - static_cast<long long>(ql) * a.n_blocks);
     const long long lo = static_cast<long long>(b) * kStreamBlk;
     const int nb = static_cast<int>(min(a.n_docs, lo + kStreamBlk) - lo);
+    // the query's threshold is fetched now and used after the accumulation (its latency hides behind the stages; a
+    // slightly stale value is only a lower bound that is a little lower)
+    const u64 taug_early = a.dense ? 0ull : *(reinterpret_cast<volatile u64*>(a.tau_g) + ql);
     // ---- accumulate: stages arrive in token order (acc is zero: cleared at start / by the previous select) ----
     for (;;) {
       mbar_wait_wd(&full[s], ph);
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
 
     // ---- fused select: best k of this block among the documents that can still matter ----
     const int k = a.k;
-    const u64 taug = (a.debug_skip & 1) ? ~0ull : *(reinterpret_cast<volatile u64*>(a.tau_g) + ql);
+    const u64 taug = (a.debug_skip & 1) ? ~0ull : taug_early;
     u64 sk[kStreamBlk / 256];
     u32 act = 0;  // bit i: document i * 256 + ct is a live candidate
 #pragma unroll
