@@ -785,14 +785,14 @@ class VectorRetriever:
         out = [None] * nq
 
         def exp_hits(qi, exp, source):
+            """(hit, walk score) of every step of a walk, lazily: a failing record (e.g. a chunk whose page is missing)
+            stops the (query, report) task where the reference's try / except does, keeping the hits before it."""
             emb = query_items[qi][1]
-            got = []
             for score, idx in exp.get("results", []):
                 if idx == -1:
                     continue
                 sim = self._query_similarity_vec(emb, idx, score, row_of)
-                got.append((self._hit(sha1, chunks, pages, idx, sim, source, return_parent_pages), score))
-            return got
+                yield self._hit(sha1, chunks, pages, idx, sim, source, return_parent_pages), score
 
         row_of = {}   # id -> stored row, filled by the batched gathers below
 
@@ -820,7 +820,8 @@ class VectorRetriever:
                 details = exp["traversal_details"]
                 details["anchor"]["score"] = float(D[qi][0])
                 try:
-                    hits = [h for h, _ in exp_hits(qi, exp, retrieval_method)]
+                    for h, _ in exp_hits(qi, exp, retrieval_method):
+                        hits.append(h)
                 except Exception as e:  # noqa: BLE001
                     self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
                 out[qi] = (q, {"hits": hits, "traversal_details": details})
