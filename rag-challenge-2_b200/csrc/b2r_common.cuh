@@ -198,88 +198,6 @@ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// device: select the k largest keys out of n_lists lists of `stride` keys each (every list sorted
-// descending, empty slots == 0) and leave them sorted in buf[0..k).  Whole-CTA routine.
-//   src      : global memory, n_lists * stride keys
-//   buf      : shared scratch of buf_cap keys (power of two, >= 2k)
-//   s_ctl    : shared u64[2] scratch
-// Fast path: every key that can be in the answer is >= T = max over lists of the list's k-th key
-// (that list alone already holds k keys >= T), so only the survivors of that filter are sorted —
-// for randomly distributed data a little over k of them.  If the survivors do not fit (adversarial
-// layouts) fall back to streaming rounds of "keep best k, append, sort".
-// ----------------------------------------------------------------------------------------------
-// the part of a key the prefilter compares (the score bits; for 128-bit keys ties on the score
-// survive the filter and are resolved by the sort)
-__device__ __forceinline__ u64 key_prune_part(u64 k) { return k; }
-__device__ __forceinline__ u64 key_prune_part(u128 k) { return static_cast<u64>(k >> 64); }
-
-template <class K>
-__device__ __forceinline__ void block_select_lists(const K* __restrict__ src, int n_lists, int stride,
-                                                   int k, K* buf, int buf_cap, u64* s_ctl) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const long long total = static_cast<long long>(n_lists) * stride;
-  u32* s_cnt = reinterpret_cast<u32*>(s_ctl);  // [0] survivor count
-  u64* s_thr = s_ctl + 1;                      // threshold key
-  if (tid == 0) {
-    *s_cnt = 0;
-    *s_thr = 0;
-  }
-  __syncthreads();
-  if (k <= stride) {
-    u64 t = 0;
-    for (int l = tid; l < n_lists; l += nt) {
-      const u64 v = key_prune_part(src[static_cast<long long>(l) * stride + (k - 1)]);
-      t = v > t ? v : t;
-    }
-    if (t) atomicMax(s_thr, t);
-  }
-  __syncthreads();
-  const u64 thr = *s_thr;
-  // Second, usually much tighter bound when there are many lists: the k-th largest of the lists'
-  // best entries.  Those k lists each hold at least one key >= theta, so >= k keys survive, and
-  // for data spread over many lists only a little over k do.  Compared as full keys, so runs of
-  // equal scores (BM25's zero-score tail) do not all survive.
-  K theta = 0;
-  const int lp = next_pow2(n_lists < 2 ? 2 : n_lists);
-  if (n_lists >= k && lp <= buf_cap) {
-    for (int l = tid; l < lp; l += nt) buf[l] = l < n_lists ? src[static_cast<long long>(l) * stride] : static_cast<K>(0);
-    __syncthreads();
-    block_sort_desc(buf, lp);
-    theta = buf[k - 1];
-    __syncthreads();
-  }
-  for (long long i = tid; i < total; i += nt) {
-    const K v = src[i];
-    if (v != 0 && key_prune_part(v) >= thr && v >= theta) {
-      const u32 pos = atomicAdd(s_cnt, 1u);
-      if (pos < static_cast<u32>(buf_cap)) buf[pos] = v;
-    }
-  }
-  __syncthreads();
-  const u32 cnt = *s_cnt;
-  if (cnt <= static_cast<u32>(buf_cap)) {
-    const int need = static_cast<int>(cnt) > k ? static_cast<int>(cnt) : k;
-    const int p = next_pow2(need < 2 ? 2 : need);
-    for (int i = cnt + tid; i < p; i += nt) buf[i] = 0;
-    __syncthreads();
-    block_sort_desc(buf, p);
-    return;
-  }
-  // fallback: streaming rounds; buf[0..k) holds the best so far
-  for (int i = tid; i < buf_cap; i += nt) buf[i] = 0;
-  __syncthreads();
-  const int chunk = buf_cap - k;
-  for (long long base = 0; base < total; base += chunk) {
-    for (int i = tid; i < chunk; i += nt) {
-      const long long g = base + i;
-      buf[k + i] = g < total ? src[g] : static_cast<K>(0);
-    }
-    __syncthreads();
-    block_sort_desc(buf, buf_cap);
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
 // device: the kp largest of n UNSORTED keys in shared memory, by histogram (O(n) instead of a full
 // bitonic sort).  Whole-CTA routine; leaves the result sorted descending in out[0..) (zero padded up
 // to at least kp entries).
@@ -321,7 +239,9 @@ __device__ __forceinline__ void block_topk_hist(K* keys, int n, int n_pow2_cap, 
   {
     u32 lo = 0xFFFFFFFFu, hi = 0u;
     for (int i = tid; i < n; i += nt) {
-      const u32 s = key_score_bits(keys[i]);
+      const K v = keys[i];
+      if (v == 0) continue;  // empty slot: never selected, and it must not stretch the bin range
+      const u32 s = key_score_bits(v);
       lo = s < lo ? s : lo;
       hi = s > hi ? s : hi;
     }
@@ -334,10 +254,13 @@ __device__ __forceinline__ void block_topk_hist(K* keys, int n, int n_pow2_cap, 
   }
   __syncthreads();
   const u32 lo = *s_lo;
-  const u32 range = *s_hi - lo;
+  const u32 range = *s_hi >= lo ? *s_hi - lo : 0u;  // no valid key at all: lo = 0xFFFFFFFF, hi = 0
   int sh = 0;
   while ((range >> sh) >= static_cast<u32>(kSelBins)) ++sh;
-  for (int i = tid; i < n; i += nt) atomicAdd(&hist[(key_score_bits(keys[i]) - lo) >> sh], 1u);
+  for (int i = tid; i < n; i += nt) {
+    const K v = keys[i];
+    if (v != 0) atomicAdd(&hist[(key_score_bits(v) - lo) >> sh], 1u);
+  }
   __syncthreads();
   if (tid < 32) {  // one warp walks the bins from the top: lane l owns bins [2048 - 64 (l + 1), 2048 - 64 l)
     constexpr int per = kSelBins / 32;
@@ -366,7 +289,7 @@ __device__ __forceinline__ void block_topk_hist(K* keys, int n, int n_pow2_cap, 
   const u32 bstar = *s_bin;
   for (int i = tid; i < n; i += nt) {
     const K v = keys[i];
-    if (((key_score_bits(v) - lo) >> sh) >= bstar) {
+    if (v != 0 && ((key_score_bits(v) - lo) >> sh) >= bstar) {
       const u32 pos = atomicAdd(s_cnt, 1u);
       if (pos < static_cast<u32>(out_cap)) out[pos] = v;
     }
@@ -390,6 +313,94 @@ __device__ __forceinline__ void block_topk_hist(K* keys, int n, int n_pow2_cap, 
   block_sort_desc(keys, p);
   for (int i = tid; i < out_cap; i += nt) out[i] = i < p ? keys[i] : static_cast<K>(0);
   __syncthreads();
+}
+
+// ----------------------------------------------------------------------------------------------
+// device: select the k largest keys out of n_lists lists of `stride` keys each (every list sorted
+// descending, empty slots == 0) and leave them sorted in buf[0..k).  Whole-CTA routine.
+//   src      : global memory, n_lists * stride keys
+//   buf      : shared scratch of buf_cap keys (power of two, >= 2k)
+//   s_ctl    : shared u64[2] scratch
+// Fast path: every key that can be in the answer is >= T = max over lists of the list's k-th key
+// (that list alone already holds k keys >= T), so only the survivors of that filter are sorted —
+// for randomly distributed data a little over k of them.  If the survivors do not fit (adversarial
+// layouts) fall back to streaming rounds of "keep best k, append, sort".
+// ----------------------------------------------------------------------------------------------
+// the part of a key the prefilter compares (the score bits; for 128-bit keys ties on the score
+// survive the filter and are resolved by the sort)
+__device__ __forceinline__ u64 key_prune_part(u64 k) { return k; }
+__device__ __forceinline__ u64 key_prune_part(u128 k) { return static_cast<u64>(k >> 64); }
+
+template <class K>
+__device__ __forceinline__ void block_select_lists(const K* __restrict__ src, int n_lists, int stride,
+                                                   int k, K* buf, int buf_cap, u64* s_ctl, u32* hist = nullptr) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const long long total = static_cast<long long>(n_lists) * stride;
+  u32* s_cnt = reinterpret_cast<u32*>(s_ctl);  // [0] survivor count
+  u64* s_thr = s_ctl + 1;                      // threshold key
+  if (tid == 0) {
+    *s_cnt = 0;
+    *s_thr = 0;
+  }
+  __syncthreads();
+  if (k <= stride) {
+    u64 t = 0;
+    for (int l = tid; l < n_lists; l += nt) {
+      const u64 v = key_prune_part(src[static_cast<long long>(l) * stride + (k - 1)]);
+      t = v > t ? v : t;
+    }
+    if (t) atomicMax(s_thr, t);
+  }
+  __syncthreads();
+  const u64 thr = *s_thr;
+  // Second, usually much tighter bound when there are many lists: the k-th largest of the lists'
+  // best entries.  Those k lists each hold at least one key >= theta, so >= k keys survive, and
+  // for data spread over many lists only a little over k do.  Compared as full keys, so runs of
+  // equal scores (BM25's zero-score tail) do not all survive.
+  K theta = 0;
+  const int lp = next_pow2(n_lists < 2 ? 2 : n_lists);
+  if (n_lists >= k && lp <= buf_cap) {
+    for (int l = tid; l < lp; l += nt) buf[l] = l < n_lists ? src[static_cast<long long>(l) * stride] : static_cast<K>(0);
+    __syncthreads();
+    const int oc = next_pow2(2 * k);
+    if (hist != nullptr && lp > oc && lp + oc <= buf_cap) {  // histogram select of the k-th largest list maximum
+      block_topk_hist(buf, lp, lp, k, hist, buf + lp, oc);
+      theta = buf[lp + k - 1];
+    } else {
+      block_sort_desc(buf, lp);
+      theta = buf[k - 1];
+    }
+    __syncthreads();
+  }
+  for (long long i = tid; i < total; i += nt) {
+    const K v = src[i];
+    if (v != 0 && key_prune_part(v) >= thr && v >= theta) {
+      const u32 pos = atomicAdd(s_cnt, 1u);
+      if (pos < static_cast<u32>(buf_cap)) buf[pos] = v;
+    }
+  }
+  __syncthreads();
+  const u32 cnt = *s_cnt;
+  if (cnt <= static_cast<u32>(buf_cap)) {
+    const int need = static_cast<int>(cnt) > k ? static_cast<int>(cnt) : k;
+    const int p = next_pow2(need < 2 ? 2 : need);
+    for (int i = cnt + tid; i < p; i += nt) buf[i] = 0;
+    __syncthreads();
+    block_sort_desc(buf, p);
+    return;
+  }
+  // fallback: streaming rounds; buf[0..k) holds the best so far
+  for (int i = tid; i < buf_cap; i += nt) buf[i] = 0;
+  __syncthreads();
+  const int chunk = buf_cap - k;
+  for (long long base = 0; base < total; base += chunk) {
+    for (int i = tid; i < chunk; i += nt) {
+      const long long g = base + i;
+      buf[k + i] = g < total ? src[g] : static_cast<K>(0);
+    }
+    __syncthreads();
+    block_sort_desc(buf, buf_cap);
+  }
 }
 
 // write buf[0..k) (sorted keys) as (score, int64 id) with faiss padding for empty slots

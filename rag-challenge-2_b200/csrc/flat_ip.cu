@@ -70,13 +70,28 @@ __device__ __forceinline__ void scan_epilogue(const ScanArgs& a, u64* cand, int 
                                               u64* ctl) {
   const int tid = threadIdx.x;
   const int region = lists_per_q * a.cap;
+  // Scratch (the idle stage ring): the per-CTA merge and the last CTA's threshold step select by histogram instead of
+  // sorting everything when the scratch has room for it: [out / lists: sel_cap / 2 keys][histogram].
+  const int oc = next_pow2(2 * a.k);
+  constexpr int kHistKeys = (kSelBins + 4 + 1) / 2;
+  const bool use_hist = region > oc && a.sel_cap / 2 >= oc && a.sel_cap / 2 >= kHistKeys;
+  u32* hist = reinterpret_cast<u32*>(sel_buf + a.sel_cap / 2);
 #pragma unroll
   for (int qi = 0; qi < NQ; ++qi) {
     if (qi < a.nq) {
       u64* reg = cand + static_cast<size_t>(qi) * region;
-      block_sort_desc(reg, region);
+      const u64* best = reg;
+      int n_best = region;
+      if (use_hist) {
+        block_topk_hist(reg, region, region, a.k, hist, sel_buf, oc);
+        best = sel_buf;
+        n_best = oc;
+      } else {
+        block_sort_desc(reg, region);
+      }
       u64* dst = a.partial + (static_cast<size_t>(qi) * gridDim.x + blockIdx.x) * a.k;
-      for (int i = tid; i < a.k; i += blockDim.x) dst[i] = i < region ? reg[i] : 0ull;
+      for (int i = tid; i < a.k; i += blockDim.x) dst[i] = i < n_best ? best[i] : 0ull;
+      __syncthreads();
     }
   }
   __threadfence();
@@ -90,8 +105,12 @@ __device__ __forceinline__ void scan_epilogue(const ScanArgs& a, u64* cand, int 
   if (*s_last == 0) return;
   __threadfence();
   for (int qi = 0; qi < a.nq; ++qi) {
-    block_select_lists(a.partial + static_cast<size_t>(qi) * gridDim.x * a.k, gridDim.x, a.k, a.k,
-                       sel_buf, a.sel_cap, ctl);
+    if (use_hist) {
+      block_select_lists(a.partial + static_cast<size_t>(qi) * gridDim.x * a.k, gridDim.x, a.k, a.k, sel_buf, a.sel_cap / 2,
+                         ctl, hist);
+    } else {
+      block_select_lists(a.partial + static_cast<size_t>(qi) * gridDim.x * a.k, gridDim.x, a.k, a.k, sel_buf, a.sel_cap, ctl);
+    }
     block_emit_keys(sel_buf, a.k, a.D + static_cast<size_t>(qi) * a.k, a.I + static_cast<size_t>(qi) * a.k,
                     a.id_offset);
     __syncthreads();
