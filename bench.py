@@ -167,7 +167,8 @@ def cpu_baseline(args, steps, rows_sample=None, verbose=False):
     per_query = t_dense * (args.rows / n_dense) + t_bm * (args.rows / n_docs)
     return {
         "value": 1.0 / per_query, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-        "sample": (f"oracle port (numpy/OpenBLAS fp32 scan + partial sort; rank_bm25-style per-document dict loops + "
+        "threads": {"dense_scan_openblas": os.cpu_count(), "bm25_python_loops": 1},
+        "sample": (f"oracle port (numpy/OpenBLAS fp32 scan on all cores + partial sort; rank_bm25-style per-document dict loops + "
                    f"Python stable sort): dense {n_dense} x {args.dim} rows {t_dense * 1e3:.1f} ms/query, BM25 {n_docs} docs "
                    f"{t_bm * 1e3:.1f} ms/query, both scaled linearly to {args.rows} chunks (extrapolated); {steps} queries"),
         "t_dense_ms_sample": t_dense * 1e3, "t_bm25_ms_sample": t_bm * 1e3,
@@ -187,7 +188,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.nq / cb["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "threads")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "timed_steps": steps,
     }
@@ -425,7 +426,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             n_s = min(args.cpu_rows, hi - lo)
             cb = cpu_baseline(args, 10, rows_sample=rows[:n_s].cpu().numpy())
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "threads")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
