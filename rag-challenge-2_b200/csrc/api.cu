@@ -39,6 +39,7 @@ static std::map<std::string, int>& tunables() {
       {"cosine.no_pair", 0},       // 1: N x N statistics on the single-CTA 3xTF32 kernel instead of the CTA-pair one
       {"gemm.no_bf16", 0},         // 1: ignore the bf16 copy of the rows (candidate pass stays tf32)
       {"gemm.no_pair", 0},         // 1: at most 128 queries per pass (no CTA-pair kernel)
+      {"gemm.small_rescore", 0},   // 1: indexes under 16,384 rows also take the candidate + fp32 rescoring path
       {"gemm.no_wide", 0},         // 1: candidate pass keeps lists in shared memory (<= 64 queries / pass) instead of thresholds
       {"gemm.wide_sub", 0},        // 128-row sub-tiles per tile of the threshold candidate pass (1 or 2; default by width)
       {"gemm.tile256", 0},         // 1: candidate pass scores 256 rows per query slab (experimental)

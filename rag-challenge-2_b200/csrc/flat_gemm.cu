@@ -775,7 +775,11 @@ int gemm_search_chunk(const float* rows, const void* rows_bf16, long long n, int
   u32* premax = reinterpret_cast<u32*>(scratch + kScrPremax);
   const int mode = tunable("gemm.mode");  // 0/1: approximate pass + exact rescoring (+ verified fallback); 3: 3xTF32 only
   int rc;
-  if (mode == 3 || k > 64) {
+  // Report-sized indexes (below the threshold pass's 16,384 rows) are latency-bound: the 3xTF32 scan alone is three
+  // launches, the candidate + rescoring + redo chain nine, and the 3xTF32 kernel's shared-memory appetite does not
+  // matter on a few MB of rows (profiles/r01_small_index_sweep.json).
+  const bool small_index = n < 16384 && !tunable("gemm.small_rescore");
+  if (mode == 3 || k > 64 || small_index) {
     const int step = list_scan_max_batch(k);
     for (int off = 0; off < nq; off += step) {
       const int c = std::min(step, nq - off);
