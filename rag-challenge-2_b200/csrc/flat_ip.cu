@@ -440,7 +440,8 @@ struct HostCtx {
   float* q_pin = nullptr;
   size_t q_cap = 0;  // floats
   unsigned char* out_dev = nullptr;
-  unsigned char* out_pin = nullptr;
+  unsigned char* out_pin = nullptr;      // mapped pinned memory
+  unsigned char* out_pin_dev = nullptr;  // its device alias: small results are stored straight into host memory
   size_t out_cap = 0;  // bytes
 };
 
@@ -792,7 +793,8 @@ static int ensure_ctx_buffers(HostCtx* c, size_t q_floats, size_t out_bytes) {
     c->out_cap = 0;
     const size_t cap = std::max<size_t>(out_bytes, 64 * 1024);
     B2R_CUDA(cudaMalloc(&c->out_dev, cap));
-    B2R_CUDA(cudaMallocHost(&c->out_pin, cap));
+    B2R_CUDA(cudaHostAlloc(&c->out_pin, cap, cudaHostAllocMapped));
+    B2R_CUDA(cudaHostGetDevicePointer(&c->out_pin_dev, c->out_pin, 0));
     c->out_cap = cap;
   }
   return B2R_OK;
@@ -918,13 +920,17 @@ int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, i
   rc = ensure_ctx_buffers(c, q_floats, out_bytes);
   if (rc == B2R_OK) {
     memcpy(c->q_pin, q, q_floats * sizeof(float));
-    float* D_dev = reinterpret_cast<float*>(c->out_dev);
-    int64_t* I_dev = reinterpret_cast<int64_t*>(c->out_dev + d_bytes);
+    // small results (the retriever's case: a few queries x top-n) are written by the kernels straight into mapped
+    // pinned host memory — one copy operation (~10 us of a ~55 us call) less; large ones go through a device buffer
+    const bool zero_copy = out_bytes <= 256 * 1024;
+    unsigned char* out_base = zero_copy ? c->out_pin_dev : c->out_dev;
+    float* D_dev = reinterpret_cast<float*>(out_base);
+    int64_t* I_dev = reinterpret_cast<int64_t*>(out_base + d_bytes);
     cudaError_t e = cudaMemcpyAsync(c->q_dev, c->q_pin, q_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
       rc = flat_search_dev_impl(h, c->q_dev, nq, k, D_dev, I_dev, 0, c->stream);
       if (rc == B2R_OK) {
-        e = cudaMemcpyAsync(c->out_pin, c->out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (!zero_copy) e = cudaMemcpyAsync(c->out_pin, c->out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       }
     }
