@@ -687,11 +687,11 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
   if (rc) return rc;
   int done = 0;
   // batches go to the tensor cores (K2): one pass over the rows per <= 256 queries
-  // smallest batch that goes to the tensor cores: 5 on report-sized indexes, 3 from 32k rows on, where one
-  // tensor-core pass beats a 4-query SIMT pass (profiles/r01_small_index_sweep.json: 200k rows, 4 queries SIMT
-  // 365 us vs 5 queries on the tensor path 241 us; equal at 10k rows)
+  // smallest batch that goes to the tensor cores: 3.  One tensor-core pass beats a 4-query SIMT pass at every index
+  // size (profiles/r01_small_index_sweep.json: 10k rows, 4 queries SIMT 115 us vs 8 queries on the tensor path
+  // 86 us; 200k rows 337 vs 233 us); two queries stay on the SIMT kernel (81 us at 10k rows).
   int gemm_min = tunable("flat.gemm_min_nq");
-  if (gemm_min <= 0) gemm_min = h->n >= 32768 ? 3 : 5;
+  if (gemm_min <= 0) gemm_min = 3;
   int gemm_max = tunable("flat.gemm_max_n");
   if (gemm_max <= 0 || gemm_max > 256) gemm_max = 256;
   const bool use_gemm = nq >= gemm_min && gemm_path_supported(h->d, k) && !tunable("flat.force_generic") &&

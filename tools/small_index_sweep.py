@@ -18,7 +18,7 @@ for n in (2000, 10000, 50000, 200000):
     xb /= np.linalg.norm(xb, axis=1, keepdims=True)
     index = pkg.FlatIPIndex(1024)
     index.add(xb)
-    for nq in (1, 2, 4, 5, 8, 12, 16, 32):
+    for nq in (1, 2, 3, 4, 5, 8, 12, 16, 32):
         xq = xb[:nq] + 0.01 * rng.standard_normal((nq, 1024), dtype=np.float32)
         rec = {"n": n, "nq": nq}
         for name, flag in (("simt_us", 1), ("tensor_us", 0)):
