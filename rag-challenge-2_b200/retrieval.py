@@ -750,11 +750,14 @@ class VectorRetriever:
             except Exception as e:  # noqa: BLE001
                 self._safe_print(f"[ERROR] Vector search failed in report {report.get('name')}: {e}")
                 return [(q, []) for q in texts]
+            # .tolist() yields the same Python floats / ints as float(d) / int(i) per element, without the numpy
+            # scalar round trips (23k hits for a 127-question batch over six databases)
+            D_rows, I_rows = np.asarray(D).tolist(), np.asarray(I).tolist()
             for qi, q in enumerate(texts):
                 hits = []
                 try:
-                    for distance, index in zip(D[qi], I[qi]):
-                        hits.append(self._hit(sha1, chunks, pages, int(index), round(float(distance) * 1.0, 4),
+                    for distance, index in zip(D_rows[qi], I_rows[qi]):
+                        hits.append(self._hit(sha1, chunks, pages, index, round(distance * 1.0, 4),
                                               "basic", return_parent_pages))
                 except Exception as e:  # noqa: BLE001 - partial hits are kept (:1441-1442)
                     self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
@@ -1213,7 +1216,8 @@ class VectorRetriever:
     def fuse_similarity(info):
         """final = max(similarities) * (1 + 0.2*(count-1)) * (1 + 0.1*(methods-1) if methods >= 2 else 1)
         (reference :1639-1661; worked examples in docs/retrieval_algorithms/...20251203.md:139-151)."""
-        base = max(info["similarities"])
+        sims = info["similarities"]
+        base = sims[0] if len(sims) == 1 else max(sims)
         query_bonus = 1.0 + 0.2 * (info["count"] - 1)
         methods = set(info.get("retrieval_sources") or ["basic"])
         method_bonus = 1.0 + 0.1 * (len(methods) - 1) if len(methods) >= 2 else 1.0
