@@ -1225,6 +1225,13 @@ class VectorRetriever:
 
     @classmethod
     def _final_record(cls, info):
+        sims, sources = info["similarities"], info.get("retrieval_sources")
+        if len(sims) == 1 and info["count"] == 1 and sources and len(sources) == 1:
+            # the common record (one query, one method hit it once): both bonuses are exactly 1.0
+            r = round(sims[0], 4)
+            return {"vector_similarity": r, "max_original_similarity": r, "page": info["page"], "text": info["text"],
+                    "hit_count": 1, "retrieval_sources": [sources[0]], "source_sha1": info["source_sha1"],
+                    "query_sources": info.get("query_sources", [])}
         final, base, methods = cls.fuse_similarity(info)
         return {"vector_similarity": round(final, 4), "max_original_similarity": round(base, 4),
                 "page": info["page"], "text": info["text"], "hit_count": info["count"],
