@@ -34,6 +34,17 @@ VECTOR_CASES = {
                              retrieval_method="hybrid_expansion", max_hops=2, neighbor_k=6, selected_years=[2024]),
     "unknown_method_falls_back": dict(company_name=COMPANY, query=QUESTIONS[2], top_n=5, use_hyde=False,
                                       use_multi_query=False, retrieval_method="nonsense", selected_years=[2020]),
+    # graph expansions over several reports and several (expanded) queries: many walks advance together
+    "hybrid_expansion_multi": dict(company_name=COMPANY, query=QUESTIONS[3], top_n=20, return_parent_pages=True,
+                                   use_hyde=True, use_multi_query=True, multi_query_config=MQ_ALL,
+                                   retrieval_method="hybrid_expansion", max_hops=3, neighbor_k=6,
+                                   selected_years=[2023, 2024, 2025]),
+    "ssg_all_reports_expanded": dict(company_name=COMPANY, query=QUESTIONS[0], top_n=15, use_hyde=False,
+                                     use_multi_query=True, multi_query_config=MQ_ALL, retrieval_method="ssg",
+                                     max_hops=4, neighbor_k=10),
+    "triangulation_all_reports_hyde": dict(company_name=COMPANY, query=QUESTIONS[2], top_n=12, use_hyde=True,
+                                           use_multi_query=False, retrieval_method="triangulation", max_hops=3,
+                                           neighbor_k=7),
     "instance_attr_overrides_default": dict(company_name=COMPANY, query=QUESTIONS[1], top_n=6, use_hyde=False,
                                             use_multi_query=False, selected_years=[2021],
                                             _init=dict(retrieval_method="triangulation", max_hops=1, neighbor_k=4)),
