@@ -37,7 +37,35 @@ def cosine_stats(rows, col_begin=0, col_end=None, n_bins=N_BINS, finalize=True):
                                         None, None, rows.device.index or 0, C.c_void_p(stream)))
     if not finalize:
         return stats, hist
-    return finalize_stats(stats.cpu().numpy(), hist.cpu().numpy())
+    out = finalize_stats(stats.cpu().numpy(), hist.cpu().numpy())
+    if 2 <= n <= EXACT_MEDIAN_MAX_ROWS and int(col_begin) == 0 and col_end == n:
+        out["median_similarity"] = exact_median_small(rows)
+    return out
+
+
+EXACT_MEDIAN_MAX_ROWS = 1024
+
+
+def exact_median_small(rows):
+    """Report-sized inputs (n <= 1024, the reference's real case: a report has 1e3-1e4 chunks at most and the
+    miniature fixtures tens): with so few entries the two middle order statistics np.median averages
+    (generate_similarity_matrix.py:166) can lie further apart than a histogram bin, so the median is taken from the
+    values themselves — every row's n inner products with the normalised rows through the exact scan (k = n),
+    self entries dropped by id, clipped, sorted on the device."""
+    import torch
+
+    from .flat_index import FlatIPIndex
+
+    n = int(rows.shape[0])
+    xn = (rows / (rows.norm(dim=1, keepdim=True) + 1e-8)).contiguous()
+    index = FlatIPIndex.from_device_tensor(xn)
+    D, J = index.search_dev(xn, n)
+    off = D[J != torch.arange(n, device=rows.device).unsqueeze(1)].clamp_(-1.0, 1.0)
+    if off.numel() != n * (n - 1):
+        raise RuntimeError("exact_median_small: the k = n search did not return every row once")
+    s = off.sort().values
+    m = s.numel()  # n (n - 1): always even
+    return float((s[m // 2 - 1] + s[m // 2]) / 2)
 
 
 def finalize_stats(stats, hist):
@@ -128,3 +156,85 @@ def heatmap_tiles(rows, pixels=512):
     gram[torch.arange(p), torch.arange(p)] += sizes - self_dot
     tiles = gram / (sizes[:, None] * sizes[None, :])
     return tiles.clamp_(-1.0, 1.0).to(torch.float32), bounds
+
+
+class SimilarityMatrixGenerator:
+    """Script-level mirror of semantic_similarity_analysis/generate_similarity_matrix.py:19-331
+    (`SimilarityMatrixGenerator(vector_db_dir, documents_dir, output_dir)`, `process_document`,
+    `process_all_documents` -> `self.stats`, written to `<output_dir>/statistics.json`): the same per-report
+    statistics dictionary, computed on the GPU without the N x N matrix.  The Plotly page (:124-238, out of
+    scope) is replaced by the down-sampled tile map `<name>_similarity_tiles.npy` (`heatmap_tiles`)."""
+
+    def __init__(self, vector_db_dir, documents_dir, output_dir, device=0, pixels=512):
+        from pathlib import Path
+
+        self.vector_db_dir = Path(vector_db_dir)
+        self.documents_dir = Path(documents_dir)
+        self.output_dir = Path(output_dir)
+        self.output_dir.mkdir(parents=True, exist_ok=True)
+        self.device = int(device)
+        self.pixels = int(pixels)
+        self.stats = {}
+
+    def load_vectors_from_faiss(self, faiss_path):
+        """:38-64 — all rows of the index, as a float32 CUDA tensor (the reference returns a numpy array)."""
+        import torch
+
+        from .flat_index import read_index_rows
+
+        _, rows = read_index_rows(faiss_path)
+        return torch.from_numpy(np.ascontiguousarray(rows)).to(torch.device("cuda", self.device))
+
+    @staticmethod
+    def load_document_info(doc_path):
+        """:102-122"""
+        import json
+
+        with open(doc_path, "r", encoding="utf-8") as f:
+            doc = json.load(f)
+        return {
+            "name": doc["metainfo"]["sha1_name"],
+            "company": doc["metainfo"].get("company_name", "Unknown"),
+            "chunks_count": len(doc["content"]["chunks"]),
+            "pages": doc["metainfo"].get("pages_amount", 0),
+            "text_blocks": doc["metainfo"].get("text_blocks_amount", 0),
+            "tables": doc["metainfo"].get("tables_amount", 0),
+        }
+
+    def process_document(self, doc_name):
+        """:258-301 — missing files are reported and skipped."""
+        faiss_path = self.vector_db_dir / f"{doc_name}.faiss"
+        doc_path = self.documents_dir / f"{doc_name}.json"
+        if not faiss_path.exists():
+            print(f"❌ 未找到 FAISS 文件: {faiss_path}")
+            return
+        if not doc_path.exists():
+            print(f"❌ 未找到文档文件: {doc_path}")
+            return
+        doc_info = self.load_document_info(doc_path)
+        rows = self.load_vectors_from_faiss(faiss_path)
+        n = int(rows.shape[0])
+        s = cosine_stats(rows)  # raises on n < 2 as numpy's max() of an empty off-diagonal does (:170)
+        self.stats[doc_info["name"]] = {
+            "chunks_count": n,
+            "avg_similarity": s["avg_similarity"], "median_similarity": s["median_similarity"],
+            "std_similarity": s["std_similarity"], "max_similarity": s["max_similarity"],
+            "min_similarity": s["min_similarity"],
+            "company": doc_info["company"], "pages": doc_info["pages"], "text_blocks": doc_info["text_blocks"],
+            "tables": doc_info["tables"],
+        }
+        tiles, _ = heatmap_tiles(rows, self.pixels)
+        np.save(self.output_dir / f"{doc_name}_similarity_tiles.npy", tiles.cpu().numpy())
+
+    def process_all_documents(self):
+        """:303-349 — every `*.faiss` in sorted order; a failing document is reported and skipped."""
+        import json
+
+        for doc_name in [f.stem for f in sorted(self.vector_db_dir.glob("*.faiss"))]:
+            try:
+                self.process_document(doc_name)
+            except Exception as e:  # noqa: BLE001 - the reference catches, prints and continues (:326-331)
+                print(f"\n❌ 处理 {doc_name} 时出错: {e}")
+        with open(self.output_dir / "statistics.json", "w", encoding="utf-8") as f:
+            json.dump(self.stats, f, ensure_ascii=False, indent=2)
+        return self.stats

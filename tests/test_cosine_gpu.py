@@ -14,10 +14,12 @@ def compare(x, got):
     assert got["count"] == n * (n - 1)
     for key in ("avg_similarity", "std_similarity", "max_similarity", "min_similarity"):
         assert abs(got[key] - want[key]) <= 1e-5 * abs(want[key]) + 2e-6, (key, got[key], want[key])
-    assert abs(got["median_similarity"] - want["median_similarity"]) <= 1e-4, (got["median_similarity"], want["median_similarity"])
+    # n <= 1024: the median comes from the values themselves; above, from the 8192-bin histogram
+    med_tol = 2e-6 if n <= 1024 else 1e-4
+    assert abs(got["median_similarity"] - want["median_similarity"]) <= med_tol, (got["median_similarity"], want["median_similarity"])
 
 
-@pytest.mark.parametrize("n,d", [(2, 64), (65, 128), (130, 1024), (1000, 1024), (3001, 1024), (2500, 96)])
+@pytest.mark.parametrize("n,d", [(2, 64), (19, 1024), (65, 128), (130, 1024), (1000, 1024), (1024, 96), (3001, 1024), (2500, 96)])
 def test_stats_match_reference(b2r, n, d):
     import torch
 
