@@ -1,0 +1,148 @@
+"""Differential run: the REAL reference retrievers (/root/reference/src/retrieval.py, unmodified, over the
+oracle-backed faiss / rank_bm25 stand-ins of make_golden.py) and this repo's retrievers (same stand-in
+index objects), side by side in one process, on randomly drawn call parameters over the miniature corpus:
+top_n, parent pages, year filters, HyDE / multi-query switches and method subsets, retrieval method, hop
+and neighbour counts, reranking sample sizes, BM25 queries.  Every returned dictionary must be identical
+(timings zeroed, set-derived lists sorted — tests/golden_util.canon_result).
+
+Complements the fixed scenarios of cases.py: the committed golden file pins 25 hand-picked calls, this
+sweeps the parameter space (seeded, so a failure reproduces).  Needs the reference checkout, i.e. the
+authoring container; tests/test_differential.py skips elsewhere.
+
+    python -m tests.golden.differential --cases 200 --seed 1
+"""
+import argparse
+import io
+import json
+import os
+import sys
+import tempfile
+from contextlib import redirect_stdout
+
+import numpy as np
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests import golden_util as gu  # noqa: E402
+from tests.golden import corpus, make_golden, stubs  # noqa: E402
+
+WORDS = corpus.TOPICS + corpus.FILL + ["2020", "2021", "2022", "2023", "2024", "2025", "金盘科技", "毛利率", "zzzz"]
+
+
+def draw_vector_case(rng):
+    method = str(rng.choice(["basic", "basic", "ssg", "triangulation", "hybrid_expansion", "nonsense"]))
+    company = corpus.COMPANY if rng.random() < 0.85 else corpus.OTHER
+    if rng.random() < 0.03:
+        company = "nobody"  # ValueError("No report found with ...") on both sides (:844)
+    years = None
+    r = rng.random()
+    if r < 0.5:
+        years = sorted({int(y) for y in rng.choice(np.arange(2019, 2027), size=int(rng.integers(1, 4)))})
+    elif r < 0.55:
+        years = []
+    use_mq = bool(rng.random() < 0.35)
+    mq = None
+    if use_mq and rng.random() < 0.8:
+        mq = {m: bool(rng.random() < 0.6) for m in ("synonym", "subquestion", "variant")}
+    query = " ".join(str(w) for w in rng.choice(WORDS, size=int(rng.integers(1, 9))))
+    kw = dict(company_name=company, query=query, top_n=int(rng.choice([1, 2, 3, 5, 10, 30, 64, 100])),
+              return_parent_pages=bool(rng.random() < 0.5), use_hyde=bool(rng.random() < 0.3), use_multi_query=use_mq,
+              multi_query_config=mq, selected_years=years, retrieval_method=method,
+              max_hops=int(rng.integers(1, 5)), neighbor_k=int(rng.choice([1, 3, 6, 10, 30, 80])))
+    if rng.random() < 0.3:
+        kw["llm_reranking_sample_size"] = int(rng.integers(1, 40))
+    return kw
+
+
+def draw_hybrid_case(rng):
+    kw = draw_vector_case(rng)
+    kw["llm_reranking_sample_size"] = int(rng.integers(1, 40))
+    kw["documents_batch_size"] = int(rng.integers(1, 6))
+    kw["llm_weight"] = float(rng.choice([0.3, 0.7]))
+    return kw
+
+
+def draw_bm25_case(rng):
+    query = " ".join(str(w) for w in rng.choice(WORDS, size=int(rng.integers(1, 10))))
+    years = None
+    if rng.random() < 0.5:
+        years = sorted({int(y) for y in rng.choice(np.arange(2019, 2027), size=int(rng.integers(1, 4)))})
+    return dict(company_name=corpus.COMPANY if rng.random() < 0.8 else corpus.OTHER, query=query,
+                top_n=int(rng.choice([1, 3, 7, 30, 200])), return_parent_pages=bool(rng.random() < 0.5),
+                selected_years=years)
+
+
+def _call(fn):
+    try:
+        return {"ok": fn()}
+    except Exception as e:  # noqa: BLE001 - error behaviour is part of the contract
+        return {"error": [type(e).__name__, str(e)]}
+
+
+def _canon(x):
+    if "ok" in x:
+        return {"ok": gu.canon_result(x["ok"]) if isinstance(x["ok"], dict) else gu.canon_records(gu.strip_unpinned(x["ok"]))}
+    return x
+
+
+def run(n_cases, seed, verbose=False):
+    make_golden.install_stubs()
+    sys.path.insert(0, REF)
+    import src.retrieval as ref
+
+    assert ref.__file__.startswith(REF), ref.__file__
+    import rag_challenge_2_b200.retrieval as ours
+
+    ours.flat_index.read_index = lambda path, device=0: stubs.read_ixfi(path)
+    ours.load_bm25_pickle = gu.oracle_bm25_loader
+    ours.clear_resident_cache()
+    rng = np.random.default_rng(seed)
+    failures = []
+    sink = sys.stderr if verbose else io.StringIO()
+    with tempfile.TemporaryDirectory() as tmp, redirect_stdout(sink):
+        paths = corpus.build(tmp)
+        common = dict(vector_db_dir=paths["vector_db_dir"], documents_dir=paths["documents_dir"],
+                      subset_path=paths["subset_path"], parallel_workers=1)
+        for i in range(n_cases):
+            kind = ("vector", "vector", "vector", "hybrid", "bm25")[i % 5]
+            if kind == "vector":
+                kw = draw_vector_case(rng)
+                init = {}
+                if rng.random() < 0.2:  # constructor defaults that the call's defaults override or not (:808-822)
+                    init = dict(retrieval_method=kw.pop("retrieval_method"), max_hops=kw.pop("max_hops"),
+                                neighbor_k=kw.pop("neighbor_k"))
+                a = _call(lambda: ref.VectorRetriever(**common, **init).retrieve_by_company_name(**kw))
+                b = _call(lambda: ours.VectorRetriever(**common, qwen=stubs.ScriptedQwen(), **init).retrieve_by_company_name(**kw))
+            elif kind == "hybrid":
+                kw = draw_hybrid_case(rng)
+                a = _call(lambda: ref.HybridRetriever(**common).retrieve_by_company_name(**kw))
+                b = _call(lambda: ours.HybridRetriever(**common, qwen=stubs.ScriptedQwen(),
+                                                       reranker=stubs.ScriptedReranker()).retrieve_by_company_name(**kw))
+            else:
+                kw = draw_bm25_case(rng)
+                args = (paths["bm25_db_dir"], paths["bm25_documents_dir"])
+                a = _call(lambda: ref.BM25Retriever(*args, subset_path=paths["subset_path"]).retrieve_by_company_name(**kw))
+                b = _call(lambda: ours.BM25Retriever(*args, subset_path=paths["subset_path"]).retrieve_by_company_name(**kw))
+            ja = json.dumps(_canon(a), sort_keys=True, ensure_ascii=False)
+            jb = json.dumps(_canon(b), sort_keys=True, ensure_ascii=False)
+            if ja != jb:
+                failures.append({"case": i, "kind": kind, "kwargs": kw, "reference": ja[:400], "ours": jb[:400]})
+    return failures
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=100)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    failures = run(args.cases, args.seed, args.verbose)
+    print(json.dumps({"cases": args.cases, "seed": args.seed, "failures": failures}, ensure_ascii=False, indent=1))
+    raise SystemExit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()
