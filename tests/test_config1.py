@@ -1,0 +1,77 @@
+"""BASELINE config 1: the reference's own test set (token structure of the 64 report pages it quotes, its five
+questions, its subset.csv) — dense top-30, parent pages, vector + rerank, BM25 top-30 — against outputs of the
+REAL reference retrievers (tests/golden/config1.py).  CPU: this repo's retriever classes over oracle-backed
+index objects, records identical.  GPU: the CUDA index objects, scores within the 4-dp rounding band, same
+records.  The pages hold exact duplicates (the reference quotes some pages twice), so equal scores and their
+order are part of the check."""
+import json
+
+import pytest
+
+from tests import golden_util as gu
+from tests.golden import config1, stubs
+
+
+def load_golden():
+    with open(config1.GOLDEN, encoding="utf-8") as f:
+        return json.load(f)
+
+
+def canon(r):
+    return gu.canon_result(config1.compact(r)) if isinstance(r, dict) else gu.canon_records(config1.compact(r))
+
+
+def run_ours(R, paths):
+    return config1.run_all(R, paths, qwen_kw=dict(qwen=stubs.ScriptedQwen()), reranker_kw=dict(reranker=stubs.ScriptedReranker()))
+
+
+def test_fixture_shape():
+    fx = config1.load_fixture()
+    assert len(fx["reports"]) == 5 and sum(len(r["pages"]) for r in fx["reports"]) == 64
+    assert len(fx["questions"]) == 5
+    assert {q["company"] for q in fx["questions"]} == {r["company"] for r in fx["reports"]}
+    g = load_golden()
+    assert all(len(g[k]) == 5 for k in ("vector_chunks", "vector_pages", "rerank", "bm25_chunks", "bm25_pages"))
+    assert max(len(x["results"]) for x in g["vector_chunks"]) == config1.TOP_N
+
+
+def test_config1_cpu_identical_records(tmp_path):
+    import rag_challenge_2_b200.retrieval as R
+
+    mp = pytest.MonkeyPatch()
+    mp.setattr(R.flat_index, "read_index", lambda path, device=0: stubs.read_ixfi(path))
+    mp.setattr(R, "load_bm25_pickle", gu.oracle_bm25_loader)
+    R.clear_resident_cache()
+    try:
+        got = run_ours(R, config1.build(tmp_path))
+    finally:
+        mp.undo()
+        R.clear_resident_cache()
+    want = load_golden()
+    for key in want:
+        for qi, (g, w) in enumerate(zip(got[key], want[key])):
+            gj = json.dumps(canon(g), sort_keys=True, ensure_ascii=False)
+            wj = json.dumps(canon(w), sort_keys=True, ensure_ascii=False)
+            assert gj == wj, (key, qi)
+
+
+@pytest.mark.gpu
+def test_config1_gpu(tmp_path):
+    import rag_challenge_2_b200.retrieval as R
+    from tests.test_retrieval_gpu import assert_records_close
+
+    R.clear_resident_cache()
+    try:
+        got = run_ours(R, config1.build(tmp_path))
+    finally:
+        R.clear_resident_cache()
+    want = load_golden()
+    for qi in range(5):
+        for key in ("vector_chunks", "vector_pages"):
+            g, w = canon(got[key][qi]), canon(want[key][qi])
+            assert_records_close(g["results"], w["results"])
+            assert_records_close(g["initial_retrieval_results"], w["initial_retrieval_results"])
+        g, w = canon(got["rerank"][qi]), canon(want["rerank"][qi])
+        assert_records_close(g["results"], w["results"], sort_field="combined_score")
+        for key in ("bm25_chunks", "bm25_pages"):
+            assert_records_close(canon(got[key][qi]), canon(want[key][qi]))
