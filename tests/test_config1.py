@@ -55,6 +55,30 @@ def test_config1_cpu_identical_records(tmp_path):
             assert gj == wj, (key, qi)
 
 
+def _close_up_to_boundary_ties(got, want, sort_field="vector_similarity"):
+    """north_star's bar: identical top-k except ties within tolerance.  The test set holds chunks with the same
+    bag of words in a different order: their embeddings differ in the last bit and their scores by ~1e-8, so the
+    fp32 summation order decides which one is 30th.  Records may differ only at the cut, by records whose score
+    equals the cut-off score within the band; everything else is compared record by record.  Returns False when
+    such a swap happened (callers then skip what depends on the swapped record)."""
+    from collections import Counter
+
+    from tests.test_retrieval_gpu import BAND, assert_records_close, rec_key
+
+    gk, wk = Counter(map(rec_key, got)), Counter(map(rec_key, want))
+    if gk == wk:
+        assert_records_close(got, want, sort_field=sort_field)
+        return True
+    cut = min(r[sort_field] for r in want)
+    extra, missing = gk - wk, wk - gk
+    assert sum(extra.values()) == sum(missing.values()) and len(got) == len(want)
+    for r in [r for r in got if rec_key(r) in extra] + [r for r in want if rec_key(r) in missing]:
+        assert abs(r[sort_field] - cut) <= BAND, ("record swapped away from the cut", r[sort_field], cut)
+    assert_records_close([r for r in got if rec_key(r) not in extra], [r for r in want if rec_key(r) not in missing],
+                         sort_field=sort_field)
+    return False
+
+
 @pytest.mark.gpu
 def test_config1_gpu(tmp_path):
     import rag_challenge_2_b200.retrieval as R
@@ -69,9 +93,10 @@ def test_config1_gpu(tmp_path):
     for qi in range(5):
         for key in ("vector_chunks", "vector_pages"):
             g, w = canon(got[key][qi]), canon(want[key][qi])
-            assert_records_close(g["results"], w["results"])
-            assert_records_close(g["initial_retrieval_results"], w["initial_retrieval_results"])
+            _close_up_to_boundary_ties(g["results"], w["results"])
+            _close_up_to_boundary_ties(g["initial_retrieval_results"], w["initial_retrieval_results"])
         g, w = canon(got["rerank"][qi]), canon(want["rerank"][qi])
-        assert_records_close(g["results"], w["results"], sort_field="combined_score")
+        if _close_up_to_boundary_ties(g["initial_retrieval_results"], w["initial_retrieval_results"]):
+            assert_records_close(g["results"], w["results"], sort_field="combined_score")  # same sample -> same rerank
         for key in ("bm25_chunks", "bm25_pages"):
             assert_records_close(canon(got[key][qi]), canon(want[key][qi]))
