@@ -70,3 +70,51 @@ def test_cosine_matrix_kat():
     st = oracle.cosine_stats_ref(s)
     assert abs(st["avg_similarity"] - (-1 / 3)) < 1e-6 and st["max_similarity"] == np.float32(0.8)
     assert abs(st["min_similarity"] + 1) < 1e-6 and abs(st["median_similarity"] + 0.8) < 1e-6
+
+
+def test_oracle_cross_checked_with_sklearn_and_scipy():
+    """Independent formulations from libraries that ARE installed here (neither faiss nor rank_bm25 is): sklearn's
+    linear_kernel / cosine_similarity for the dense side, a scipy-sparse matrix form of the Okapi formula for BM25."""
+    import scipy.sparse as sp
+    from sklearn.feature_extraction.text import CountVectorizer
+    from sklearn.metrics.pairwise import cosine_similarity, linear_kernel
+
+    from rag_challenge_2_b200 import synth
+
+    rng = np.random.default_rng(5)
+    xb = rng.standard_normal((500, 64)).astype(np.float32)
+    xq = rng.standard_normal((7, 64)).astype(np.float32)
+    D, I = oracle.flat_ip_search_ref(xb, xq, 10)
+    S = linear_kernel(xq.astype(np.float64), xb.astype(np.float64))
+    order = np.argsort(-S, axis=1, kind="stable")[:, :10]
+    assert np.array_equal(I, order)
+    assert np.allclose(D, np.take_along_axis(S, order, 1), rtol=1e-5)
+
+    x = rng.standard_normal((60, 32)).astype(np.float32) * rng.uniform(0.5, 2, (60, 1)).astype(np.float32)
+    mine = oracle.cosine_matrix_ref(x)
+    theirs = cosine_similarity(x.astype(np.float64))
+    np.fill_diagonal(theirs, 1.0)
+    assert np.allclose(mine, np.clip(theirs, -1, 1), atol=2e-6)
+
+    docs = synth.token_corpus_np(300, vocab=400, seed=3)
+    bm = oracle.BM25OkapiRef(docs)
+    cv = CountVectorizer(analyzer=lambda d: d)
+    tf = cv.fit_transform(docs).astype(np.float64).tocsc()            # [n_docs, n_terms]
+    n = tf.shape[0]
+    dl = np.asarray(tf.sum(axis=1)).ravel()
+    df = np.diff(tf.indptr)
+    idf = np.log(n - df + 0.5) - np.log(df + 0.5)
+    idf[idf < 0] = 0.25 * idf.mean()                                  # epsilon floor with the mean over ALL terms' raw idf
+    k1, b = 1.5, 0.75
+    norm = k1 * (1 - b + b * dl / dl.mean())
+    for q in synth.token_queries_np(6, vocab=400, seed=4):
+        toks = [f"t{r}" for r in q]
+        want = np.zeros(n)
+        for t in toks:
+            j = cv.vocabulary_.get(t)
+            if j is None:
+                continue
+            col = np.asarray(tf[:, j].todense()).ravel()
+            want += idf[j] * col * (k1 + 1) / (col + norm)
+        assert np.allclose(bm.get_scores(toks), want, rtol=1e-12, atol=1e-12)
+    assert sp.issparse(tf)
