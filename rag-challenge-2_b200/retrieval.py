@@ -31,7 +31,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import flat_index
-from .bm25 import BM25Okapi, load_bm25_pickle
+from .bm25 import BM25Okapi, load_bm25_pickle  # noqa: F401  (BM25Okapi re-exported)
 
 _log = logging.getLogger(__name__)
 
