@@ -361,6 +361,89 @@ _MQ_METHODS = [
 # --------------------------------------------------------------------------------------------------
 # VectorRetriever (reference :431-1858)
 # --------------------------------------------------------------------------------------------------
+def _raise_reference_unbound_local(name):
+    """A hybrid_expansion task of the reference builds its result AFTER its `except` block and reads
+    `ssg_total_expanded` / `tri_total_expanded` there (src/retrieval.py:1461,1466); a task that failed before those
+    counters were first assigned (:1289, :1356 — e.g. a hit whose parent page is missing from the report JSON) ends
+    in UnboundLocalError, which `future.result()` (:1508) re-raises out of retrieve_by_company_name.  Kept as is
+    (behaviour visible to callers is preserved; tests/golden/differential.py --corrupt compares it).
+    The interpreter raises it, so the message is the running Python's own."""
+    if name == "ssg_total_expanded":
+        def task():
+            if name is None:
+                ssg_total_expanded = 0  # noqa: F841
+            return ssg_total_expanded  # noqa: F821
+    else:
+        def task():
+            if name is None:
+                tri_total_expanded = 0  # noqa: F841
+            return tri_total_expanded  # noqa: F821
+    task()
+
+
+class _RawHits:
+    """Result rows of one (query, report) basic search, not yet turned into hit tuples (reference :1142-1157)."""
+    __slots__ = ("sha1", "chunks", "pages", "scores", "ids", "parent_pages", "report_name")
+
+    def __init__(self, sha1, chunks, pages, scores, ids, parent_pages, report_name):
+        self.sha1, self.chunks, self.pages = sha1, chunks, pages
+        self.scores, self.ids, self.parent_pages, self.report_name = scores, ids, parent_pages, report_name
+
+    def __bool__(self):
+        return bool(self.ids)
+
+    def hits(self, query_text, log):
+        """The reference's hit tuples, in rank order; a failing hit ends the list, the hits before it are kept
+        (the per-task try / except of the reference, :1441-1442)."""
+        out = []
+        try:
+            for distance, index in zip(self.scores, self.ids):
+                out.append(VectorRetriever._hit(self.sha1, self.chunks, self.pages, index, round(distance * 1.0, 4),
+                                                "basic", self.parent_pages))
+        except Exception as e:  # noqa: BLE001
+            log(f"[ERROR] Vector search failed for query '{query_text[:60]}' in report {self.report_name}: {e}")
+        return out
+
+    def records(self, query_text, log):
+        """Final records of a question that has ONE query text and only basic hits: every aggregation key then
+        holds one query and one method, so both bonuses are exactly 1.0 and a record is its best hit
+        (fuse_similarity / _final_record with count == 1).  Chunk mode needs distinct, valid ids (anything else
+        goes through hits()); page mode merges the chunks of a page in first-hit order, as the aggregation does."""
+        sha1, chunks, pages = self.sha1, self.chunks, self.pages
+        out = []
+        try:
+            if not self.parent_pages:
+                for distance, index in zip(self.scores, self.ids):
+                    chunk = chunks[index]
+                    if chunk["page"] not in pages:  # a missing parent page fails the hit, as in the reference (:1145)
+                        raise KeyError(chunk["page"])
+                    r = round(distance * 1.0, 4)
+                    out.append({"vector_similarity": r, "max_original_similarity": r, "page": chunk["page"],
+                                "text": chunk["text"], "hit_count": 1, "retrieval_sources": ["basic"],
+                                "source_sha1": sha1, "query_sources": [query_text]})
+            else:
+                by_page = {}
+                for distance, index in zip(self.scores, self.ids):
+                    parent = pages[chunks[index]["page"]]
+                    r = round(distance * 1.0, 4)
+                    rec = by_page.get(parent["page"])
+                    if rec is None:
+                        rec = by_page[parent["page"]] = {
+                            "vector_similarity": r, "max_original_similarity": r, "page": parent["page"],
+                            "text": parent["text"], "hit_count": 1, "retrieval_sources": ["basic"],
+                            "source_sha1": sha1, "query_sources": [query_text]}
+                        out.append(rec)
+                    elif r > rec["vector_similarity"]:
+                        rec["vector_similarity"] = rec["max_original_similarity"] = r
+        except Exception as e:  # noqa: BLE001
+            log(f"[ERROR] Vector search failed for query '{query_text[:60]}' in report {self.report_name}: {e}")
+        return out
+
+    def direct_ok(self):
+        ids = self.ids
+        return self.parent_pages or (len(set(ids)) == len(ids) and (not ids or min(ids) >= 0))
+
+
 class VectorRetriever:
     def __init__(self, vector_db_dir: Path, documents_dir: Path, use_hyde: bool = True, use_multi_query: bool = True,
                  subset_path: Path = None, parallel_workers: int = 4,
@@ -751,18 +834,12 @@ class VectorRetriever:
                 self._safe_print(f"[ERROR] Vector search failed in report {report.get('name')}: {e}")
                 return [(q, []) for q in texts]
             # .tolist() yields the same Python floats / ints as float(d) / int(i) per element, without the numpy
-            # scalar round trips (23k hits for a 127-question batch over six databases)
+            # scalar round trips (23k hits for a 127-question batch over six databases).  The rows stay raw here:
+            # _finalize turns them into records directly when it can, into hit tuples otherwise (_RawHits).
             D_rows, I_rows = np.asarray(D).tolist(), np.asarray(I).tolist()
-            for qi, q in enumerate(texts):
-                hits = []
-                try:
-                    for distance, index in zip(D_rows[qi], I_rows[qi]):
-                        hits.append(self._hit(sha1, chunks, pages, index, round(distance * 1.0, 4),
-                                              "basic", return_parent_pages))
-                except Exception as e:  # noqa: BLE001 - partial hits are kept (:1441-1442)
-                    self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
-                out.append((q, hits))
-            return out
+            name = report.get("name")
+            return [(q, _RawHits(sha1, chunks, pages, D_rows[qi], I_rows[qi], return_parent_pages, name))
+                    for qi, q in enumerate(texts)]
 
         if getattr(self, "batched_expansion", True):
             try:
@@ -847,7 +924,8 @@ class VectorRetriever:
             except Exception as e:  # noqa: BLE001
                 failed = e
                 self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
-            per_q.append({"hits": hits, "basic": basic_results, "keys": basic_keys, "failed": failed})
+            per_q.append({"hits": hits, "basic": basic_results, "keys": basic_keys, "failed": failed,
+                          "unbound": "ssg_total_expanded" if failed is not None else None})
         gather(b[5] for st in per_q if st["failed"] is None for b in st["basic"][:20])
         for qi, st in enumerate(per_q):
             if st["failed"] is not None:
@@ -883,6 +961,8 @@ class VectorRetriever:
                             acc["tri_new_only"] += 1
             except Exception as e:  # noqa: BLE001 - the reference abandons the rest of this (query, report) task
                 st["failed"] = e
+                if source == "ssg":  # the triangulation counters were never assigned (:1356)
+                    st["unbound"] = "tri_total_expanded"
                 q = query_items[qi][0]
                 self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
         for qi, (q, _) in enumerate(query_items):
@@ -894,6 +974,8 @@ class VectorRetriever:
                               "in_basic_top50": acc["ssg_total"] - acc["ssg_new_only"]},
                 "triangulation_stats": {"total_expanded": acc["tri_total"], "new_only": acc["tri_new_only"],
                                         "in_basic_top50": acc["tri_total"] - acc["tri_new_only"]}}})
+            if st["unbound"]:
+                out[qi][1]["_reference_unbound_local"] = st["unbound"]
         return out
 
     def _query_similarity_vec(self, embedding_array, idx, fallback_score, row_of):
@@ -940,6 +1022,7 @@ class VectorRetriever:
                         sim = self._query_similarity(vector_db, emb, idx, score)
                         hits.append(self._hit(sha1, chunks, pages, idx, sim, retrieval_method, return_parent_pages))
                 else:  # hybrid_expansion: basic top-50, SSG from the top 10, triangulation from the top 20 (:1258-1418)
+                    unbound = "ssg_total_expanded"   # what the reference has not assigned yet if the task fails now
                     D, I = vector_db.search(x=emb, k=min(50, len(chunks)))
                     basic_keys = set()
                     for distance, index in zip(D[0], I[0]):
@@ -949,6 +1032,7 @@ class VectorRetriever:
                         basic_keys.add(h[0])
                         hits.append(h)
                     for limit, source in ((10, "ssg"), (20, "triangulation")):
+                        unbound = "tri_total_expanded" if source == "ssg" else None
                         for key, page_id, text, sim0, _sha, idx in basic_results[:limit]:
                             vec = self._get_vector_by_id(vector_db, idx)
                             if vec is None:
@@ -977,10 +1061,15 @@ class VectorRetriever:
                                     if is_new:
                                         tri_new.append(rec)
                                         tri_new_only += 1
+                    unbound = None
             except Exception as e:  # noqa: BLE001
                 self._safe_print(f"[ERROR] Vector search failed for query '{q[:60]}' in report {report.get('name')}: {e}")
+            else:
+                unbound = None
             if trav or retrieval_method == "hybrid_expansion":
                 result = {"hits": hits}
+                if retrieval_method == "hybrid_expansion" and unbound:
+                    result["_reference_unbound_local"] = unbound
                 if trav:
                     result["traversal_details"] = trav[0] if len(trav) == 1 else trav
                 if retrieval_method == "hybrid_expansion":
@@ -1141,13 +1230,20 @@ class VectorRetriever:
         algo = {"ssg_new_chunks": [], "triangulation_new_chunks": [], "basic_count": 0,
                 "ssg_stats": {"total_expanded": 0, "new_only": 0, "in_basic_top50": 0},
                 "triangulation_stats": {"total_expanded": 0, "new_only": 0, "in_basic_top50": 0}}
-        for per_query in per_report:
+        direct = self._direct_records(per_report)
+        for per_query in (() if direct is not None else per_report):
             if per_query is None:
                 continue
             for query_text, result in per_query:
                 if not result:
                     continue
+                if isinstance(result, _RawHits):
+                    result = result.hits(query_text, self._safe_print)
+                    if not result:
+                        continue
                 if isinstance(result, dict):
+                    if result.get("_reference_unbound_local"):
+                        _raise_reference_unbound_local(result["_reference_unbound_local"])
                     hits = result.get("hits", [])
                     if result.get("traversal_details"):
                         traversal_details.append(result["traversal_details"])
@@ -1163,7 +1259,7 @@ class VectorRetriever:
                     hits = result
                 self._aggregate(aggregated, hits, query_text)
 
-        final_results = [self._final_record(info) for info in aggregated.values()]
+        final_results = direct if direct is not None else [self._final_record(info) for info in aggregated.values()]
         final_results = sorted(final_results, key=lambda x: x["vector_similarity"], reverse=True)
         all_initial_results = final_results.copy()
         final_results = final_results[:top_n]
@@ -1187,6 +1283,24 @@ class VectorRetriever:
         return {"results": final_results, "timing": plan["timing"], "expansion_texts": plan["expansion_texts"],
                 "retrieval_details": retrieval_details, "initial_retrieval_results": all_initial_results,
                 "algorithm_contribution": algorithm_contribution}
+
+    def _direct_records(self, per_report):
+        """Records of a question whose hits need no cross-hit aggregation — one query text, basic searches only,
+        every report under its own sha1 (keys of different reports cannot collide) — built straight from the result
+        rows in aggregation order (reports, then ranks).  None when the general path is needed."""
+        raws = []
+        for per_query in per_report:
+            if per_query is None:
+                continue
+            if len(per_query) != 1 or not isinstance(per_query[0][1], _RawHits) or not per_query[0][1].direct_ok():
+                return None
+            raws.append(per_query[0])
+        if not raws or len({q for q, _ in raws}) != 1 or len({r.sha1 for _, r in raws}) != len(raws):
+            return None
+        out = []
+        for query_text, raw in raws:
+            out.extend(raw.records(query_text, self._safe_print))
+        return out
 
     # ---- aggregation and score fusion (reference :1552-1599, :1639-1716) -----------------------------------
     @staticmethod

@@ -193,6 +193,9 @@ class _LazyPages(dict):
         rec = self[page_no] = self._make(int(page_no))
         return rec
 
+    def __contains__(self, page_no):
+        return isinstance(page_no, int) and 1 <= page_no <= self._n
+
 
 def synthetic_year_report(name, company, n_chunks, vector_db, chunks_per_page=8):
     """A report dict {"name", "vector_db", "document"} in the chunked-report schema whose

@@ -75,6 +75,24 @@ def draw_bm25_case(rng):
                 selected_years=years)
 
 
+def corrupt(paths):
+    """Damage the fixture the way real data directories get damaged: a page record missing (hits on its chunks fail,
+    the hits before them are kept, :1145,1441), an index with more rows than the report has chunks (ids past the chunk
+    list), and one with fewer (faiss pads with id -1, which Python indexes as the LAST chunk — kept as is)."""
+    import json
+
+    docs, vec = paths["documents_dir"], paths["vector_db_dir"]
+    with open(docs / "J2023.json", encoding="utf-8") as f:
+        rep = json.load(f)
+    rep["content"]["pages"] = [p for p in rep["content"]["pages"] if p["page"] not in (3, 7)]
+    with open(docs / "J2023.json", "w", encoding="utf-8") as f:
+        json.dump(rep, f, ensure_ascii=False)
+    rows = stubs.read_ixfi(vec / "J2024.faiss").rows
+    corpus.write_ixfi(vec / "J2024.faiss", np.concatenate([rows, rows[:7] * np.float32(1.01)]))
+    rows = stubs.read_ixfi(vec / "J2025.faiss").rows
+    corpus.write_ixfi(vec / "J2025.faiss", rows[:9])
+
+
 def _call(fn):
     try:
         return {"ok": fn()}
@@ -88,7 +106,7 @@ def _canon(x):
     return x
 
 
-def run(n_cases, seed, verbose=False):
+def run(n_cases, seed, verbose=False, corrupted=False):
     make_golden.install_stubs()
     sys.path.insert(0, REF)
     import src.retrieval as ref
@@ -104,6 +122,8 @@ def run(n_cases, seed, verbose=False):
     sink = sys.stderr if verbose else io.StringIO()
     with tempfile.TemporaryDirectory() as tmp, redirect_stdout(sink):
         paths = corpus.build(tmp)
+        if corrupted:
+            corrupt(paths)
         common = dict(vector_db_dir=paths["vector_db_dir"], documents_dir=paths["documents_dir"],
                       subset_path=paths["subset_path"], parallel_workers=1)
         for i in range(n_cases):
@@ -138,8 +158,9 @@ def main():
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--corrupt", action="store_true", help="damaged fixture: missing pages, index / chunk count mismatches")
     args = ap.parse_args()
-    failures = run(args.cases, args.seed, args.verbose)
+    failures = run(args.cases, args.seed, args.verbose, args.corrupt)
     print(json.dumps({"cases": args.cases, "seed": args.seed, "failures": failures}, ensure_ascii=False, indent=1))
     raise SystemExit(1 if failures else 0)
 

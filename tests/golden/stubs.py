@@ -101,7 +101,10 @@ class OracleFlatIndex:
         return self.rows[i].copy()
 
     def reconstruct_batch(self, ids):
-        return self.rows[np.asarray(ids, dtype=np.int64)].copy()
+        ids = np.asarray(ids, dtype=np.int64)
+        if ids.size and (ids.min() < 0 or ids.max() >= self.ntotal):  # faiss raises; numpy would wrap -1 around
+            raise RuntimeError("id out of range")
+        return self.rows[ids].copy()
 
 
 def read_ixfi(path):

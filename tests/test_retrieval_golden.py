@@ -225,3 +225,40 @@ def test_graph_expansions_use_batched_calls(env):
     assert len(calls["search"]) <= n_reports * (1 + kw["max_hops"])
     assert max(calls["search"]) >= 20               # the walks advance together
     assert calls["reconstruct_batch"] <= n_reports * (2 + kw["max_hops"])
+
+
+def test_damaged_data_directory_behaves_like_the_reference(tmp_path):
+    """Portable restatement of what tests/golden/differential.py --corrupt establishes against the real reference:
+    a report whose JSON lost page records keeps the hits ranked before the first failing one (:1441-1442), and a
+    hybrid_expansion task that fails in its basic stage ends the call in the reference's UnboundLocalError
+    (:1289,1461)."""
+    import rag_challenge_2_b200.retrieval as R
+    from tests.golden import differential
+
+    paths = corpus.build(tmp_path)
+    differential.corrupt(paths)
+    mp = pytest.MonkeyPatch()
+    mp.setattr(R.flat_index, "read_index", lambda path, device=0: stubs.read_ixfi(path))
+    R.clear_resident_cache()
+    try:
+        r = R.VectorRetriever(paths["vector_db_dir"], paths["documents_dir"], subset_path=paths["subset_path"],
+                              parallel_workers=1, qwen=stubs.ScriptedQwen())
+        kw = dict(company_name=corpus.COMPANY, query=corpus.QUESTIONS[0], use_hyde=False, use_multi_query=False,
+                  selected_years=[2023])
+        full = len(r.all_dbs[[d["name"] for d in r.all_dbs].index("J2023")]["document"]["content"]["chunks"])
+        partial = 0
+        for question in corpus.QUESTIONS:
+            got = r.retrieve_by_company_name(top_n=full, **dict(kw, query=question))
+            assert len(got["results"]) < full                     # ranks after the first chunk of a lost page are gone
+            assert all(rec["page"] not in (3, 7) for rec in got["results"])
+            partial += bool(got["results"])
+        assert partial                                            # ... and the ranks before it are kept
+        with pytest.raises(UnboundLocalError, match="ssg_total_expanded"):
+            r.retrieve_by_company_name(top_n=10, retrieval_method="hybrid_expansion", **kw)
+        # more index rows than chunks (J2024): ids past the chunk list fail the hit; fewer (J2025): faiss pads with -1,
+        # which indexes the last chunk
+        r.retrieve_by_company_name(company_name=corpus.COMPANY, query=corpus.QUESTIONS[1], top_n=100, use_hyde=False,
+                                   use_multi_query=False, selected_years=[2024, 2025])
+    finally:
+        mp.undo()
+        R.clear_resident_cache()
