@@ -128,7 +128,26 @@ def run(n_cases, seed, verbose=False, corrupted=False):
                       subset_path=paths["subset_path"], parallel_workers=1)
         for i in range(n_cases):
             kind = ("vector", "vector", "vector", "hybrid", "bm25")[i % 5]
-            if kind == "vector":
+            if i % 10 == 7:
+                # this repo's retrieve_batch (one batched search per report for the whole question list) against the
+                # reference called once per question (its caller's loop, src/questions_processing.py:1104-1138)
+                kind = "batch"
+                kw = draw_vector_case(rng)
+                kw.pop("llm_reranking_sample_size", None)
+                kw.pop("query")
+                if kw["company_name"] == "nobody":
+                    kw["company_name"] = corpus.COMPANY
+                questions = [" ".join(str(w) for w in rng.choice(WORDS, size=int(rng.integers(1, 9))))
+                             for _ in range(int(rng.integers(2, 7)))]
+                a = _call(lambda: [ref.VectorRetriever(**common).retrieve_by_company_name(query=q, **kw) for q in questions])
+                b = _call(lambda: ours.VectorRetriever(**common, qwen=stubs.ScriptedQwen()).retrieve_batch(
+                    kw["company_name"], questions, **{k: v for k, v in kw.items() if k != "company_name"}))
+                for side in (a, b):
+                    if "ok" in side:
+                        side["ok"] = {"results": [gu.canon_result(r) for r in side["ok"]]}
+                        for r in side["ok"]["results"]:
+                            r["timing"] = None
+            elif kind == "vector":
                 kw = draw_vector_case(rng)
                 init = {}
                 if rng.random() < 0.2:  # constructor defaults that the call's defaults override or not (:808-822)
