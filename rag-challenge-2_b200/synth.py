@@ -194,7 +194,10 @@ class _LazyPages(dict):
         return rec
 
     def __contains__(self, page_no):
-        return isinstance(page_no, int) and 1 <= page_no <= self._n
+        try:
+            return 1 <= page_no.__index__() <= self._n   # Python and numpy integers alike
+        except AttributeError:
+            return False
 
 
 def synthetic_year_report(name, company, n_chunks, vector_db, chunks_per_page=8):

@@ -52,3 +52,7 @@ def test_synthetic_year_report_records():
     assert key == id(pages) and lookup[126]["text"] == "J2024 page 126" and lookup[126] is lookup[126]
     with pytest.raises(KeyError):
         lookup[127]
+    import numpy as np
+
+    assert 1 in lookup and 126 in lookup and np.int64(5) in lookup       # membership without materialising the record
+    assert 0 not in lookup and 127 not in lookup and "3" not in lookup and 3.5 not in lookup
