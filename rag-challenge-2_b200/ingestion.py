@@ -22,33 +22,42 @@ from . import flat_index
 from .bm25 import BM25Okapi
 
 
+def _report_chunks(reports_dir):
+    """(sha1_name, [chunk text, ...]) for every `*.json` under reports_dir, in directory order — the loop both
+    builders of the reference run (src/ingestion.py:32-44, :93-100)."""
+    for path in list(Path(reports_dir).glob("*.json")):
+        with open(path, "r", encoding="utf-8") as f:
+            report = json.load(f)
+        yield report["metainfo"]["sha1_name"], [c["text"] for c in report["content"]["chunks"]]
+
+
 class BM25Ingestor:
+    """`BM25Ingestor().process_reports(chunked_reports_dir, bm25_dbs_dir)`"""
+
     def __init__(self, device: int = 0):
         self.device = int(device)
 
     def create_bm25_index(self, chunks: List[str]) -> BM25Okapi:
-        """src/ingestion.py:19-22 — whitespace tokenisation, one document per chunk."""
-        tokenized_chunks = [chunk.split() for chunk in chunks]
-        return BM25Okapi(tokenized_chunks, device=self.device)
+        """One document per chunk, whitespace tokens (src/ingestion.py:19-22); postings land on `device`."""
+        return BM25Okapi([text.split() for text in chunks], device=self.device)
 
     def process_reports(self, all_reports_dir: Path, output_dir: Path):
-        """src/ingestion.py:24-49 — one `<sha1_name>.pkl` per report JSON."""
-        all_reports_dir, output_dir = Path(all_reports_dir), Path(output_dir)
-        output_dir.mkdir(parents=True, exist_ok=True)
-        all_report_paths = list(all_reports_dir.glob("*.json"))
-        for report_path in all_report_paths:
-            with open(report_path, "r", encoding="utf-8") as f:
-                report_data = json.load(f)
-            text_chunks = [chunk["text"] for chunk in report_data["content"]["chunks"]]
-            bm25_index = self.create_bm25_index(text_chunks)
-            sha1_name = report_data["metainfo"]["sha1_name"]
-            with open(output_dir / f"{sha1_name}.pkl", "wb") as f:
-                pickle.dump(bm25_index, f)
-            bm25_index.close()
-        print(f"Processed {len(all_report_paths)} reports")
+        """`<output_dir>/<sha1_name>.pkl` per report (src/ingestion.py:24-49)."""
+        out = Path(output_dir)
+        out.mkdir(parents=True, exist_ok=True)
+        n = 0
+        for sha1_name, texts in _report_chunks(all_reports_dir):
+            index = self.create_bm25_index(texts)
+            with open(out / f"{sha1_name}.pkl", "wb") as f:
+                pickle.dump(index, f)
+            index.close()   # the pickle carries the statistics; the device copy is rebuilt on load
+            n += 1
+        print(f"Processed {n} reports")
 
 
 class VectorDBIngestor:
+    """`VectorDBIngestor().process_reports(chunked_reports_dir, vector_dbs_dir)`"""
+
     BATCH = 100  # texts per embedding request (src/ingestion.py:71-72)
 
     def __init__(self, qwen=None, device: int = 0, retry_wait: float = 20.0):
@@ -56,56 +65,52 @@ class VectorDBIngestor:
             from .retrieval import _default_qwen
 
             qwen = _default_qwen(1024)
-        self.qwen = qwen
-        self.device = int(device)
-        self.retry_wait = float(retry_wait)
+        self.qwen, self.device, self.retry_wait = qwen, int(device), float(retry_wait)
+
+    def _request(self, text, model):
+        if isinstance(text, str):
+            if not text.strip():
+                raise ValueError("Input text cannot be an empty string.")
+            text = [text]
+        vectors = []
+        for lo in range(0, len(text), self.BATCH):
+            reply = self.qwen.get_embeddings(texts=text[lo: lo + self.BATCH], model=model)
+            vectors += [item["embedding"] for item in reply]
+        return vectors
 
     def _get_embeddings(self, text: Union[str, List[str]], model: str = "text-embedding-v4") -> List[List[float]]:
         """src/ingestion.py:57-76, including its `@retry(wait=wait_fixed(20), stop=stop_after_attempt(2))`: with
-        tenacity installed the same decorator is applied (a second failure raises tenacity.RetryError, as in the
-        reference); without it the call is retried once and the second exception propagates."""
+        tenacity installed the same policy is applied (a second failure raises tenacity.RetryError, as in the
+        reference); without it the request is repeated once and the second exception propagates."""
         try:
-            from tenacity import retry, stop_after_attempt, wait_fixed
+            import tenacity
         except ImportError:
             try:
-                return self._get_embeddings_once(text, model)
+                return self._request(text, model)
             except Exception:  # noqa: BLE001
                 time.sleep(self.retry_wait)
-                return self._get_embeddings_once(text, model)
-        return retry(wait=wait_fixed(self.retry_wait), stop=stop_after_attempt(2))(self._get_embeddings_once)(text, model)
-
-    def _get_embeddings_once(self, text, model):
-        if isinstance(text, str) and not text.strip():
-            raise ValueError("Input text cannot be an empty string.")
-        text_chunks = [text] if isinstance(text, str) else text
-        embeddings = []
-        for i in range(0, len(text_chunks), self.BATCH):
-            response = self.qwen.get_embeddings(texts=text_chunks[i: i + self.BATCH], model=model)
-            embeddings.extend([item["embedding"] for item in response])
-        return embeddings
+                return self._request(text, model)
+        policy = tenacity.retry(wait=tenacity.wait_fixed(self.retry_wait), stop=tenacity.stop_after_attempt(2))
+        return policy(self._request)(text, model)
 
     def _create_vector_db(self, embeddings: List[List[float]]):
-        """src/ingestion.py:78-84 — rows stored verbatim (no normalisation), inner-product metric."""
-        embeddings_array = np.array(embeddings, dtype=np.float32)
-        dimension = len(embeddings[0])
-        index = flat_index.IndexFlatIP(dimension, device=self.device)
-        index.add(embeddings_array)
+        """Rows stored verbatim, inner-product metric (src/ingestion.py:78-84)."""
+        rows = np.array(embeddings, dtype=np.float32)
+        index = flat_index.IndexFlatIP(len(embeddings[0]), device=self.device)
+        index.add(rows)
         return index
 
     def _process_report(self, report: dict):
-        text_chunks = [chunk["text"] for chunk in report["content"]["chunks"]]
-        return self._create_vector_db(self._get_embeddings(text_chunks))
+        return self._create_vector_db(self._get_embeddings([c["text"] for c in report["content"]["chunks"]]))
 
     def process_reports(self, all_reports_dir: Path, output_dir: Path):
-        """src/ingestion.py:92-102 — one `<sha1_name>.faiss` per report JSON."""
-        all_reports_dir, output_dir = Path(all_reports_dir), Path(output_dir)
-        all_report_paths = list(all_reports_dir.glob("*.json"))
-        output_dir.mkdir(parents=True, exist_ok=True)
-        for report_path in all_report_paths:
-            with open(report_path, "r", encoding="utf-8") as file:
-                report_data = json.load(file)
-            index = self._process_report(report_data)
-            sha1_name = report_data["metainfo"]["sha1_name"]
-            flat_index.write_index(index, str(output_dir / f"{sha1_name}.faiss"))
+        """`<output_dir>/<sha1_name>.faiss` per report (src/ingestion.py:92-102)."""
+        out = Path(output_dir)
+        out.mkdir(parents=True, exist_ok=True)
+        n = 0
+        for sha1_name, texts in _report_chunks(all_reports_dir):
+            index = self._create_vector_db(self._get_embeddings(texts))
+            flat_index.write_index(index, str(out / f"{sha1_name}.faiss"))
             index.close()
-        print(f"Processed {len(all_report_paths)} reports")
+            n += 1
+        print(f"Processed {n} reports")
