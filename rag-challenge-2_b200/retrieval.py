@@ -280,55 +280,92 @@ class BM25Retriever:
                 self._index_cache[key] = idx
         return idx
 
+    def _documents(self):
+        """Every report JSON of the documents directory (reference :199-206 re-reads and re-parses all of them on
+        every call); parsed documents and their page lookups stay cached until the file changes.  A file that does
+        not parse raises, as it does in the reference."""
+        out = []
+        for path in self.documents_dir.glob("*.json"):
+            st = path.stat()
+            key = ("doc", str(path), st.st_mtime_ns, st.st_size)
+            with self._lock:
+                entry = self._index_cache.get(key)
+            if entry is None:
+                with open(path, "r", encoding="utf-8") as f:
+                    doc = json.load(f)
+                entry = {"path": path, "document": doc, "sha1": doc["metainfo"]["sha1_name"],
+                         "pages": _page_text_lookup(doc["content"]["pages"])}
+                with self._lock:
+                    self._index_cache[key] = entry
+            out.append(entry)
+        return out
+
     def retrieve_by_company_name(self, company_name: str, query: str, top_n: int = 3,
                                  return_parent_pages: bool = False, selected_years: List[int] = None) -> List[Dict]:
-        all_documents = []
-        for path in self.documents_dir.glob("*.json"):
-            with open(path, "r", encoding="utf-8") as f:
-                doc = json.load(f)
-            all_documents.append({"path": path, "document": doc, "sha1": doc["metainfo"]["sha1_name"]})
-        all_reports = [{"document": d["document"], "name": d["sha1"]} for d in all_documents]
-        matching = route_reports_by_time(company_name=company_name, question=query, all_reports=all_reports,
-                                         fallback_strategy="all", selected_years=selected_years)
-        wanted = {rep["name"] for rep in matching}
-        matching_documents = [d for d in all_documents if d["sha1"] in wanted]
-        if not matching_documents:
-            raise ValueError(f"No report found with '{company_name}' company name.")
+        return self.retrieve_batch(company_name, [query], top_n=top_n, return_parent_pages=return_parent_pages,
+                                   selected_years=selected_years)[0]
 
-        tokenized_query = query.split()
-        results = []
-        for info in matching_documents:
+    def retrieve_batch(self, company_name: str, queries: List[str], top_n: int = 3, return_parent_pages: bool = False,
+                       selected_years=None) -> List[List[Dict]]:
+        """[retrieve_by_company_name(q) for q in queries] with ONE fused scoring + top-k launch per report for all the
+        questions routed to it (reference :194-295 scores one query at a time).  `selected_years` is one list for
+        the batch, or a list with one entry (list or None) per question."""
+        per_question_years = (isinstance(selected_years, (list, tuple)) and len(selected_years) == len(queries)
+                              and all(y is None or isinstance(y, (list, tuple)) for y in selected_years))
+        all_documents = self._documents()
+        all_reports = [{"document": d["document"], "name": d["sha1"]} for d in all_documents]
+        routed = []    # per question: the documents to search, in directory order
+        for i, query in enumerate(queries):
+            years = selected_years[i] if per_question_years else selected_years
+            matching = route_reports_by_time(company_name=company_name, question=query, all_reports=all_reports,
+                                             fallback_strategy="all", selected_years=years)
+            wanted = {rep["name"] for rep in matching}
+            docs = [d for d in all_documents if d["sha1"] in wanted]
+            if not docs:
+                raise ValueError(f"No report found with '{company_name}' company name.")
+            routed.append(docs)
+
+        tokenized = [query.split() for query in queries]
+        results = [[] for _ in queries]
+        for info in all_documents:
+            members = [qi for qi, docs in enumerate(routed) if any(d is info for d in docs)]
+            if not members:
+                continue
             document, sha1 = info["document"], info["sha1"]
             bm25_path = self.bm25_db_dir / f"{sha1}.pkl"
             if not bm25_path.exists():
-                print(f"[WARNING] BM25 index not found for {sha1}, skipping")
+                for _ in members:
+                    print(f"[WARNING] BM25 index not found for {sha1}, skipping")
                 continue
             bm25_index = self._bm25_index(bm25_path)
-            chunks = document["content"]["chunks"]
-            pages = _page_text_lookup(document["content"]["pages"])
+            chunks, pages = document["content"]["chunks"], info["pages"]
             actual_top_n = min(top_n, bm25_index.corpus_size)
             if actual_top_n <= 0:
                 continue
-            # get_scores + full stable sort (:262-265) fused on the GPU
-            scores, indices = bm25_index.topk([tokenized_query], actual_top_n)
-            seen_pages = set()
-            for score, index in zip(scores[0], indices[0]):
-                if index < 0:
-                    continue
-                score = round(float(score), 4)
-                chunk = chunks[int(index)]
-                if return_parent_pages:
-                    parent = pages[chunk["page"]]
-                    if parent["page"] in seen_pages:
+            # get_scores + full stable sort (:262-265) fused on the GPU, all routed questions in one launch
+            scores, indices = bm25_index.topk([tokenized[qi] for qi in members], actual_top_n)
+            scores, indices = np.asarray(scores).tolist(), np.asarray(indices).tolist()
+            for row, qi in enumerate(members):
+                out = results[qi]
+                seen_pages = set()
+                for score, index in zip(scores[row], indices[row]):
+                    if index < 0:
                         continue
-                    seen_pages.add(parent["page"])
-                    results.append({"vector_similarity": score, "page": parent["page"], "text": parent["text"],
+                    score = round(score, 4)
+                    chunk = chunks[index]
+                    if return_parent_pages:
+                        parent = pages[chunk["page"]]
+                        if parent["page"] in seen_pages:
+                            continue
+                        seen_pages.add(parent["page"])
+                        out.append({"vector_similarity": score, "page": parent["page"], "text": parent["text"],
                                     "source_sha1": sha1})
-                else:
-                    results.append({"vector_similarity": score, "page": chunk["page"], "text": chunk["text"],
+                    else:
+                        out.append({"vector_similarity": score, "page": chunk["page"], "text": chunk["text"],
                                     "source_sha1": sha1})
-        results.sort(key=lambda x: x["vector_similarity"], reverse=True)
-        return results[:top_n]
+        for out in results:
+            out.sort(key=lambda x: x["vector_similarity"], reverse=True)
+        return [out[:top_n] for out in results]
 
 
 # --------------------------------------------------------------------------------------------------

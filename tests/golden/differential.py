@@ -160,6 +160,21 @@ def run(n_cases, seed, verbose=False, corrupted=False):
                 a = _call(lambda: ref.HybridRetriever(**common).retrieve_by_company_name(**kw))
                 b = _call(lambda: ours.HybridRetriever(**common, qwen=stubs.ScriptedQwen(),
                                                        reranker=stubs.ScriptedReranker()).retrieve_by_company_name(**kw))
+            elif i % 10 == 9:
+                # BM25Retriever.retrieve_batch (one fused launch per report) against the reference called per question,
+                # with per-question year filters
+                kind = "bm25_batch"
+                kw = draw_bm25_case(rng)
+                n_q = int(rng.integers(2, 7))
+                questions = [" ".join(str(w) for w in rng.choice(WORDS, size=int(rng.integers(1, 10)))) for _ in range(n_q)]
+                years = [draw_bm25_case(rng)["selected_years"] for _ in range(n_q)]
+                args = (paths["bm25_db_dir"], paths["bm25_documents_dir"])
+                a = _call(lambda: {"per_question": [ref.BM25Retriever(*args, subset_path=paths["subset_path"]).retrieve_by_company_name(
+                    kw["company_name"], q, top_n=kw["top_n"], return_parent_pages=kw["return_parent_pages"], selected_years=y)
+                    for q, y in zip(questions, years)]})
+                b = _call(lambda: {"per_question": ours.BM25Retriever(*args, subset_path=paths["subset_path"]).retrieve_batch(
+                    kw["company_name"], questions, top_n=kw["top_n"], return_parent_pages=kw["return_parent_pages"],
+                    selected_years=years)})
             else:
                 kw = draw_bm25_case(rng)
                 args = (paths["bm25_db_dir"], paths["bm25_documents_dir"])

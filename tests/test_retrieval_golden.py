@@ -262,3 +262,35 @@ def test_damaged_data_directory_behaves_like_the_reference(tmp_path):
     finally:
         mp.undo()
         R.clear_resident_cache()
+
+
+def test_bm25_retriever_batch_and_document_cache(env, tmp_path):
+    """retrieve_batch == per-question calls (per-question year filters); parsed report JSONs are cached per file
+    version: an edited report is re-read (the reference re-reads every file on every call, :199-206)."""
+    import json as _json
+    import os
+    import shutil
+
+    R, paths, _ = env
+    docs = tmp_path / "docs"
+    shutil.copytree(paths["bm25_documents_dir"], docs)
+    b = R.BM25Retriever(paths["bm25_db_dir"], docs, subset_path=paths["subset_path"])
+    questions = ["gross margin revenue 2024", "cash flow dividend the company", "zzzz", ""]
+    years = [None, [2023, 2025], [2024], None]
+    got = b.retrieve_batch(corpus.COMPANY, questions, top_n=6, return_parent_pages=True, selected_years=years)
+    want = [b.retrieve_by_company_name(corpus.COMPANY, q, top_n=6, return_parent_pages=True, selected_years=y)
+            for q, y in zip(questions, years)]
+    assert got == want and len(got) == 4 and got[0]
+    first = b.retrieve_by_company_name(corpus.COMPANY, questions[0], top_n=3, selected_years=[2024])
+    path = docs / "J2024.json"
+    with open(path, encoding="utf-8") as f:
+        rep = _json.load(f)
+    for c in rep["content"]["chunks"]:
+        c["text"] = "EDITED " + c["text"]
+    with open(path, "w", encoding="utf-8") as f:
+        _json.dump(rep, f, ensure_ascii=False)
+    os.utime(path, ns=(path.stat().st_atime_ns, path.stat().st_mtime_ns + 1_000_000_000))
+    again = b.retrieve_by_company_name(corpus.COMPANY, questions[0], top_n=3, selected_years=[2024])
+    assert [r["text"] for r in again] == ["EDITED " + r["text"] for r in first]
+    with pytest.raises(ValueError, match="No report found with 'nobody' company name."):
+        b.retrieve_batch("nobody", ["q"])
