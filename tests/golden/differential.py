@@ -102,7 +102,8 @@ def _call(fn):
 
 def _canon(x):
     if "ok" in x:
-        return {"ok": gu.canon_result(x["ok"]) if isinstance(x["ok"], dict) else gu.canon_records(gu.strip_unpinned(x["ok"]))}
+        return {"ok": gu.canon_result(x["ok"]) if isinstance(x["ok"], dict) else gu.canon_records(gu.strip_unpinned(x["ok"])),
+                "progress": x.get("progress")}
     return x
 
 
@@ -153,13 +154,21 @@ def run(n_cases, seed, verbose=False, corrupted=False):
                 if rng.random() < 0.2:  # constructor defaults that the call's defaults override or not (:808-822)
                     init = dict(retrieval_method=kw.pop("retrieval_method"), max_hops=kw.pop("max_hops"),
                                 neighbor_k=kw.pop("neighbor_k"))
-                a = _call(lambda: ref.VectorRetriever(**common, **init).retrieve_by_company_name(**kw))
-                b = _call(lambda: ours.VectorRetriever(**common, qwen=stubs.ScriptedQwen(), **init).retrieve_by_company_name(**kw))
+                log_a, log_b = [], []   # the progress callback's (stage, percent) sequence is part of the comparison
+                a = _call(lambda: ref.VectorRetriever(**common, **init).retrieve_by_company_name(
+                    progress_callback=lambda stage, pct: log_a.append([stage, pct]), **kw))
+                b = _call(lambda: ours.VectorRetriever(**common, qwen=stubs.ScriptedQwen(), **init).retrieve_by_company_name(
+                    progress_callback=lambda stage, pct: log_b.append([stage, pct]), **kw))
+                a["progress"], b["progress"] = log_a, log_b
             elif kind == "hybrid":
                 kw = draw_hybrid_case(rng)
-                a = _call(lambda: ref.HybridRetriever(**common).retrieve_by_company_name(**kw))
+                log_a, log_b = [], []
+                a = _call(lambda: ref.HybridRetriever(**common).retrieve_by_company_name(
+                    progress_callback=lambda stage, pct: log_a.append([stage, pct]), **kw))
                 b = _call(lambda: ours.HybridRetriever(**common, qwen=stubs.ScriptedQwen(),
-                                                       reranker=stubs.ScriptedReranker()).retrieve_by_company_name(**kw))
+                                                       reranker=stubs.ScriptedReranker()).retrieve_by_company_name(
+                    progress_callback=lambda stage, pct: log_b.append([stage, pct]), **kw))
+                a["progress"], b["progress"] = log_a, log_b
             elif i % 10 == 9:
                 # BM25Retriever.retrieve_batch (one fused launch per report) against the reference called per question,
                 # with per-question year filters
