@@ -1428,12 +1428,30 @@ class HybridRetriever:
                                  progress_callback=None, selected_years: List[int] = None,
                                  multi_query_config: Optional[Dict[str, bool]] = None, retrieval_method: str = "basic",
                                  max_hops: int = 4, neighbor_k: int = 30):
-        timing_info = {"hyde_expansion": 0.0, "multi_query_expansion": 0.0, "vector_search": 0.0, "llm_reranking": 0.0}
         vec = self.vector_retriever.retrieve_by_company_name(
             company_name=company_name, query=query, top_n=llm_reranking_sample_size,
             return_parent_pages=return_parent_pages, use_hyde=use_hyde, use_multi_query=use_multi_query,
             progress_callback=progress_callback, selected_years=selected_years, multi_query_config=multi_query_config,
             retrieval_method=retrieval_method, max_hops=max_hops, neighbor_k=neighbor_k)
+        return self._rerank(query, vec, documents_batch_size, top_n, llm_weight, progress_callback)
+
+    def retrieve_batch(self, company_name: str, queries: List[str], llm_reranking_sample_size: int = 28,
+                       documents_batch_size: int = 2, top_n: int = 6, llm_weight: float = 0.7,
+                       return_parent_pages: bool = False, use_hyde: bool = None, use_multi_query: bool = None,
+                       selected_years=None, multi_query_config: Optional[Dict[str, bool]] = None,
+                       retrieval_method: str = "basic", max_hops: int = 4, neighbor_k: int = 30) -> List[Dict]:
+        """[retrieve_by_company_name(q) for q in queries]: the vector stage of the whole question list runs as
+        VectorRetriever.retrieve_batch (one batched search per report), the reranker then scores each question's sample."""
+        vecs = self.vector_retriever.retrieve_batch(
+            company_name, queries, top_n=llm_reranking_sample_size, return_parent_pages=return_parent_pages,
+            use_hyde=use_hyde, use_multi_query=use_multi_query, selected_years=selected_years,
+            multi_query_config=multi_query_config, retrieval_method=retrieval_method, max_hops=max_hops,
+            neighbor_k=neighbor_k)
+        return [self._rerank(q, vec, documents_batch_size, top_n, llm_weight, None) for q, vec in zip(queries, vecs)]
+
+    def _rerank(self, query, vec, documents_batch_size, top_n, llm_weight, progress_callback):
+        """Reference :387-429 — rerank the vector stage's sample, keep the first top_n."""
+        timing_info = {"hyde_expansion": 0.0, "multi_query_expansion": 0.0, "vector_search": 0.0, "llm_reranking": 0.0}
         expansion_texts, algorithm_contribution = {}, None
         if isinstance(vec, dict) and "timing" in vec:
             timing_info.update(vec["timing"])

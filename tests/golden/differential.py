@@ -148,6 +148,23 @@ def run(n_cases, seed, verbose=False, corrupted=False):
                         side["ok"] = {"results": [gu.canon_result(r) for r in side["ok"]]}
                         for r in side["ok"]["results"]:
                             r["timing"] = None
+            elif i % 20 == 3:
+                # HybridRetriever.retrieve_batch against the reference called per question
+                kind = "hybrid_batch"
+                kw = draw_hybrid_case(rng)
+                kw.pop("query")
+                if kw["company_name"] == "nobody":
+                    kw["company_name"] = corpus.COMPANY
+                questions = [" ".join(str(w) for w in rng.choice(WORDS, size=int(rng.integers(1, 9))))
+                             for _ in range(int(rng.integers(2, 5)))]
+                a = _call(lambda: [ref.HybridRetriever(**common).retrieve_by_company_name(query=q, **kw) for q in questions])
+                b = _call(lambda: ours.HybridRetriever(**common, qwen=stubs.ScriptedQwen(), reranker=stubs.ScriptedReranker())
+                          .retrieve_batch(kw["company_name"], questions, **{k: v for k, v in kw.items() if k != "company_name"}))
+                for side in (a, b):
+                    if "ok" in side:
+                        side["ok"] = {"per_question": [gu.canon_result(r) for r in side["ok"]]}
+                        for r in side["ok"]["per_question"]:
+                            r["timing"] = None
             elif kind == "vector":
                 kw = draw_vector_case(rng)
                 init = {}
