@@ -127,8 +127,11 @@ def run(n_cases, seed, verbose=False, corrupted=False):
             corrupt(paths)
         common = dict(vector_db_dir=paths["vector_db_dir"], documents_dir=paths["documents_dir"],
                       subset_path=paths["subset_path"], parallel_workers=1)
+        base_common = dict(common)
         for i in range(n_cases):
             kind = ("vector", "vector", "vector", "hybrid", "bm25")[i % 5]
+            # year routing with and without subset.csv (metainfo.year, then the sha1_name pattern, then the csv: :101-129)
+            common = dict(base_common, subset_path=(paths["subset_path"] if rng.random() < 0.75 else None))
             if i % 10 == 7:
                 # this repo's retrieve_batch (one batched search per report for the whole question list) against the
                 # reference called once per question (its caller's loop, src/questions_processing.py:1104-1138)
