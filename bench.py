@@ -148,14 +148,36 @@ def cpu_baseline(args, steps, rows_sample=None, verbose=False):
     docs = synth.token_corpus_np(n_docs, vocab=args.vocab, seed=4242)
     bm = oracle.BM25OkapiRef(docs)
     queries = [[f"t{r}" for r in q] for q in synth.token_queries_np(max(steps, 1), vocab=args.vocab, seed=4243)]
+    # The real third-party packages, if this machine has them (this image does not: SURVEY 8c): the reference arm
+    # then times faiss / rank_bm25 themselves and reports how far the port's answers are from theirs.
+    real, kind, deviation = {}, "port", None
+    try:
+        import faiss  # noqa: F401
+        import rank_bm25  # noqa: F401
+
+        fx = faiss.IndexFlatIP(args.dim)
+        fx.add(rows_sample)
+        real = {"flat": fx, "bm25": rank_bm25.BM25Okapi(docs)}
+        Df, If = fx.search(xq[:1], args.k)
+        Do, Io = oracle.flat_ip_search_ref(rows_sample, xq[:1], args.k)
+        so, sr = bm.get_scores(queries[0]), real["bm25"].get_scores(queries[0])
+        deviation = {"dense_ids_equal": bool(np.array_equal(If, Io)),
+                     "dense_score_max_rel": float(np.max(np.abs(Df - Do) / np.maximum(np.abs(Do), 1e-30))),
+                     "bm25_score_max_abs": float(np.max(np.abs(so - sr)))}
+        kind = "reference"
+    except Exception:  # noqa: BLE001 - not installed (or unusable): the port is the baseline
+        real = {}
     # one untimed pass (BLAS thread pool, page faults)
     oracle.flat_ip_search_ref(rows_sample, xq[:1], args.k)
     t_dense = t_bm = 0.0
     for i in range(steps):
         t0 = time.perf_counter()
-        D, I = oracle.flat_ip_search_ref(rows_sample, xq[i: i + 1], args.k)
+        if real:
+            D, I = real["flat"].search(xq[i: i + 1], args.k)
+        else:
+            D, I = oracle.flat_ip_search_ref(rows_sample, xq[i: i + 1], args.k)
         t1 = time.perf_counter()
-        sc = bm.get_scores(queries[i])
+        sc = (real["bm25"] if real else bm).get_scores(queries[i])
         top = oracle.bm25_topn_ref(sc, args.k)
         S = np.array([[sc[j] for j in top]])
         t2 = time.perf_counter()
@@ -166,10 +188,12 @@ def cpu_baseline(args, steps, rows_sample=None, verbose=False):
     t_bm /= max(steps, 1)
     per_query = t_dense * (args.rows / n_dense) + t_bm * (args.rows / n_docs)
     return {
-        "value": 1.0 / per_query, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        "value": 1.0 / per_query, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "port_vs_packages": deviation,
         "threads": {"dense_scan_openblas": os.cpu_count(), "bm25_python_loops": 1},
-        "sample": (f"oracle port (numpy/OpenBLAS fp32 scan on all cores + partial sort; rank_bm25-style per-document dict loops + "
-                   f"Python stable sort): dense {n_dense} x {args.dim} rows {t_dense * 1e3:.1f} ms/query, BM25 {n_docs} docs "
+        "sample": (("faiss-cpu IndexFlatIP.search + rank_bm25.BM25Okapi.get_scores (the packages themselves, installed on this "
+                    "machine) + Python stable sort" if real else
+                    "oracle port (numpy/OpenBLAS fp32 scan on all cores + partial sort; rank_bm25-style per-document dict loops + "
+                    "Python stable sort)") + f": dense {n_dense} x {args.dim} rows {t_dense * 1e3:.1f} ms/query, BM25 {n_docs} docs "
                    f"{t_bm * 1e3:.1f} ms/query, both scaled linearly to {args.rows} chunks (extrapolated); {steps} queries"),
         "t_dense_ms_sample": t_dense * 1e3, "t_bm25_ms_sample": t_bm * 1e3,
     }
@@ -188,7 +212,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.nq / cb["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "threads")},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "threads", "port_vs_packages")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "timed_steps": steps,
     }
@@ -428,7 +452,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             n_s = min(args.cpu_rows, hi - lo)
             cb = cpu_baseline(args, 10, rows_sample=rows[:n_s].cpu().numpy())
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "threads")}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "threads", "port_vs_packages")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

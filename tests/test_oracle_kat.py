@@ -2,6 +2,7 @@
 import math
 
 import numpy as np
+import pytest
 
 import oracle
 from oracle.bm25 import bm25_scores_csr_ref
@@ -118,3 +119,46 @@ def test_oracle_cross_checked_with_sklearn_and_scipy():
             want += idf[j] * col * (k1 + 1) / (col + norm)
         assert np.allclose(bm.get_scores(toks), want, rtol=1e-12, atol=1e-12)
     assert sp.issparse(tf)
+
+
+def test_oracle_against_the_real_packages_when_installed():
+    """faiss-cpu / rank-bm25 are not installable in this image; wherever they are, this pins the
+    restatement to them directly."""
+    from rag_challenge_2_b200 import synth
+
+    checked = 0
+    try:
+        import faiss
+    except ImportError:
+        faiss = None
+    if faiss is not None:
+        rng = np.random.default_rng(11)
+        xb = rng.standard_normal((2000, 64)).astype(np.float32)
+        xb[100] = xb[7]                                               # an exact tie
+        xq = np.concatenate([rng.standard_normal((5, 64)).astype(np.float32), xb[7:8]])
+        index = faiss.IndexFlatIP(64)
+        index.add(xb)
+        for k in (1, 10, 30):
+            D, I = index.search(xq, k)
+            oracle.assert_topk_equivalent(D, I, oracle.flat_ip_scores_ref(xb, xq, np.float64), k, what=f"faiss k={k}")
+            Do, Io = oracle.flat_ip_search_ref(xb, xq, k)
+            assert np.array_equal(I[-1, :2] if k > 1 else I[-1, :1], Io[-1, :2] if k > 1 else Io[-1, :1])   # tie order
+        small = faiss.IndexFlatIP(64)
+        small.add(xb[:2])
+        D, I = small.search(xq[:1], 5)
+        assert list(I[0, 2:]) == [-1, -1, -1] and np.all(D[0, 2:] == oracle.flat_ip.NEG)   # padding
+        checked += 1
+    try:
+        import rank_bm25
+    except ImportError:
+        rank_bm25 = None
+    if rank_bm25 is not None:
+        docs = synth.token_corpus_np(400, vocab=300, seed=12)
+        real, mine = rank_bm25.BM25Okapi(docs), oracle.BM25OkapiRef(docs)
+        assert real.avgdl == mine.avgdl and real.idf == mine.idf and real.average_idf == mine.average_idf
+        for q in synth.token_queries_np(8, vocab=300, seed=13):
+            toks = [f"t{r}" for r in q] + ["unknown-token"]
+            assert np.array_equal(real.get_scores(toks), mine.get_scores(toks))
+        checked += 1
+    if not checked:
+        pytest.skip("neither faiss nor rank_bm25 is installed here")
