@@ -93,6 +93,29 @@ def corrupt(paths):
     corpus.write_ixfi(vec / "J2025.faiss", rows[:9])
 
 
+def _first_differences(x, y, path="", out=None, limit=6):
+    out = [] if out is None else out
+    if len(out) >= limit:
+        return out
+    if type(x) is not type(y):
+        out.append(f"{path}: {type(x).__name__} vs {type(y).__name__}")
+    elif isinstance(x, dict):
+        for k in sorted(set(x) | set(y)):
+            if k not in x or k not in y:
+                out.append(f"{path}/{k}: only on one side")
+            else:
+                _first_differences(x[k], y[k], f"{path}/{k}", out, limit)
+    elif isinstance(x, list):
+        if len(x) != len(y):
+            out.append(f"{path}: length {len(x)} vs {len(y)}")
+        else:
+            for j, (p, q) in enumerate(zip(x, y)):
+                _first_differences(p, q, f"{path}[{j}]", out, limit)
+    elif x != y:
+        out.append(f"{path}: {x!r:.80} vs {y!r:.80}")
+    return out
+
+
 def _call(fn):
     try:
         return {"ok": fn()}
@@ -128,7 +151,16 @@ def run(n_cases, seed, verbose=False, corrupted=False):
         common = dict(vector_db_dir=paths["vector_db_dir"], documents_dir=paths["documents_dir"],
                       subset_path=paths["subset_path"], parallel_workers=1)
         base_common = dict(common)
-        for i in range(n_cases):
+        attempts = {}
+        i = -1
+        while i + 1 < n_cases:
+            i += 1
+            # The reference collects its per-(report, query) tasks with as_completed (:1506), which yields futures that
+            # are already finished in set order: even with one worker the aggregation order — and with it the order of
+            # equal scores and of a record's query_sources — is occasionally different from the submission order.  A
+            # mismatch is therefore replayed (same parameters: the generator state is restored) and counts only if it
+            # persists three times; a real divergence always does.
+            state = rng.bit_generator.state
             kind = ("vector", "vector", "vector", "hybrid", "bm25")[i % 5]
             # year routing with and without subset.csv (metainfo.year, then the sha1_name pattern, then the csv: :101-129)
             common = dict(base_common, subset_path=(paths["subset_path"] if rng.random() < 0.75 else None))
@@ -209,10 +241,19 @@ def run(n_cases, seed, verbose=False, corrupted=False):
                 args = (paths["bm25_db_dir"], paths["bm25_documents_dir"])
                 a = _call(lambda: ref.BM25Retriever(*args, subset_path=paths["subset_path"]).retrieve_by_company_name(**kw))
                 b = _call(lambda: ours.BM25Retriever(*args, subset_path=paths["subset_path"]).retrieve_by_company_name(**kw))
-            ja = json.dumps(_canon(a), sort_keys=True, ensure_ascii=False)
-            jb = json.dumps(_canon(b), sort_keys=True, ensure_ascii=False)
+            ca, cb = _canon(a), _canon(b)
+            ja = json.dumps(ca, sort_keys=True, ensure_ascii=False)
+            jb = json.dumps(cb, sort_keys=True, ensure_ascii=False)
+            if ja != jb and attempts.get(i, 0) < 2:
+                attempts[i] = attempts.get(i, 0) + 1
+                rng.bit_generator.state = state
+                i -= 1
+                continue
             if ja != jb:
-                failures.append({"case": i, "kind": kind, "kwargs": kw, "reference": ja[:400], "ours": jb[:400]})
+                failures.append({"case": i, "kind": kind, "kwargs": kw, "attempts": attempts.get(i, 0) + 1,
+                                 "questions": questions if kind.endswith("batch") else None,
+                                 "first_differences": _first_differences(ca, cb), "reference": ja[:400], "ours": jb[:400]})
+    run.replayed = sorted(attempts)
     return failures
 
 
@@ -224,7 +265,8 @@ def main():
     ap.add_argument("--corrupt", action="store_true", help="damaged fixture: missing pages, index / chunk count mismatches")
     args = ap.parse_args()
     failures = run(args.cases, args.seed, args.verbose, args.corrupt)
-    print(json.dumps({"cases": args.cases, "seed": args.seed, "failures": failures}, ensure_ascii=False, indent=1))
+    print(json.dumps({"cases": args.cases, "seed": args.seed, "replayed_cases": run.replayed, "failures": failures},
+                     ensure_ascii=False, indent=1))
     raise SystemExit(1 if failures else 0)
 
 
