@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--pool", type=int, default=64, help="distinct queries cycled through")
     ap.add_argument("--cpu-rows", type=int, default=1_000_000, help="rows of the CPU-baseline dense sample")
     ap.add_argument("--cpu-docs", type=int, default=50_000, help="documents of the CPU-baseline BM25 sample")
+    ap.add_argument("--bm25-weight-bits", type=int, default=32, choices=[32, 64],
+                    help="stored BM25 weight width: 32 = 8 B/posting (scores within 1e-6 of rank_bm25), 64 = bit-exact")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run BM25 after the scan instead of beside it")
     ap.add_argument("--overlap", default="pdl", choices=["pdl", "streams"],
@@ -252,8 +254,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- build this rank's shard in HBM ------------------------------------------------------------
-    align = max(synth.ROW_BLOCK, synth.DOC_BLOCK)
-    bounds = hybrid.shard_bounds(args.rows, world, align)
+    bounds = hybrid.shard_bounds(args.rows, world, 128)   # balanced to 128 rows: the largest shard sets the pace
     lo, hi = bounds[rank], bounds[rank + 1]
     rows = synth.dense_rows_torch(lo, hi, args.dim, dev)
     flat = pkg.FlatIPIndex.from_device_tensor(rows)
@@ -266,7 +267,7 @@ def run_b200(args):
     idf, _ = synth.bm25_idf_from_df(df.cpu().numpy(), args.rows)
     avgdl = float(tot.item()) / args.rows
     bm25 = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"],
-                                   torch.from_numpy(idf).to(dev), avgdl, device=local_rank)
+                                   torch.from_numpy(idf).to(dev), avgdl, device=local_rank, weight_bits=args.bm25_weight_bits)
     n_post, wbits = bm25.n_postings()
     del post
     torch.cuda.empty_cache()

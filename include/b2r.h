@@ -108,14 +108,15 @@ int b2r_topk_merge_host(const float* D_lists, const int64_t* I_lists, int n_list
  * the token counts.  idf[n_terms] (float64) and avgdl are the *corpus-global* statistics
  * computed by the caller exactly as rank_bm25 does (epsilon floor included), so that a document
  * shard scores identically to the unsharded corpus.  The library precomputes the per-posting
- * weight tf*(k1+1)/(tf+k1*(1-b+b*dl/avgdl)) in float64 and stores it as float32. */
+ * weight tf*(k1+1)/(tf+k1*(1-b+b*dl/avgdl)) in float64 and keeps it in float64 (12 B / posting):
+ * scores are bit-identical to rank_bm25's float64 arithmetic. */
 int b2r_bm25_create(int64_t n_docs, int32_t n_terms, const int64_t* indptr, const int32_t* doc_ids,
                     const int32_t* tf, const int32_t* doc_len, double avgdl, const double* idf,
                     double k1, double b, int device, b2r_bm25** out);
 /* Extended form: inputs_on_device != 0 takes all array arguments as device pointers (corpora built
- * in HBM; the arrays are only read during the call); weight_bits = 32 stores float32 weights
- * (8 B / posting), 64 keeps float64 weights (12 B / posting) — scores are then bit-identical to
- * rank_bm25's float64 arithmetic. */
+ * in HBM; the arrays are only read during the call); weight_bits = 64 keeps float64 weights
+ * (12 B / posting, bit-identical to rank_bm25; what b2r_bm25_create does), 32 is the explicit opt-in
+ * that rounds the stored weights to float32 (8 B / posting; scores within 1e-6 relative). */
 int b2r_bm25_create_ex(int64_t n_docs, int32_t n_terms, const int64_t* indptr, const int32_t* doc_ids,
                        const int32_t* tf, const int32_t* doc_len, double avgdl, const double* idf,
                        double k1, double b, int device, int inputs_on_device, int weight_bits,
@@ -165,11 +166,15 @@ int b2r_hybrid_fuse_dev(const float* D, const int64_t* I, const double* S, const
  * (peer_bufs[world], each b2r_hybrid_exchange_bytes(nq_max, k_max, world) bytes, zero-initialised,
  * mapped for peer access); `step` (>= 1) must increase by one per call, in lockstep on all ranks.
  * The kernel stores the hits into every rank's buffer, publishes system-scope flags, waits for the
- * peers' flags and merges + fuses; all ranks obtain the same F/O[nq,k]. */
+ * peers' flags and merges + fuses; all ranks obtain the same F/O[nq,k].
+ * The wait is bounded (tunable "exchange.timeout_ms", default 10 s): if a peer never publishes this step
+ * (it failed before launching, or counts steps differently) the kernel stores 1 + that peer's rank into
+ * *status (a zero-initialised device-visible word the caller owns and checks after synchronising; the
+ * query's outputs are then padding) — or traps, surfacing as a CUDA error, when status is NULL. */
 size_t b2r_hybrid_exchange_bytes(int nq_max, int k_max, int world);
 int b2r_hybrid_exchange_fuse_dev(const float* D, const int64_t* I, const double* S, const int64_t* J,
                                  int nq, int k, void* const* peer_bufs, int rank, int world, int nq_max,
-                                 int k_max, uint32_t step, float* F, int64_t* O, void* stream);
+                                 int k_max, uint32_t step, float* F, int64_t* O, uint32_t* status, void* stream);
 
 /* ---- one hybrid step behind one call (host buffers) ------------------------------------------- */
 /* What the drop-in does per question on one index: q[nq,d] + token ids in, fused top-k out.  Replaces the

@@ -50,6 +50,7 @@ static std::map<std::string, int>& tunables() {
       {"bm25.block_docs", 0},      // documents per CTA in the doc-block BM25 kernel (bm25.v1)
       {"bm25.debug_skip", 0},      // perf experiments (wrong results): 1 no select, 2 no accumulate, 4 no merge
       {"bm25.no_skip", 0},         // 1: streaming kernel ignores the block index (binary searches in the producer)
+      {"exchange.timeout_ms", 0},  // bound on the exchange kernel's wait for its peers (default 10000 ms)
       {"bm25.v1", 0},              // 1: use the doc-block kernel (binary searches, per-token barriers) instead of the streaming one
   };
   return t;

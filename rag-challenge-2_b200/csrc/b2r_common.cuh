@@ -36,6 +36,10 @@ int& launch_counter();  // thread-local: kernels enqueued by the last search on 
   } while (0)
 
 int tunable(const char* key);  // current value of a tunable (see b2r_tunable_set)
+}  // namespace b2r
+// host-side range check of query term ids against an index (csrc/bm25.cu)
+extern "C" int bm25_check_terms(const b2r_bm25* h, const int32_t* term_ids, int n);
+namespace b2r {
 
 struct DeviceGuard {
   int prev;

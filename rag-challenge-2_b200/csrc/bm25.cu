@@ -1053,7 +1053,7 @@ static int bm25_run(b2r_bm25* h, const int* term_ids_dev, const int* term_offset
 extern "C" {
 
 // weight_bits and device-resident inputs are selected through tunables-free explicit arguments in
-// b2r_bm25_create_ex; b2r_bm25_create is the plain host-input, float32-weight form of the header.
+// b2r_bm25_create_ex; b2r_bm25_create is the plain host-input, float64-weight (rank_bm25-exact) form of the header.
 int b2r_bm25_create_ex(int64_t n_docs, int32_t n_terms, const int64_t* indptr, const int32_t* doc_ids,
                        const int32_t* tf, const int32_t* doc_len, double avgdl, const double* idf, double k1, double b,
                        int device, int inputs_on_device, int weight_bits, b2r_bm25** out) {
@@ -1157,7 +1157,7 @@ int b2r_bm25_create_ex(int64_t n_docs, int32_t n_terms, const int64_t* indptr, c
 int b2r_bm25_create(int64_t n_docs, int32_t n_terms, const int64_t* indptr, const int32_t* doc_ids, const int32_t* tf,
                     const int32_t* doc_len, double avgdl, const double* idf, double k1, double b, int device,
                     b2r_bm25** out) {
-  return b2r_bm25_create_ex(n_docs, n_terms, indptr, doc_ids, tf, doc_len, avgdl, idf, k1, b, device, 0, 32, out);
+  return b2r_bm25_create_ex(n_docs, n_terms, indptr, doc_ids, tf, doc_len, avgdl, idf, k1, b, device, 0, 64, out);
 }
 
 int b2r_bm25_ndocs(const b2r_bm25* h, int64_t* out) {
@@ -1173,7 +1173,7 @@ int b2r_bm25_postings(const b2r_bm25* h, int64_t* n_post, int* weight_bits) {
   return B2R_OK;
 }
 
-static int bm25_check_terms(const b2r_bm25* h, const int32_t* term_ids, int n) {
+int bm25_check_terms(const b2r_bm25* h, const int32_t* term_ids, int n) {
   for (int i = 0; i < n; ++i) {
     if (term_ids[i] < 0 || term_ids[i] >= h->n_terms) {
       return fail(B2R_ERR_INVALID, "bm25: term id " + std::to_string(term_ids[i]) + " out of range");

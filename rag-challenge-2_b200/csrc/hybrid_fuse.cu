@@ -118,6 +118,8 @@ struct ExchangeArgs {
   int rank, world;
   int nq_max, k_max;
   u32 step;
+  u32* status;              // device-visible word (may be mapped host memory), 0 = ok; NULL: a timed-out wait traps
+  unsigned long long timeout_ns;  // bound on the wait for the peers' flags
 };
 
 __host__ __device__ inline size_t exch_slot_bytes(int nq_max, int k_max) {
@@ -138,6 +140,11 @@ __device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __global__ void __launch_bounds__(256) hybrid_exchange_fuse_kernel(const float* __restrict__ D,
                                                                    const long long* __restrict__ I,
@@ -146,7 +153,9 @@ __global__ void __launch_bounds__(256) hybrid_exchange_fuse_kernel(const float* 
                                                                    const ExchangeArgs x, float* __restrict__ F,
                                                                    long long* __restrict__ O) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int timed_out;
   const int q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) timed_out = 0;
   const int parity = static_cast<int>(x.step & 1u);
   const size_t slot = exch_slot_bytes(x.nq_max, x.k_max);
   const size_t nk = static_cast<size_t>(x.nq_max) * x.k_max;
@@ -175,10 +184,26 @@ __global__ void __launch_bounds__(256) hybrid_exchange_fuse_kernel(const float* 
     st_release_sys(pf, x.step);
     const u32* mine = reinterpret_cast<const u32*>(x.peers[x.rank] + flags_off) +
                       (static_cast<size_t>(parity) * x.world + tid) * x.nq_max + q;
+    // bounded wait: a peer that failed before launching (or runs a different step) must not hang this GPU forever
+    const unsigned long long t0 = global_timer_ns();
+    u32 spins = 0;
     while (ld_acquire_sys(mine) != x.step) {
+      if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > x.timeout_ns) {
+        if (x.status == nullptr) __trap();
+        *reinterpret_cast<volatile u32*>(x.status) = 1u + static_cast<u32>(tid);   // 1 + a rank found missing
+        timed_out = 1;
+        break;
+      }
     }
   }
   __syncthreads();
+  if (timed_out) {  // no answer for this query: pad, and let the host report B2R_ERR_CUDA from the status word
+    for (int i = tid; i < k; i += nt) {
+      F[static_cast<size_t>(q) * k + i] = -3.4028235e38f;
+      O[static_cast<size_t>(q) * k + i] = -1;
+    }
+    return;
+  }
 
   // (4) merge the world lists of this query, then fuse
   const int total = x.world * k;
@@ -284,7 +309,7 @@ extern "C" size_t b2r_hybrid_exchange_bytes(int nq_max, int k_max, int world) {
 
 extern "C" int b2r_hybrid_exchange_fuse_dev(const float* D, const int64_t* I, const double* S, const int64_t* J, int nq,
                                             int k, void* const* peer_bufs, int rank, int world, int nq_max, int k_max,
-                                            uint32_t step, float* F, int64_t* O, void* stream) {
+                                            uint32_t step, float* F, int64_t* O, uint32_t* status, void* stream) {
   if (nq < 0 || k < 1 || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(B2R_ERR_INVALID, "b2r_hybrid_exchange: bad sizes");
   if (nq > nq_max || k > k_max || k > 256) return fail(B2R_ERR_INVALID, "b2r_hybrid_exchange: nq / k exceed the buffer geometry");
   if (step == 0) return fail(B2R_ERR_INVALID, "b2r_hybrid_exchange: step must be >= 1 (0 is the cleared flag value)");
@@ -297,6 +322,9 @@ extern "C" int b2r_hybrid_exchange_fuse_dev(const float* D, const int64_t* I, co
   x.nq_max = nq_max;
   x.k_max = k_max;
   x.step = step;
+  x.status = status;
+  const int tmo_ms = tunable("exchange.timeout_ms");
+  x.timeout_ns = static_cast<unsigned long long>(tmo_ms > 0 ? tmo_ms : 10000) * 1000000ull;
   int cap = 2, fcap = 2;
   while (cap < world * k) cap <<= 1;
   while (fcap < 2 * k) fcap <<= 1;

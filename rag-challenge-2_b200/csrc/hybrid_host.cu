@@ -47,7 +47,7 @@ static int ctx_reserve(b2r_hybrid_ctx* c, size_t in_bytes, size_t nk) {
     if (c->out_dev) cudaFree(c->out_dev);
     c->out_pin = c->out_dev = nullptr;
     c->out_cap = 0;
-    B2R_CUDA(cudaHostAlloc(&c->out_pin, cap * 12, cudaHostAllocMapped));
+    B2R_CUDA(cudaHostAlloc(&c->out_pin, cap * 12 + 64, cudaHostAllocMapped));  // + the exchange kernel's status word
     B2R_CUDA(cudaHostGetDevicePointer(&c->out_pin_dev, c->out_pin, 0));
     B2R_CUDA(cudaMalloc(&c->out_dev, cap * 28));
     c->out_cap = cap;
@@ -108,6 +108,22 @@ int b2r_hybrid_search_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, co
   if (fd != d) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: query width does not match the index");
   const int n_terms = term_offsets[nq];
   if (term_offsets[0] != 0 || n_terms < 0 || (n_terms > 0 && !term_ids)) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: bad term offsets");
+  // everything that can be rejected is rejected HERE, before anything is enqueued: in the multi-GPU step a rank that
+  // fails after its peers launched leaves them waiting (for exchange.timeout_ms) on a kernel that never comes
+  rc = bm25_check_terms(bm25, term_ids, n_terms);
+  if (rc) return rc;
+  int64_t n_rows = 0;
+  rc = b2r_flat_ntotal(flat, &n_rows);
+  if (rc) return rc;
+  if (id_offset < 0 || id_offset + n_rows >= 0xFFFFFFF0LL) return fail(B2R_ERR_UNSUPPORTED, "b2r_hybrid_search_host: global ids must stay below 2^32-16 (the fusion packs them in 32 bits)");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: bad rank / world");
+  if (world > 1) {
+    if (!peer_bufs) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: world > 1 needs the peer buffers");
+    for (int p = 0; p < world; ++p)
+      if (!peer_bufs[p]) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: NULL peer buffer");
+    if (nq > nq_max || k > k_max || k > 256) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: nq / k exceed the exchange buffer geometry");
+    if (step == 0) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: step must be >= 1");
+  }
   DeviceGuard g(c->device);
   if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_hybrid_search_host: cudaSetDevice failed");
   std::lock_guard<std::mutex> lock(c->mu);
@@ -139,15 +155,20 @@ int b2r_hybrid_search_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, co
   rc = b2r_bm25_topk_dev_ex(bm25, tids_dev, offs_dev, nullptr, nq, k, S_dev, J_dev, id_offset, c->stream,
                             B2R_LAUNCH_OVERLAP_PREVIOUS);
   if (rc) return rc;
+  volatile uint32_t* status_host = reinterpret_cast<volatile uint32_t*>(c->out_pin + c->out_cap * 12);
   if (world > 1) {
-    if (!peer_bufs) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: world > 1 needs the peer buffers");
+    *status_host = 0;
     rc = b2r_hybrid_exchange_fuse_dev(D_dev, I_dev, S_dev, J_dev, nq, k, peer_bufs, rank, world, nq_max, k_max, step, F_dev,
-                                      O_dev, c->stream);
+                                      O_dev, reinterpret_cast<uint32_t*>(c->out_pin_dev + c->out_cap * 12), c->stream);
   } else {
     rc = b2r_hybrid_fuse_dev(D_dev, I_dev, S_dev, J_dev, nq, k, k, k, F_dev, O_dev, nullptr, c->stream);
   }
   if (rc) return rc;
   B2R_CUDA(cudaStreamSynchronize(c->stream));
+  if (world > 1 && *status_host != 0) {
+    return fail(B2R_ERR_CUDA, "b2r_hybrid_search_host: the exchange timed out waiting for rank " + std::to_string(*status_host - 1) +
+                                  " (step " + std::to_string(step) + "): a peer failed or the ranks are out of lockstep");
+  }
   memcpy(O, c->out_pin, nk * 8);
   memcpy(F, c->out_pin + nk * 8, nk * 4);
   c->last_h2d = h2d;

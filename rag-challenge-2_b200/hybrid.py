@@ -16,10 +16,16 @@ from . import _lib
 
 def shard_bounds(n, world_size, align=1):
     """Contiguous row ranges, one per rank, starting on multiples of `align` (the synthetic
-    generators are seeded per block); the last rank takes the remainder."""
-    per = -(-n // world_size)
-    per = -(-per // align) * align
-    bounds = [min(n, r * per) for r in range(world_size)] + [n]
+    generators are seeded per block), balanced to within one block: the step ends with the slowest
+    rank, so the largest shard sets the pace.  The ceil(n / align) blocks are dealt out evenly; the
+    ranks that get the extra block come first and the (possibly partial) last block goes to the last
+    rank, which therefore never holds more rows than the first."""
+    blocks = -(-n // align)
+    base, extra = divmod(blocks, world_size)
+    bounds = [0]
+    for r in range(world_size):
+        bounds.append(min(n, bounds[-1] + (base + (1 if r < extra else 0)) * align))
+    bounds[-1] = n
     return bounds
 
 
@@ -57,8 +63,9 @@ def hybrid_fuse(D, I, S, J, k_out, want_methods=False, stream=None):
     return (F, O, M) if want_methods else (F, O)
 
 
-def exchange_fuse(D, I, S, J, peer_ptrs, rank, world, nq_max, k_max, step, stream=None):
-    """One-kernel exchange + merge + fusion over peer memory (csrc/hybrid_fuse.cu)."""
+def exchange_fuse(D, I, S, J, peer_ptrs, rank, world, nq_max, k_max, step, stream=None, status=None):
+    """One-kernel exchange + merge + fusion over peer memory (csrc/hybrid_fuse.cu).  status: int32 CUDA tensor [1]
+    (zero = ok) that receives 1 + a missing rank if the bounded wait for the peers expires; None: the kernel traps."""
     import torch
 
     lib = _lib.load()
@@ -71,7 +78,9 @@ def exchange_fuse(D, I, S, J, peer_ptrs, rank, world, nq_max, k_max, step, strea
     _lib.check(lib.b2r_hybrid_exchange_fuse_dev(C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
                                                 C.c_void_p(S.data_ptr()), C.c_void_p(J.data_ptr()), nq, k, arr,
                                                 int(rank), int(world), int(nq_max), int(k_max), int(step),
-                                                C.c_void_p(F.data_ptr()), C.c_void_p(O.data_ptr()), C.c_void_p(stream)))
+                                                C.c_void_p(F.data_ptr()), C.c_void_p(O.data_ptr()),
+                                                C.c_void_p(status.data_ptr()) if status is not None else None,
+                                                C.c_void_p(stream)))
     return F, O
 
 
@@ -96,10 +105,22 @@ class PeerExchange:
         dist.barrier(group)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
         self.step = 0
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
 
     def fuse(self, D, I, S, J):
+        # the step counter advances only once the launch has been accepted: a call rejected by the argument checks
+        # must not leave this rank one step ahead of its peers
+        out = exchange_fuse(D, I, S, J, self.ptrs, self.rank, self.world, self.nq_max, self.k_max, self.step + 1,
+                            status=self.status)
         self.step += 1
-        return exchange_fuse(D, I, S, J, self.ptrs, self.rank, self.world, self.nq_max, self.k_max, self.step)
+        return out
+
+    def check(self):
+        """Synchronises and raises if any exchange kernel since the last check gave up waiting for a peer."""
+        v = int(self.status.item())
+        if v:
+            self.status.zero_()
+            raise RuntimeError(f"hybrid exchange timed out waiting for rank {v - 1}: a peer failed or the ranks are out of lockstep")
 
 
 class ShardedSearcher:
@@ -339,14 +360,15 @@ class HybridIndex:
             import torch
 
             torch.cuda.current_stream(torch.device("cuda", self.flat.device)).synchronize()  # order after resident steps
-            px.step += 1
             arr = (C.c_void_p * len(px.ptrs))(*[C.c_void_p(int(p)) for p in px.ptrs])
-            args = (arr, px.rank, px.world, px.nq_max, px.k_max, px.step)
+            args = (arr, px.rank, px.world, px.nq_max, px.k_max, px.step + 1)
         else:
             args = (None, 0, 1, 0, 0, 0)
         self.bm25._ensure_built()
         _lib.check(lib.b2r_hybrid_search_host(self._ctx, self.flat._h, self.bm25._h, _lib.ptr(x), nq, d, _lib.ptr(tids),
                                               _lib.ptr(offs), int(k), self.offset, *args, _lib.ptr(F), _lib.ptr(O)))
+        if px is not None:
+            px.step += 1   # only after the call succeeded: a rejected call enqueued nothing (the checks come first)
         h2d, d2h = C.c_size_t(0), C.c_size_t(0)
         lib.b2r_hybrid_ctx_bytes(self._ctx, C.byref(h2d), C.byref(d2h))
         self.last_h2d_bytes, self.last_d2h_bytes = int(h2d.value), int(d2h.value)

@@ -22,15 +22,15 @@ DOC_BLOCK = 1 << 14   # documents per seeded block (tokens)
 # dense rows
 # ------------------------------------------------------------------------------------------------
 def dense_rows_torch(row_lo, row_hi, d, device, seed=1234):
-    """float32 CUDA tensor with global rows [row_lo, row_hi); row_lo must be block aligned."""
+    """float32 CUDA tensor with global rows [row_lo, row_hi).  Blocks are seeded whole, so a shard may start or end
+    anywhere: a boundary block is generated in full and sliced (the corpus does not depend on the sharding)."""
     import torch
 
-    assert row_lo % ROW_BLOCK == 0, "shards must start on a ROW_BLOCK boundary"
     out = torch.empty((row_hi - row_lo, d), dtype=torch.float32, device=device)
-    for lo in range(row_lo, row_hi, ROW_BLOCK):
-        hi = min(row_hi, lo + ROW_BLOCK)
-        g = torch.Generator(device=device).manual_seed(seed + lo // ROW_BLOCK)
-        blk = torch.randn((ROW_BLOCK, d), generator=g, device=device, dtype=torch.float32)[: hi - lo]
+    for blk_lo in range(row_lo // ROW_BLOCK * ROW_BLOCK, row_hi, ROW_BLOCK):
+        lo, hi = max(row_lo, blk_lo), min(row_hi, blk_lo + ROW_BLOCK)
+        g = torch.Generator(device=device).manual_seed(seed + blk_lo // ROW_BLOCK)
+        blk = torch.randn((ROW_BLOCK, d), generator=g, device=device, dtype=torch.float32)[lo - blk_lo: hi - blk_lo]
         blk /= blk.norm(dim=1, keepdim=True)
         out[lo - row_lo: hi - row_lo] = blk
     return out
@@ -99,22 +99,25 @@ def token_postings_torch(doc_lo, doc_hi, vocab, device, seed=4242, mean_len=120.
     """Term-major CSR postings of global documents [doc_lo, doc_hi), built in HBM.
 
     Returns dict(indptr int64[V+1], doc_ids int32[P] (LOCAL ids, ascending per term), tf int32[P],
-    doc_len int32[n], df int64[V], total_len int).  doc_lo must be DOC_BLOCK aligned.
+    doc_len int32[n], df int64[V], total_len int).  Blocks of DOC_BLOCK documents are seeded whole; a shard that
+    starts or ends inside a block generates that block in full and keeps its own documents, so the corpus does not
+    depend on the sharding (the corpus end, `doc_hi` of the last shard, truncates the last block as before).
     """
     import torch
 
-    assert doc_lo % DOC_BLOCK == 0, "shards must start on a DOC_BLOCK boundary"
     n = doc_hi - doc_lo
     cdf = torch.from_numpy(zipf_cdf(vocab)).to(device)
     keys = []
     lens_all = []
-    for lo in range(doc_lo, doc_hi, DOC_BLOCK):
-        hi = min(doc_hi, lo + DOC_BLOCK)
-        g = torch.Generator(device=device).manual_seed(seed + lo // DOC_BLOCK)
-        z = torch.randn((DOC_BLOCK,), generator=g, device=device, dtype=torch.float64)[: hi - lo]
+    for blk_lo in range(doc_lo // DOC_BLOCK * DOC_BLOCK, doc_hi, DOC_BLOCK):
+        lo, hi = max(doc_lo, blk_lo), min(doc_hi, blk_lo + DOC_BLOCK)
+        g = torch.Generator(device=device).manual_seed(seed + blk_lo // DOC_BLOCK)
+        z = torch.randn((DOC_BLOCK,), generator=g, device=device, dtype=torch.float64)[: hi - blk_lo]
         lens = torch.clamp(torch.round(torch.exp(math.log(mean_len) + sigma * z)), 8, 512).to(torch.int64)
         total = int(lens.sum().item())
-        u = torch.rand((int(DOC_BLOCK) * 512,), generator=g, device=device, dtype=torch.float64)[:total]
+        skip = int(lens[: lo - blk_lo].sum().item()) if lo > blk_lo else 0   # tokens of the block's documents before `lo`
+        u = torch.rand((int(DOC_BLOCK) * 512,), generator=g, device=device, dtype=torch.float64)[skip:total]
+        lens = lens[lo - blk_lo:]
         ranks = torch.clamp(torch.searchsorted(cdf, u), max=vocab - 1)
         doc_of = torch.repeat_interleave(torch.arange(lo - doc_lo, hi - doc_lo, device=device), lens)
         keys.append(ranks * n + doc_of)

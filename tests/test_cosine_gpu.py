@@ -119,3 +119,59 @@ def test_stats_cta_pair_kernel(b2r, n, d):
     merged = cosine.finalize_stats(np.array([stats[0], stats[1], min(float(p[0][2]) for p in parts),
                                              max(float(p[0][3]) for p in parts), stats[2], 0.0]), hist)
     compare(x, merged)
+
+
+def test_stats_at_baseline_config5_size(b2r):
+    """BASELINE config 5's stated size (N = 200k x 1024, un-normalised rows; B2R_COSINE_ROWS overrides): the statistics of the
+    CTA-pair kernel against a blocked FLOAT64 recomputation of generate_similarity_matrix.py:84-98,164-171 — normalise
+    (X / (|X| + 1e-8), fp32 like the script), S = Xn Xn^T in float64 by cuBLAS (checker only), diagonal dropped, clip,
+    then sum / sum^2 / min / max / a 2^22-bin histogram for the median (bin 4.8e-7).  Bars: mean / std / min / max 1e-5
+    relative (+2e-6), median 1e-4."""
+    import os
+
+    import torch
+
+    from rag_challenge_2_b200 import cosine
+
+    n, d = int(os.environ.get("B2R_COSINE_ROWS", "200000")), 1024
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(777)
+    x = torch.randn((n, d), generator=g, device=dev) + 0.3 * torch.randn((1, d), generator=g, device=dev)
+    x *= 0.5 + 1.5 * torch.rand((n, 1), generator=g, device=dev)
+    x[7] = 3.0 * x[3]                                   # a pair that must clip at 1.0
+    x[n - 1] = -2.0 * x[n - 5]                          # and one at -1.0
+    got = cosine.cosine_stats(x.contiguous())
+    xn = (x / (x.norm(dim=1, keepdim=True) + 1e-8)).double()
+    bins = 1 << 22
+    hist = torch.zeros(bins, dtype=torch.int64, device=dev)
+    tot = torch.zeros(2, dtype=torch.float64, device=dev)
+    mn, mx = 2.0, -2.0
+    blk = 2048
+    for lo in range(0, n, blk):
+        hi = min(n, lo + blk)
+        s = (xn[lo:hi] @ xn.T).clamp_(-1.0, 1.0)
+        idx = torch.arange(lo, hi, device=dev)
+        diag = s[idx - lo, idx].clone()
+        s[idx - lo, idx] = 0.0                          # drop the diagonal from the sums ...
+        tot[0] += s.sum()
+        tot[1] += (s * s).sum()
+        s[idx - lo, idx] = 2.0                          # ... and park it outside the value range for min / histogram
+        mn = min(mn, float(s.min()))
+        b = ((s + 1.0) * (bins / 2)).long().clamp_(0, bins)         # the parked diagonal lands in bin `bins`
+        hist += torch.bincount(b.reshape(-1), minlength=bins + 1)[:bins]
+        s[idx - lo, idx] = -2.0
+        mx = max(mx, float(s.max()))
+        del s, b, diag
+    count = n * (n - 1)
+    assert int(hist.sum()) == count and got["count"] == count
+    mean = float(tot[0]) / count
+    std = (float(tot[1]) / count - mean * mean) ** 0.5
+    c = torch.cumsum(hist, 0)
+    j = int(torch.searchsorted(c, torch.tensor([count // 2], device=dev)))
+    median = -1.0 + (j + 0.5) * (2.0 / bins)
+    want = {"avg_similarity": mean, "std_similarity": std, "min_similarity": mn, "max_similarity": mx}
+    for key, w in want.items():
+        assert abs(got[key] - w) <= 1e-5 * abs(w) + 2e-6, (key, got[key], w)
+    assert abs(got["median_similarity"] - median) <= 1e-4, (got["median_similarity"], median)
+    print("config-5 size parity:", {k: (got[k], want.get(k, median)) for k in
+                                    ("avg_similarity", "std_similarity", "min_similarity", "max_similarity", "median_similarity")})

@@ -121,6 +121,61 @@ def test_oracle_cross_checked_with_sklearn_and_scipy():
     assert sp.issparse(tf)
 
 
+# ---- vectors PUBLISHED by the two third-party packages themselves --------------------------------------------
+# rank_bm25's README ("Ranking of documents"): the only numeric output rank-bm25 0.2.2 documents.
+RANK_BM25_README_CORPUS = ["Hello there good man!", "It is quite windy in London", "How is the weather today?"]
+RANK_BM25_README_SCORES = [0.0, 0.93729472, 0.0]
+
+# faiss wiki, "Getting started" (IndexFlatL2, d = 64, nb = 100000, nq = 10000, np.random.seed(1234), k = 4): the printed
+# sanity check (the first five database rows searched against the index) and the first / last five query results.
+FAISS_WIKI_SANITY_I = [[0, 393, 363, 78], [1, 555, 277, 364], [2, 304, 101, 13], [3, 173, 18, 182], [4, 288, 370, 531]]
+FAISS_WIKI_SANITY_D = [[0.0, 7.17517328, 7.2076292, 7.25116253], [0.0, 6.32356453, 6.6845808, 6.79994535],
+                       [0.0, 5.79640865, 6.39173603, 7.28151226], [0.0, 7.27790546, 7.52798653, 7.66284657],
+                       [0.0, 6.76380348, 7.29512024, 7.36881447]]
+FAISS_WIKI_FIRST_I = [[381, 207, 210, 477], [526, 911, 142, 72], [838, 527, 1290, 425], [196, 184, 164, 359], [526, 377, 120, 425]]
+FAISS_WIKI_LAST_I = [[9900, 10500, 9309, 9831], [11055, 10895, 10812, 11321], [11353, 11103, 10164, 9787],
+                     [10571, 10664, 10632, 9638], [9628, 9554, 10036, 9582]]
+
+
+def faiss_wiki_dataset():
+    """The tutorial's data, bit for bit (numpy's legacy MT19937 stream is frozen), and its IndexFlatL2 search restated as an
+    inner-product search: ||q - x||^2 = ||q||^2 - (2 q.x - ||x||^2), so ranking by L2 distance ascending is ranking by the
+    inner product of [q, 1] with [2x, -||x||^2] descending — what IndexFlatIP (and this repo's kernels) compute."""
+    d, nb, nq = 64, 100000, 10000
+    np.random.seed(1234)
+    xb = np.random.random((nb, d)).astype("float32")
+    xb[:, 0] += np.arange(nb) / 1000.0
+    xq = np.random.random((nq, d)).astype("float32")
+    xq[:, 0] += np.arange(nq) / 1000.0
+    rows = np.concatenate([2 * xb, -np.sum(xb.astype(np.float64) ** 2, axis=1, keepdims=True).astype(np.float32)], axis=1)
+    return xb, xq, np.ascontiguousarray(rows)
+
+
+def faiss_wiki_queries(x):
+    return np.ascontiguousarray(np.concatenate([x, np.ones((len(x), 1), np.float32)], axis=1))
+
+
+def test_rank_bm25_published_readme_vector():
+    """The README's example: query "windy London" -> array([0., 0.93729472, 0.]) and get_top_n(..., n=1) -> doc 1."""
+    corpus = [doc.split(" ") for doc in RANK_BM25_README_CORPUS]
+    bm = oracle.BM25OkapiRef(corpus)
+    scores = bm.get_scores("windy London".split(" "))
+    assert np.round(scores, 8).tolist() == RANK_BM25_README_SCORES
+    assert oracle.bm25_topn_ref(scores, 1) == [1]
+
+
+def test_faiss_published_getting_started_vectors():
+    """The oracle's search (scores, selection, order) reproduces every id the faiss tutorial prints, and its distances."""
+    xb, xq, rows = faiss_wiki_dataset()
+    for x, want_i, want_d in ((xb[:5], FAISS_WIKI_SANITY_I, FAISS_WIKI_SANITY_D), (xq[:5], FAISS_WIKI_FIRST_I, None),
+                              (xq[-5:], FAISS_WIKI_LAST_I, None)):
+        D, I = oracle.flat_ip_search_ref(rows, faiss_wiki_queries(x), 4)
+        assert I.tolist() == want_i
+        if want_d is not None:
+            l2 = np.sum(x.astype(np.float64) ** 2, axis=1, keepdims=True) - D
+            assert np.allclose(l2, want_d, atol=2e-4)
+
+
 def test_oracle_against_the_real_packages_when_installed():
     """faiss-cpu / rank-bm25 are not installable in this image; wherever they are, this pins the
     restatement to them directly."""

@@ -105,10 +105,17 @@ def test_sharded_search_world2_gloo(tmp_path):
 def test_shard_bounds():
     from rag_challenge_2_b200.hybrid import shard_bounds
 
-    assert shard_bounds(10_000_000, 8, 1 << 14) == [0, 1261568, 2523136, 3784704, 5046272, 6307840, 7569408, 8830976, 10_000_000]
-    assert shard_bounds(10, 4) == [0, 3, 6, 9, 10]
+    b = shard_bounds(10_000_000, 8, 128)                      # the bench's sharding: balanced to one 128-row block
+    sizes = [hi - lo for lo, hi in zip(b[:-1], b[1:])]
+    assert b[0] == 0 and b[-1] == 10_000_000 and all(x % 128 == 0 for x in b[:-1])
+    assert max(sizes) - min(sizes) <= 128 and max(sizes) == 1_250_048 and sizes[-1] == min(sizes)
+    assert shard_bounds(10_000_000, 8, 1 << 14)[:4] == [0, 1261568, 2523136, 3784704]   # 611 blocks: 3 ranks get 77, 5 get 76
+    assert shard_bounds(10, 4) == [0, 3, 6, 8, 10]
     assert shard_bounds(5, 8) == [0, 1, 2, 3, 4, 5, 5, 5, 5]
     assert shard_bounds(1000, 1, 128) == [0, 1000]
+    for n, w, a in ((1000, 3, 128), (129, 2, 128), (7, 3, 4)):
+        bb = shard_bounds(n, w, a)
+        assert bb[0] == 0 and bb[-1] == n and all(x <= y for x, y in zip(bb[:-1], bb[1:]))
 
 
 def _token_corpus(n=1200, V=300, seed=5):

@@ -18,7 +18,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 n, d, V, k, nq = 16 * synth.ROW_BLOCK - 3_000, 1024, 20_000, 30, 12  # ragged last shard, none empty up to 8 ranks
-bounds = hybrid.shard_bounds(n, world, synth.ROW_BLOCK)
+bounds = hybrid.shard_bounds(n, world, 128)   # boundaries inside seeded blocks, like the bench
 lo, hi = bounds[rank], bounds[rank + 1]
 
 
