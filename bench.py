@@ -38,11 +38,13 @@ def parse_args():
     ap.add_argument("--nq", type=int, default=1, help="queries per step")
     ap.add_argument("--k", type=int, default=30)
     ap.add_argument("--pool", type=int, default=64, help="distinct queries cycled through")
-    ap.add_argument("--cpu-rows", type=int, default=1_000_000, help="rows of the CPU-baseline dense sample")
-    ap.add_argument("--cpu-docs", type=int, default=50_000, help="documents of the CPU-baseline BM25 sample")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU-baseline dense sample (0: the whole corpus if host RAM allows)")
+    ap.add_argument("--cpu-docs", type=int, default=250_000, help="documents of the CPU-baseline BM25 sample inside the B200 arm's line")
+    ap.add_argument("--ref-docs", type=int, default=1_000_000, help="documents of the BM25 sample of --impl reference (extrapolation x10 at 10M)")
     ap.add_argument("--bm25-weight-bits", type=int, default=32, choices=[32, 64],
                     help="stored BM25 weight width: 32 = 8 B/posting (scores within 1e-6 of rank_bm25), 64 = bit-exact")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (extras) after the headline")
     ap.add_argument("--no-overlap", action="store_true", help="run BM25 after the scan instead of beside it")
     ap.add_argument("--overlap", default="pdl", choices=["pdl", "streams"],
                     help="how BM25 runs beside the scan: programmatic dependent launch (one stream) or two streams")
@@ -130,26 +132,71 @@ def ncu_traffic_bytes(rows_local, dim):
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle (port of faiss / rank_bm25 semantics) on a bounded sample, scaled to N
+# CPU baseline: the oracle (port of faiss / rank_bm25 semantics) timed on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_baseline(args, steps, rows_sample=None, verbose=False):
-    """Times the CPU restatement of the reference path on a bounded sample and extrapolates linearly
-    in the corpus size (a flat scan and rank_bm25's per-document loops are both O(N))."""
+def host_mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1048576.0
+    except OSError:
+        pass
+    return 0.0
+
+
+def host_dense_rows(n, d, seed=1234, block=1 << 20):
+    """n unit rows on the HOST without minutes of random-number generation: one random block of `block` rows, then
+    column rotations of it (every row distinct, still unit norm).  A flat scan's cost does not depend on the values."""
+    import numpy as np
+
+    from rag_challenge_2_b200 import synth
+
+    base = synth.dense_rows_np(min(block, n), d, seed=seed)
+    if n <= block:
+        return base
+    out = np.empty((n, d), dtype=np.float32)
+    for i, lo in enumerate(range(0, n, block)):
+        hi = min(n, lo + block)
+        out[lo:hi] = np.roll(base[: hi - lo], 37 * i, axis=1)
+    return out
+
+
+def cpu_baseline(args, n_queries, rows_host=None, bm25_docs=None, budget_s=60.0, verbose=False):
+    """Times the CPU restatement of the reference path — faiss-style flat scan (numpy/OpenBLAS sgemv over ALL host
+    cores + partial sort; also with ONE thread, which is what faiss itself uses below 20 queries) and rank_bm25's
+    get_scores (one Python dict lookup per document and query token) + the reference's full Python sort — on the
+    largest sample the host holds and the time budget allows, and scales each leg linearly to the corpus size (both are
+    O(N) per query; the factors are reported, the dense leg runs at full size when 41 GB of host RAM are free)."""
     import numpy as np
 
     import oracle
+    from oracle.bm25 import bm25_ref_from_arrays, token_corpus_arrays_np
     from rag_challenge_2_b200 import synth
 
-    n_dense = min(args.cpu_rows, args.rows)
-    n_docs = min(args.cpu_docs, args.rows)
-    if rows_sample is None:
-        rows_sample = synth.dense_rows_np(n_dense, args.dim, seed=1234)
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:  # noqa: BLE001
+        threadpool_limits = None
+
+    N = args.rows
+    n_docs = min(N, bm25_docs if bm25_docs is not None else args.cpu_docs)
+    avail = host_mem_available_gb()
+    if rows_host is None:
+        bm_gb = 7.0 * n_docs / 1e6 + 4.0                     # the dict-of-dicts corpus + slack
+        fit = int(max(0.0, avail - bm_gb) * 0.8 * 2**30 / (4.0 * args.dim))
+        n_dense = min(N, args.cpu_rows if args.cpu_rows > 0 else N, max(fit, min(N, 1 << 20)))
+        rows_host = host_dense_rows(n_dense, args.dim)
+    n_dense = int(rows_host.shape[0])
     rng = np.random.default_rng(99)
-    xq = rng.standard_normal((max(steps, 1), args.dim)).astype(np.float32)
+    xq = rng.standard_normal((max(n_queries, 1), args.dim)).astype(np.float32)
     xq /= np.linalg.norm(xq, axis=1, keepdims=True)
-    docs = synth.token_corpus_np(n_docs, vocab=args.vocab, seed=4242)
-    bm = oracle.BM25OkapiRef(docs)
-    queries = [[f"t{r}" for r in q] for q in synth.token_queries_np(max(steps, 1), vocab=args.vocab, seed=4243)]
+    t_build0 = time.perf_counter()
+    ranks, lens = token_corpus_arrays_np(n_docs, vocab=args.vocab, seed=4242)
+    bm = bm25_ref_from_arrays(ranks, lens, args.vocab)
+    del ranks, lens
+    t_build = time.perf_counter() - t_build0
+    queries = [[f"t{r}" for r in q] for q in synth.token_queries_np(max(n_queries, 1), vocab=args.vocab, seed=4243)]
     # The real third-party packages, if this machine has them (this image does not: SURVEY 8c): the reference arm
     # then times faiss / rank_bm25 themselves and reports how far the port's answers are from theirs.
     real, kind, deviation = {}, "port", None
@@ -158,65 +205,97 @@ def cpu_baseline(args, steps, rows_sample=None, verbose=False):
         import rank_bm25  # noqa: F401
 
         fx = faiss.IndexFlatIP(args.dim)
-        fx.add(rows_sample)
-        real = {"flat": fx, "bm25": rank_bm25.BM25Okapi(docs)}
+        fx.add(rows_host)
+        rb = rank_bm25.BM25Okapi.__new__(rank_bm25.BM25Okapi)
+        rb.__dict__.update({k: getattr(bm, k) for k in ("k1", "b", "epsilon", "corpus_size", "doc_len", "doc_freqs", "idf",
+                                                        "avgdl", "average_idf")})
+        real = {"flat": fx, "bm25": rb}
         Df, If = fx.search(xq[:1], args.k)
-        Do, Io = oracle.flat_ip_search_ref(rows_sample, xq[:1], args.k)
-        so, sr = bm.get_scores(queries[0]), real["bm25"].get_scores(queries[0])
+        Do, Io = oracle.flat_ip_search_ref(rows_host, xq[:1], args.k)
+        so, sr = bm.get_scores(queries[0]), rb.get_scores(queries[0])
         deviation = {"dense_ids_equal": bool(np.array_equal(If, Io)),
                      "dense_score_max_rel": float(np.max(np.abs(Df - Do) / np.maximum(np.abs(Do), 1e-30))),
                      "bm25_score_max_abs": float(np.max(np.abs(so - sr)))}
         kind = "reference"
     except Exception:  # noqa: BLE001 - not installed (or unusable): the port is the baseline
         real = {}
-    # one untimed pass (BLAS thread pool, page faults)
-    oracle.flat_ip_search_ref(rows_sample, xq[:1], args.k)
-    t_dense = t_bm = 0.0
-    for i in range(steps):
+    dense = (lambda x: real["flat"].search(x, args.k)) if real else (lambda x: oracle.flat_ip_search_ref(rows_host, x, args.k))
+    dense(xq[:1])   # one untimed pass (BLAS thread pool, page faults)
+    t_dense = t_bm = t_fuse = 0.0
+    done = 0
+    t_start = time.perf_counter()
+    for i in range(max(n_queries, 1)):
         t0 = time.perf_counter()
-        if real:
-            D, I = real["flat"].search(xq[i: i + 1], args.k)
-        else:
-            D, I = oracle.flat_ip_search_ref(rows_sample, xq[i: i + 1], args.k)
+        D, I = dense(xq[i: i + 1])
         t1 = time.perf_counter()
         sc = (real["bm25"] if real else bm).get_scores(queries[i])
-        top = oracle.bm25_topn_ref(sc, args.k)
+        top = oracle.bm25_topn_ref(sc, args.k)                      # src/retrieval.py:264-265: full Python sort
         S = np.array([[sc[j] for j in top]])
         t2 = time.perf_counter()
         oracle.hybrid_fuse_ref(D, I, S, np.array([top]), args.k)
+        t3 = time.perf_counter()
         t_dense += t1 - t0
         t_bm += t2 - t1
-    t_dense /= max(steps, 1)
-    t_bm /= max(steps, 1)
-    per_query = t_dense * (args.rows / n_dense) + t_bm * (args.rows / n_docs)
+        t_fuse += t3 - t2
+        done += 1
+        if time.perf_counter() - t_start > budget_s and done >= 2:
+            break
+    t_dense, t_bm, t_fuse = t_dense / done, t_bm / done, t_fuse / done
+    # one thread (faiss's own nq < 20 path is single-threaded per query): a 2M-row slice, scaled
+    t_dense_1t, n_1t = None, min(n_dense, 2_000_000)
+    if threadpool_limits is not None and not real:
+        with threadpool_limits(limits=1):
+            oracle.flat_ip_search_ref(rows_host[:n_1t], xq[:1], args.k)
+            t0 = time.perf_counter()
+            for i in range(2):
+                oracle.flat_ip_search_ref(rows_host[:n_1t], xq[i % len(xq): i % len(xq) + 1], args.k)
+            t_dense_1t = (time.perf_counter() - t0) / 2
+    f_dense, f_bm = N / n_dense, N / n_docs
+    dense_at_n, bm_at_n = t_dense * f_dense, t_bm * f_bm
+    per_query = dense_at_n + bm_at_n + t_fuse
+    cores = os.cpu_count()
     return {
-        "value": 1.0 / per_query, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "port_vs_packages": deviation,
-        "threads": {"dense_scan_openblas": os.cpu_count(), "bm25_python_loops": 1},
+        "value": 1.0 / per_query, "unit": UNIT, "cores": cores, "kind": kind, "port_vs_packages": deviation,
+        "threads": {"dense_scan_openblas": cores, "bm25_python_loops": 1},
         "sample": (("faiss-cpu IndexFlatIP.search + rank_bm25.BM25Okapi.get_scores (the packages themselves, installed on this "
                     "machine) + Python stable sort" if real else
-                    "oracle port (numpy/OpenBLAS fp32 scan on all cores + partial sort; rank_bm25-style per-document dict loops + "
-                    "Python stable sort)") + f": dense {n_dense} x {args.dim} rows {t_dense * 1e3:.1f} ms/query, BM25 {n_docs} docs "
-                   f"{t_bm * 1e3:.1f} ms/query, both scaled linearly to {args.rows} chunks (extrapolated); {steps} queries"),
-        "t_dense_ms_sample": t_dense * 1e3, "t_bm25_ms_sample": t_bm * 1e3,
+                    "oracle port (numpy/OpenBLAS fp32 scan on all cores + partial sort; rank_bm25's per-document dict loops + "
+                    "the reference's full Python sort)") +
+                   f": dense MEASURED on {n_dense} x {args.dim} rows ({t_dense * 1e3:.1f} ms/query, x{f_dense:.2f} to {N}), "
+                   f"BM25 MEASURED on {n_docs} documents ({t_bm * 1e3:.1f} ms/query, x{f_bm:.2f} to {N}); {done} queries"),
+        "extrapolation": {"dense_factor": f_dense, "bm25_factor": f_bm, "law": "linear in the corpus size (flat scan; one dict lookup "
+                          "per document and token; n log n sort treated as linear)"},
+        "parts": {"dense_ms_per_query_at_N": dense_at_n * 1e3, "bm25_ms_per_query_at_N": bm_at_n * 1e3, "fusion_ms": t_fuse * 1e3,
+                  "dense_1thread_ms_per_query_at_N": (None if t_dense_1t is None else t_dense_1t * (N / n_1t) * 1e3),
+                  "dense_1thread_sample_rows": n_1t, "dense_GBps_all_cores": 4.0 * n_dense * args.dim / t_dense / 1e9,
+                  "bm25_index_build_s": t_build},
+        "measured_ms_per_query_on_sample": (t_dense + t_bm + t_fuse) * 1e3, "queries_timed": done,
+        "host_mem_available_gb": avail,
     }
+
+
+CB_KEYS = ("value", "unit", "cores", "kind", "sample", "threads", "port_vs_packages", "extrapolation", "parts",
+           "measured_ms_per_query_on_sample", "queries_timed")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    for _ in range(max(0, min(args.warmup, 1))):
-        pass
-    steps = max(1, min(args.steps, 20))  # bounded: each step is one hybrid query on the CPU sample
-    cb = cpu_baseline(args, steps)
+    # --steps K: up to K queries are timed, bounded so that the whole run ends within a few minutes
+    cb = cpu_baseline(args, max(1, min(args.steps, 20)), bm25_docs=args.ref_docs, budget_s=90.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.nq / cb["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "threads", "port_vs_packages")},
+        "cpu_baseline": {k: cb[k] for k in CB_KEYS},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "timed_steps": steps,
+        "gpu_launches": 0, "timed_steps": cb["queries_timed"],
+        "ms_per_step_note": ("ms_per_step is the per-query time AT THE FULL CORPUS SIZE: the dense leg is measured at "
+                             f"x{cb['extrapolation']['dense_factor']:.2f} and the BM25 leg at x{cb['extrapolation']['bm25_factor']:.2f} "
+                             "of it (rank_bm25's list of per-document dicts for 10M documents needs ~70 GB and ~15 min to build); "
+                             "the time actually spent per query on the sample is cpu_baseline.measured_ms_per_query_on_sample"),
     }
     print(json.dumps(line), flush=True)
 
@@ -226,6 +305,189 @@ def workload_config(args, world):
                         f"chunks (vocab {args.vocab}, Zipf) + fusion; {args.nq} query/step",
             "rows": args.rows, "dim": args.dim, "vocab": args.vocab, "k": args.k, "queries_per_step": args.nq,
             "sharding": f"rows/{world}", "bm25_overlapped_with_scan": (False if args.no_overlap else args.overlap), "l2": "inputs (rows + postings) far larger than the 126 MB L2; no flush needed"}
+
+
+# --------------------------------------------------------------------------------------------------
+# extras: the other BASELINE configs, each with its own roofline (explanatory; the metric is the headline)
+# --------------------------------------------------------------------------------------------------
+def cuda_time_ms(fn, iters, warm=1):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def measured_tensor_peaks(dev):
+    """Denominators for the tensor-core extras: tf32 measured here (cuBLAS fp32 matmul with TF32 allowed, 8192^3, best of
+    5 — library call as a yardstick only), bf16 from MEASURED_PEAKS.json (sustained) or the same probe."""
+    import torch
+
+    out = {}
+    a = torch.randn((8192, 8192), device=dev)
+    b = torch.randn((8192, 8192), device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        best = min(cuda_time_ms(lambda: torch.matmul(a, b), 3) for _ in range(5))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    out["tf32_tflops"] = 2 * 8192.0**3 / best / 1e9
+    out["tf32_source"] = "measured in this run: torch.matmul fp32 with TF32 allowed, 8192^3, best of 5"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        out["bf16_tflops"] = float(mp.get("bf16_tflops_sustained") or mp["bf16_tflops"])
+        out["bf16_source"] = "MEASURED_PEAKS.json (sustained)"
+    except Exception:  # noqa: BLE001
+        a16, b16 = a.bfloat16(), b.bfloat16()
+        best = min(cuda_time_ms(lambda: torch.matmul(a16, b16), 3) for _ in range(5))
+        out["bf16_tflops"] = 2 * 8192.0**3 / best / 1e9
+        out["bf16_source"] = "measured in this run: torch.matmul bf16 8192^3, best of 5"
+    return out
+
+
+def config_extras(args, flat, bm25, rows, df, dev, hbm_peak):
+    import numpy as np
+    import torch
+
+    import rag_challenge_2_b200 as pkg
+    from rag_challenge_2_b200 import cosine, retrieval, synth
+
+    ex = {}
+    n, d = int(rows.shape[0]), args.dim
+
+    def guarded(name, fn):
+        try:
+            ex[name] = fn()
+        except Exception as e:  # noqa: BLE001 - an extra must never cost the headline line
+            ex[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.synchronize()
+
+    peaks = {}
+    guarded("tensor_peaks", lambda: peaks.update(measured_tensor_peaks(dev)) or dict(peaks))
+
+    # ---- config 3: dense batches of 1024 and 4096 queries on the tensor cores (tf32 candidates; bf16 copy of the rows) ----
+    def dense_batch(nq, bf16):
+        def run():
+            q = synth.dense_queries_torch(nq, d, dev, rows, seed=500 + nq)
+            flat.enable_bf16_candidates(bf16)
+            try:
+                ms = cuda_time_ms(lambda: flat.search_dev(q, args.k), 3 if nq <= 1024 else 2)
+            finally:
+                flat.enable_bf16_candidates(False)
+            tf = 2.0 * n * d * nq / ms / 1e9
+            peak = peaks.get("bf16_tflops" if bf16 else "tf32_tflops")
+            return {"ms": ms, "rows": n, "queries_per_s": nq / ms * 1e3,
+                    "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                                 "frac": (tf / peak if peak else None), "flops_per_launch_sequence": 2.0 * n * d * nq,
+                                 "peak_source": peaks.get("bf16_source" if bf16 else "tf32_source"),
+                                 "note": "whole search (pre-pass, candidate pass on tcgen05, select, fp32 rescoring, redo check); "
+                                         "useful flops 2*n*d*nq"},
+                    "hbm_GBps_equiv": (4.0 if not bf16 else 2.0) * n * d * -(-nq // 256) / ms / 1e6}
+        return run
+
+    for nq in (1024, 4096):
+        guarded(f"config3_dense_batch{nq}_tf32", dense_batch(nq, False))
+        guarded(f"config3_dense_batch{nq}_bf16_candidates", dense_batch(nq, True))
+
+    # ---- config 4 alone: BM25 top-k, 1 and 64 queries per launch (bytes = sum of df * bytes per posting) ----
+    def bm25_only(nq):
+        def run():
+            pool = synth.token_queries_np(64, vocab=args.vocab, seed=4243)
+            _, wbits = bm25.n_postings()
+            bpp = 4 + wbits // 8
+            batches = []
+            for i in range(0, 64, nq):
+                toks = pool[i: i + nq]
+                offs = np.zeros(len(toks) + 1, np.int32)
+                np.cumsum([len(t) for t in toks], out=offs[1:])
+                batches.append((torch.from_numpy(np.concatenate(toks).astype(np.int32)).to(dev), torch.from_numpy(offs).to(dev),
+                                sum(int(df[t]) for q in toks for t in q)))
+
+            def sweep():
+                for t, o, _ in batches:
+                    bm25.topk_dev(t, o, args.k)
+            ms = cuda_time_ms(sweep, 3) / len(batches)
+            nbytes = float(np.mean([b[2] for b in batches])) * bpp
+            gbs = nbytes / ms / 1e6
+            return {"ms": ms, "queries_per_s": nq / ms * 1e3,
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "algorithmic_bytes_per_launch": nbytes, "bytes_per_posting": bpp}}
+        return run
+
+    guarded("bm25_only_1_query", bm25_only(1))
+    guarded("bm25_only_64_queries", bm25_only(64))
+
+    # ---- config 2: six time-routed year databases, a 127-question batch, host strings in / record dicts out ----
+    def config2():
+        company, years = "\u91d1\u76d8\u79d1\u6280", [2020, 2021, 2022, 2023, 2024, 2025]
+        sizes = np.linspace(200_000, 2_000_000, len(years)).astype(np.int64)
+        reports = []
+        for i, (year, m) in enumerate(zip(years, sizes)):
+            lo = (700 + 130 * i) * synth.ROW_BLOCK                      # seeded blocks disjoint from the main corpus
+            r = synth.dense_rows_torch(lo, lo + int(m), d, dev)
+            reports.append(synth.synthetic_year_report(f"J{year}", company, int(m), pkg.FlatIPIndex.from_device_tensor(r)))
+        rt = retrieval.VectorRetriever.from_reports(reports, qwen=retrieval.HashEmbedder(d), parallel_workers=8)
+        questions = [f"{years[i % 6]}\u5e74{company}\u7684\u7b2c{i}\u4e2a\u8d22\u52a1\u6307\u6807\u662f\u591a\u5c11\uff1f" for i in range(127)]
+        kw = dict(top_n=args.k, use_hyde=False, use_multi_query=False)
+        out = {"dbs": 6, "rows_per_db": [int(m) for m in sizes], "questions": 127, "n_gpus": 1}
+        for name, sel in (("all_years", None), ("three_years", [2023, 2024, 2025])):
+            rt.retrieve_batch(company, questions, selected_years=sel, **kw)
+            best = 1e30
+            for _ in range(3):
+                t0 = time.perf_counter()
+                got = rt.retrieve_batch(company, questions, selected_years=sel, **kw)
+                best = min(best, time.perf_counter() - t0)
+            emb = torch.from_numpy(np.concatenate([rt.qwen.embed(q).reshape(1, -1) for q in questions]).astype(np.float32)).to(dev)
+            idxs = [r["vector_db"] for r in reports if sel is None or int(r["name"][1:]) in sel]
+            dev_ms = cuda_time_ms(lambda: [ix.search_dev(emb, args.k) for ix in idxs], 3)
+            scanned = sum(int(ix.ntotal) for ix in idxs)
+            out[name] = {"e2e_questions_per_s": 127 / best, "e2e_ms": best * 1e3, "device_ms": dev_ms,
+                         "host_over_device": best * 1e3 / dev_ms, "records_returned": sum(len(g["results"]) for g in got),
+                         "roofline": {"bound": "hbm", "achieved": 4.0 * scanned * d / dev_ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": 4.0 * scanned * d / dev_ms / 1e6 / hbm_peak,
+                                      "algorithmic_bytes_per_launch_sequence": 4.0 * scanned * d,
+                                      "note": "127 queries share every row read (one tensor-core batch per database)"}}
+        for r in reports:
+            r["vector_db"].close()
+        return out
+
+    guarded("config2_year_dbs_127_questions", config2)
+
+    # ---- config 5: N x N cosine statistics, N = 200k x 1024 ----
+    def config5():
+        m = 200_000
+        g = torch.Generator(device=dev).manual_seed(777)
+        x = torch.randn((m, d), generator=g, device=dev) * (0.5 + 1.5 * torch.rand((m, 1), generator=g, device=dev))
+        x = x.contiguous()
+        cosine.cosine_stats(x[:8192].contiguous())
+        times = []
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st = cosine.cosine_stats(x)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        dt = min(times)
+        useful = 2.0 * m * m * d / 2            # symmetry: each pair once
+        issued = 3.0 * useful                   # 3xTF32: three tf32 MMAs per product
+        peak = peaks.get("tf32_tflops")
+        return {"n": m, "seconds": dt, "stats": st,
+                "roofline": {"bound": "tensor", "achieved": issued / dt / 1e12, "peak": peak, "unit": "TFLOP/s",
+                             "frac": (issued / dt / 1e12 / peak if peak else None), "useful_fp32_equiv_tflops": useful / dt / 1e12,
+                             "flops_per_launch": issued, "peak_source": peaks.get("tf32_source"),
+                             "note": "tf32 MMA flops issued (3 per fp32-accurate product, upper triangle only) / wall time of the call"}}
+
+    guarded("config5_cosine_200k", config5)
+    return ex
 
 
 # --------------------------------------------------------------------------------------------------
@@ -264,7 +526,8 @@ def run_b200(args):
     if world > 1:  # corpus-global statistics, as an unsharded BM25Okapi would compute them
         dist.all_reduce(df)
         dist.all_reduce(tot)
-    idf, _ = synth.bm25_idf_from_df(df.cpu().numpy(), args.rows)
+    df_host = df.cpu().numpy()
+    idf, _ = synth.bm25_idf_from_df(df_host, args.rows)
     avgdl = float(tot.item()) / args.rows
     bm25 = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"],
                                    torch.from_numpy(idf).to(dev), avgdl, device=local_rank, weight_bits=args.bm25_weight_bits)
@@ -450,10 +713,25 @@ def run_b200(args):
             "top1_last_step": top1,
             "extras": extras,
         }
+        if world == 1 and not args.no_extras:
+            line["extras"].update(config_extras(args, flat, bm25, rows, df_host, dev, peak))
         if world == 1 and not args.no_cpu_baseline:
-            n_s = min(args.cpu_rows, hi - lo)
-            cb = cpu_baseline(args, 10, rows_sample=rows[:n_s].cpu().numpy())
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "threads", "port_vs_packages")}
+            # the dense leg at the FULL corpus size when the host can hold it (the rows come back from HBM, untimed)
+            n_s = hi - lo if args.cpu_rows <= 0 else min(args.cpu_rows, hi - lo)
+            fit = int(max(0.0, host_mem_available_gb() - 12.0) * 0.8 * 2**30 / (4.0 * args.dim))
+            n_s = min(n_s, max(fit, min(hi - lo, 1 << 20)))
+            rows_host = rows[:n_s].cpu().numpy()
+            cb = cpu_baseline(args, 10, rows_host=rows_host, budget_s=30.0)
+            del rows_host
+            line["cpu_baseline"] = {k: cb[k] for k in CB_KEYS}
+            ex = line["extras"]
+            line["vs_cpu_by_leg"] = {   # each leg of the step against the same leg on the host cores (both at the full corpus size)
+                "dense_all_cores": cb["parts"]["dense_ms_per_query_at_N"] / ex["dense_single_query"]["ms"],
+                "dense_1_thread": (None if cb["parts"]["dense_1thread_ms_per_query_at_N"] is None
+                                   else cb["parts"]["dense_1thread_ms_per_query_at_N"] / ex["dense_single_query"]["ms"]),
+                "bm25": (cb["parts"]["bm25_ms_per_query_at_N"] / ex["bm25_only_1_query"]["ms"]
+                         if "ms" in ex.get("bm25_only_1_query", {}) else None),
+                "note": "CPU ms per query at N (see cpu_baseline.extrapolation) / GPU ms per query of the same leg, device-timed"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -75,3 +75,75 @@ def bm25_scores_csr_ref(indptr, doc_ids, tf, doc_len, avgdl, idf, term_ids, k1=1
         f = tf[lo:hi].astype(np.int64)
         score[d] += idf[t] * (f * (k1 + 1) / (f + k1 * (1 - b + b * doc_len[d] / avgdl)))
     return score
+
+
+def token_corpus_arrays_np(n_docs, vocab=50_000, seed=4242, mean_len=120.0, sigma=0.5):
+    """The synthetic token corpus of SURVEY 8d (Zipf(1.0) ranks, lognormal lengths clipped to [8, 512]) as flat
+    arrays — (ranks int32[total], lens int64[n_docs]) — generated vectorised so that a million documents take
+    seconds, not minutes.  Same law as rag_challenge_2_b200.synth.token_corpus_np, not the same random stream."""
+    rng = np.random.default_rng(seed)
+    w = 1.0 / np.arange(1, vocab + 1, dtype=np.float64)
+    cdf = np.cumsum(w / w.sum())
+    lens = np.clip(np.rint(rng.lognormal(math.log(mean_len), sigma, n_docs)), 8, 512).astype(np.int64)
+    total = int(lens.sum())
+    ranks = np.empty(total, dtype=np.int32)
+    step = 1 << 24
+    for lo in range(0, total, step):
+        hi = min(total, lo + step)
+        ranks[lo:hi] = np.minimum(np.searchsorted(cdf, rng.random(hi - lo), side="left"), vocab - 1)
+    return ranks, lens
+
+
+def bm25_ref_from_arrays(ranks, lens, vocab, k1=1.5, b=0.75, epsilon=0.25):
+    """A BM25OkapiRef — the rank_bm25 structure itself: one {token: tf} dict per document, idf dict, doc_len list —
+    built from the flat arrays above without the per-token Python loop of __init__ (that loop is not what the
+    bench times; get_scores, the per-query loop over the dictionaries, is).  Tokens are the strings "t<rank>";
+    the statistics are computed exactly as __init__ computes them (first-seen term order for the idf average)."""
+    n_docs = int(lens.shape[0])
+    names = [f"t{r}" for r in range(vocab)]
+    doc_of = np.repeat(np.arange(n_docs, dtype=np.int64), lens)
+    key = doc_of * vocab + ranks
+    # first position of every term: fancy assignment keeps the LAST value written to a repeated index, so writing the
+    # positions in descending order leaves the first occurrence
+    first_seen = np.full(vocab, np.iinfo(np.int64).max, dtype=np.int64)
+    first_seen[ranks[::-1]] = np.arange(len(ranks) - 1, -1, -1, dtype=np.int64)
+    del doc_of
+    key.sort()
+    new = np.empty(key.shape[0], dtype=bool)
+    new[0] = True
+    np.not_equal(key[1:], key[:-1], out=new[1:])
+    idx = np.flatnonzero(new)
+    tfs = np.diff(np.r_[idx, key.shape[0]])
+    uniq = key[idx]
+    del key, new, idx
+    docs = uniq // vocab
+    terms = (uniq - docs * vocab).astype(np.int64)
+    del uniq
+    bounds = np.zeros(n_docs + 1, dtype=np.int64)
+    np.cumsum(np.bincount(docs, minlength=n_docs), out=bounds[1:])
+    self = BM25OkapiRef.__new__(BM25OkapiRef)
+    self.k1, self.b, self.epsilon = k1, b, epsilon
+    self.corpus_size = n_docs
+    self.doc_len = lens.tolist()
+    self.avgdl = int(lens.sum()) / n_docs
+    tl, fl, bl = terms.tolist(), tfs.tolist(), bounds.tolist()
+    getname = names.__getitem__
+    self.doc_freqs = [dict(zip(map(getname, tl[bl[i]:bl[i + 1]]), fl[bl[i]:bl[i + 1]])) for i in range(n_docs)]
+    df = np.bincount(terms, minlength=vocab)
+    present = np.flatnonzero(df > 0)
+    present = present[np.argsort(first_seen[present], kind="stable")]   # dict insertion order of rank_bm25's nd
+    self.nd = {names[t]: int(df[t]) for t in present.tolist()}
+    self.idf = {}
+    idf_sum = 0
+    negative = []
+    for word, freq in self.nd.items():
+        idf = math.log(self.corpus_size - freq + 0.5) - math.log(freq + 0.5)
+        self.idf[word] = idf
+        idf_sum += idf
+        if idf < 0:
+            negative.append(word)
+    self.average_idf = idf_sum / len(self.idf)
+    eps = self.epsilon * self.average_idf
+    for word in negative:
+        self.idf[word] = eps
+    return self

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                          "--rows", "100000", "--cpu-rows", "20000", "--cpu-docs", "1500"], capture_output=True, text=True,
+                          "--rows", "100000", "--cpu-rows", "20000", "--ref-docs", "10000"], capture_output=True, text=True,
                          timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
@@ -24,7 +24,13 @@ def test_reference_arm_json_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "extrapolated" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "MEASURED on 10000 documents" in cb["sample"]
+    # the extrapolation from the sample to the corpus is stated per leg, and the per-leg times add up to the value
+    assert cb["extrapolation"]["dense_factor"] == 5.0 and cb["extrapolation"]["bm25_factor"] == 10.0
+    parts = cb["parts"]
+    total_ms = parts["dense_ms_per_query_at_N"] + parts["bm25_ms_per_query_at_N"] + parts["fusion_ms"]
+    assert abs(total_ms - 1e3 / d["value"]) < 1e-6 * total_ms and parts["dense_1thread_ms_per_query_at_N"] > 0
+    assert cb["measured_ms_per_query_on_sample"] < total_ms and cb["queries_timed"] == d["timed_steps"] == 2
     assert abs(d["ms_per_step"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step"]
 
 

@@ -147,7 +147,8 @@ def _bm25_reference_scores(corpus, terms, k1=1.5, b=0.75):
     post, idf, avgdl = corpus["post"], corpus["idf"], corpus["avgdl"]
     score = torch.zeros(N, dtype=torch.float64, device=corpus["dev"])
     dl = post["doc_len"]
-    for t in terms:
+    avgdl = torch.tensor(avgdl, dtype=torch.float64, device=corpus["dev"])   # a tensor: torch turns division by a Python
+    for t in terms:                                                           # scalar into a multiplication by 1/x
         lo, hi = int(post["indptr"][t]), int(post["indptr"][t + 1])
         d = post["doc_ids"][lo:hi].long()
         f = post["tf"][lo:hi].double()
