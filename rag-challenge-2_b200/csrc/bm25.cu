@@ -69,6 +69,11 @@ __device__ __forceinline__ long long lower_bound_i32(const int* __restrict__ ids
   return lo;
 }
 
+// A kernel launched BESIDE its predecessor (programmatic stream serialization) never needs that grid's data, but the
+// kernels that follow in the stream (merge, fusion) rely on "after BM25" meaning "after the scan too".  Waiting on the
+// previous grid just before exiting makes that ordering explicit (a no-op for an ordinary launch).
+__device__ __forceinline__ void pdl_wait_for_previous_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <class W>
 struct Bm25Args {
   const long long* indptr;
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(kBm25Warps * 32) bm25_kernel(const Bm25Args<W>
 
   if (a.dense) {
     for (int i = tid; i < nb; i += nt) a.dense[lo + i] = acc[i];
+    pdl_wait_for_previous_grid();
     return;
   }
 
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(kBm25Warps * 32) bm25_kernel(const Bm25Args<W>
     *s_last = (t == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
+  pdl_wait_for_previous_grid();
   if (*s_last == 0) return;
   __threadfence();
   // last CTA of this query: the accumulator area becomes the select scratch
@@ -257,6 +264,22 @@ __device__ __forceinline__ void mbar_wait_wd(u64* bar, u32 parity) {
 
 // barrier over the 256 consumer threads of the streaming kernel (the producer warp never joins)
 __device__ __forceinline__ void named_bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// OR-reduction over the 256 consumer threads in ONE named barrier
+__device__ __forceinline__ bool named_bar_red_or_256(bool pred) {
+  u32 out;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "barrier.red.or.pred p, 1, 256, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(out)
+      : "r"(static_cast<u32>(pred))
+      : "memory");
+  return out != 0;
+}
 
 // bitonic sort (descending) by the 256 consumer threads; n is a power of two
 template <class K>
@@ -485,6 +508,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
         }
       }
     }
+    pdl_wait_for_previous_grid();
     return;
   }
 
@@ -551,6 +575,13 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
       acc[dcl] = 0.0;  // ready for the next item (this thread is the only reader of these entries)
       if (dcl < nb && sk[i] >= taug) act |= 1u << i;
     }
+    u128* dst = a.partial + (static_cast<size_t>(ql) * a.n_blocks + b) * k;
+    // ONE barrier decides the usual case (after the first wave of a query no document of a block reaches tau_g): it
+    // also orders this item's accumulator reads / clears before the next item's updates
+    if (!named_bar_red_or_256(act != 0u)) {
+      for (int i = ct; i < k; i += 256) dst[i] = 0;
+      continue;
+    }
     if (ct == 0) {
       s_cnt[0] = 0;
       s_cnt[1] = 0;
@@ -561,12 +592,6 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
       if (lane == 0 && c) atomicAdd(&s_cnt[0], c);
     }
     named_bar_sync_256();
-    u128* dst = a.partial + (static_cast<size_t>(ql) * a.n_blocks + b) * k;
-    if (s_cnt[0] == 0) {  // no document of this block can enter the query's top k (usual after the first wave)
-      for (int i = ct; i < k; i += 256) dst[i] = 0;
-      named_bar_sync_256();
-      continue;
-    }
     int need = min(k, static_cast<int>(s_cnt[0]));
     int live = static_cast<int>(s_cnt[0]);
     // narrow the live set by histogram levels until what is left fits the list
@@ -706,6 +731,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
     }
     named_bar_sync_256();  // the list area is reused by the next item
   }
+  pdl_wait_for_previous_grid();
 }
 
 // one CTA per query: merge the per-block lists of the streaming kernel into the query's top k, reset its threshold.
@@ -821,8 +847,19 @@ struct b2r_bm25 {
   int num_sms = 148;
   std::mutex mu;
   std::map<cudaStream_t, Bm25Ws> stream_ws;
-  cudaStream_t host_stream = nullptr;
-  std::mutex host_mu;  // host entry points are serialised per handle
+  // Host entry points are re-entrant: every call borrows a "lane" (its own stream, grow-only device + pinned
+  // staging, and — through stream_ws — its own kernel workspace), so concurrent callers of one index run
+  // concurrently (the reference calls one index from a thread pool, src/retrieval.py:1498-1504) and no call pays a
+  // cudaMalloc.  host_mu only guards the free list.
+  struct HostLane {
+    cudaStream_t stream = nullptr;
+    unsigned char* dev = nullptr;
+    unsigned char* pin = nullptr;
+    size_t cap = 0;
+  };
+  std::vector<HostLane*> free_lanes;
+  std::vector<HostLane*> all_lanes;
+  std::mutex host_mu;
 };
 
 namespace b2r {
@@ -830,6 +867,51 @@ namespace b2r {
 static const size_t kBm25WsBytes = static_cast<size_t>(256) << 20;  // partial lists + tickets + thresholds
 static const size_t kBm25CtlBytes = 64 * 1024;                      // tickets[<=4096] + tau_g[<=4096]
 static const int kBm25MaxQPerLaunch = 4096;
+
+static int bm25_lane_acquire(b2r_bm25* h, size_t bytes, b2r_bm25::HostLane** out) {
+  b2r_bm25::HostLane* lane = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    if (!h->free_lanes.empty()) {
+      lane = h->free_lanes.back();
+      h->free_lanes.pop_back();
+    }
+  }
+  if (!lane) {
+    lane = new b2r_bm25::HostLane();
+    cudaError_t e = cudaStreamCreateWithFlags(&lane->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      delete lane;
+      return fail(B2R_ERR_CUDA, std::string("bm25: cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    h->all_lanes.push_back(lane);
+  }
+  if (lane->cap < bytes) {
+    if (lane->dev) cudaFree(lane->dev);
+    if (lane->pin) cudaFreeHost(lane->pin);
+    lane->dev = lane->pin = nullptr;
+    lane->cap = 0;
+    const size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+    cudaError_t e = cudaMalloc(&lane->dev, cap);
+    if (e == cudaSuccess) e = cudaMallocHost(&lane->pin, cap);
+    if (e != cudaSuccess) {
+      if (lane->dev) cudaFree(lane->dev);
+      lane->dev = nullptr;
+      std::lock_guard<std::mutex> lock(h->host_mu);
+      h->free_lanes.push_back(lane);
+      return fail(e == cudaErrorMemoryAllocation ? B2R_ERR_NOMEM : B2R_ERR_CUDA, std::string("bm25: staging: ") + cudaGetErrorString(e));
+    }
+    lane->cap = cap;
+  }
+  *out = lane;
+  return B2R_OK;
+}
+
+static void bm25_lane_release(b2r_bm25* h, b2r_bm25::HostLane* lane) {
+  std::lock_guard<std::mutex> lock(h->host_mu);
+  h->free_lanes.push_back(lane);
+}
 
 static int bm25_get_ws(b2r_bm25* h, cudaStream_t stream, Bm25Ws* out) {
   std::lock_guard<std::mutex> lock(h->mu);
@@ -923,7 +1005,8 @@ static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<W> a, cudaStream_t str
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const long long n_items = static_cast<long long>(a.nq_launch) * a.n_blocks;
-  const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024))));
+  int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024))));
+  if (tunable("bm25.ctas_per_sm") > 0) per_sm = std::min(per_sm, tunable("bm25.ctas_per_sm"));
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_items, static_cast<long long>(h->num_sms) * per_sm)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -1143,7 +1226,6 @@ int b2r_bm25_create_ex(int64_t n_docs, int32_t n_terms, const int64_t* indptr, c
       }
     }
   }
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     const int code = e == cudaErrorMemoryAllocation ? B2R_ERR_NOMEM : B2R_ERR_CUDA;
     std::string msg = std::string("b2r_bm25_create: ") + cudaGetErrorString(e);
@@ -1217,30 +1299,31 @@ int b2r_bm25_topk_host(b2r_bm25* h, const int32_t* term_ids, const int32_t* term
   if (rc) return rc;
   DeviceGuard g(h->device);
   if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_bm25_topk: cudaSetDevice failed");
-  std::lock_guard<std::mutex> lock(h->host_mu);
   const size_t nk = static_cast<size_t>(nq) * k;
-  int *t_dev = nullptr, *o_dev = nullptr;
-  double* S_dev = nullptr;
-  long long* I_dev = nullptr;
-  cudaStream_t st = h->host_stream;
-  cudaError_t e = cudaMalloc(&t_dev, std::max<size_t>(1, n_terms_total) * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&o_dev, (static_cast<size_t>(nq) + 1) * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&S_dev, nk * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&I_dev, nk * sizeof(long long));
-  if (e == cudaSuccess && n_terms_total) e = cudaMemcpyAsync(t_dev, term_ids, static_cast<size_t>(n_terms_total) * sizeof(int), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(o_dev, term_offsets, (static_cast<size_t>(nq) + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
+  // staging layout (device and pinned alike): [S f64 nk][I i64 nk][offsets i32 nq+1][term ids i32]
+  const size_t off_o = nk * 16, off_t = off_o + ((static_cast<size_t>(nq) + 1) * 4 + 15) / 16 * 16;
+  const size_t in_bytes = off_t + static_cast<size_t>(std::max(n_terms_total, 1)) * 4 - off_o;
+  b2r_bm25::HostLane* lane = nullptr;
+  rc = bm25_lane_acquire(h, off_o + in_bytes, &lane);
+  if (rc) return rc;
+  cudaStream_t st = lane->stream;
+  memcpy(lane->pin + off_o, term_offsets, (static_cast<size_t>(nq) + 1) * 4);
+  if (n_terms_total) memcpy(lane->pin + off_t, term_ids, static_cast<size_t>(n_terms_total) * 4);
+  cudaError_t e = cudaMemcpyAsync(lane->dev + off_o, lane->pin + off_o, in_bytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
-    rc = bm25_run(h, t_dev, o_dev, nq, k, S_dev, I_dev, 0, nullptr, st);
+    rc = bm25_run(h, reinterpret_cast<const int*>(lane->dev + off_t), reinterpret_cast<const int*>(lane->dev + off_o), nq, k,
+                  reinterpret_cast<double*>(lane->dev), reinterpret_cast<long long*>(lane->dev + nk * 8), 0, nullptr, st);
     if (rc == B2R_OK) {
-      e = cudaMemcpyAsync(S, S_dev, nk * sizeof(double), cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(I, I_dev, nk * sizeof(long long), cudaMemcpyDeviceToHost, st);
+      e = cudaMemcpyAsync(lane->pin, lane->dev, nk * 16, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) {
+        memcpy(S, lane->pin, nk * 8);
+        memcpy(I, lane->pin + nk * 8, nk * 8);
+      }
     }
   }
-  cudaFree(t_dev);
-  cudaFree(o_dev);
-  cudaFree(S_dev);
-  cudaFree(I_dev);
+  if (e != cudaSuccess) cudaStreamSynchronize(st);  // nothing may still be using the lane when it goes back
+  bm25_lane_release(h, lane);
   if (rc == B2R_OK && e != cudaSuccess) rc = fail(B2R_ERR_CUDA, std::string("b2r_bm25_topk_host: ") + cudaGetErrorString(e));
   return rc;
 }
@@ -1252,26 +1335,28 @@ int b2r_bm25_scores_host(b2r_bm25* h, const int32_t* term_ids, int n_q_terms, do
   if (rc) return rc;
   DeviceGuard g(h->device);
   if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_bm25_scores: cudaSetDevice failed");
-  std::lock_guard<std::mutex> lock(h->host_mu);
-  int *t_dev = nullptr, *o_dev = nullptr;
-  double* dense = nullptr;
-  cudaStream_t st = h->host_stream;
+  // staging: [dense f64 n_docs][offsets i32 x 2 (16 B)][term ids]; the scores come back through the pinned half
+  const size_t off_o = static_cast<size_t>(h->n_docs) * 8, off_t = off_o + 16;
+  const size_t in_bytes = 16 + static_cast<size_t>(std::max(n_q_terms, 1)) * 4;
+  b2r_bm25::HostLane* lane = nullptr;
+  rc = bm25_lane_acquire(h, off_o + in_bytes, &lane);
+  if (rc) return rc;
+  cudaStream_t st = lane->stream;
   const int offs[2] = {0, n_q_terms};
-  cudaError_t e = cudaMalloc(&t_dev, std::max<size_t>(1, n_q_terms) * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&o_dev, 2 * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&dense, static_cast<size_t>(h->n_docs) * sizeof(double));
-  if (e == cudaSuccess && n_q_terms) e = cudaMemcpyAsync(t_dev, term_ids, static_cast<size_t>(n_q_terms) * sizeof(int), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(o_dev, offs, sizeof(offs), cudaMemcpyHostToDevice, st);
+  memcpy(lane->pin + off_o, offs, sizeof(offs));
+  if (n_q_terms) memcpy(lane->pin + off_t, term_ids, static_cast<size_t>(n_q_terms) * 4);
+  cudaError_t e = cudaMemcpyAsync(lane->dev + off_o, lane->pin + off_o, in_bytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
-    rc = bm25_run(h, t_dev, o_dev, 1, 1, nullptr, nullptr, 0, dense, st);
+    rc = bm25_run(h, reinterpret_cast<const int*>(lane->dev + off_t), reinterpret_cast<const int*>(lane->dev + off_o), 1, 1,
+                  nullptr, nullptr, 0, reinterpret_cast<double*>(lane->dev), st);
     if (rc == B2R_OK) {
-      e = cudaMemcpyAsync(scores, dense, static_cast<size_t>(h->n_docs) * sizeof(double), cudaMemcpyDeviceToHost, st);
+      e = cudaMemcpyAsync(lane->pin, lane->dev, off_o, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) memcpy(scores, lane->pin, off_o);
     }
   }
-  cudaFree(t_dev);
-  cudaFree(o_dev);
-  cudaFree(dense);
+  if (e != cudaSuccess) cudaStreamSynchronize(st);
+  bm25_lane_release(h, lane);
   if (rc == B2R_OK && e != cudaSuccess) rc = fail(B2R_ERR_CUDA, std::string("b2r_bm25_scores_host: ") + cudaGetErrorString(e));
   return rc;
 }
@@ -1288,7 +1373,12 @@ int b2r_bm25_destroy(b2r_bm25* h) {
   if (h->weight) cudaFree(h->weight);
   if (h->idf) cudaFree(h->idf);
   if (h->skip) cudaFree(h->skip);
-  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  for (b2r_bm25::HostLane* lane : h->all_lanes) {
+    if (lane->dev) cudaFree(lane->dev);
+    if (lane->pin) cudaFreeHost(lane->pin);
+    if (lane->stream) cudaStreamDestroy(lane->stream);
+    delete lane;
+  }
   delete h;
   return B2R_OK;
 }

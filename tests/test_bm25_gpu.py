@@ -312,3 +312,35 @@ def test_index_build_from_token_ids_on_gpu(b2r):
     S0, I0 = host.topk(queries, 30)
     S1, I1 = dev.topk(queries, 30)
     assert np.array_equal(I0, I1) and np.array_equal(S0, S1)
+
+
+def test_concurrent_host_callers_share_one_index(b2r):
+    """The reference calls one index object from a thread pool (src/retrieval.py:1498-1504): host entry points are
+    re-entrant (one lane — stream, staging, workspace — per concurrent caller) and every caller gets its own answer."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    docs = s.token_corpus_np(30000, vocab=3000, seed=21)
+    idx = BM25Okapi(docs)
+    queries = [as_tokens(q) for q in s.token_queries_np(48, vocab=3000, seed=22)]
+    want = [idx.topk([q], 20) for q in queries]
+    want_scores = idx.get_scores(queries[0])
+
+    def work(i):
+        if i % 7 == 0:
+            return ("scores", idx.get_scores(queries[0]))
+        q = queries[i % len(queries)]
+        return ("topk", i % len(queries), idx.topk([q, q], 20))
+
+    with ThreadPoolExecutor(max_workers=12) as pool:
+        results = list(pool.map(work, range(240)))
+    for r in results:
+        if r[0] == "scores":
+            assert np.array_equal(r[1], want_scores)
+        else:
+            S, I = r[2]
+            Sw, Iw = want[r[1]]
+            assert np.array_equal(S[0], Sw[0]) and np.array_equal(I[0], Iw[0])
+            assert np.array_equal(S[1], Sw[0]) and np.array_equal(I[1], Iw[0])

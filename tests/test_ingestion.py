@@ -83,3 +83,54 @@ def test_ingestors_write_what_the_reference_writes(tmp_path):
         mk.corpus.COMPANY, "gross margin revenue 2024", top_n=5, selected_years=[2024])
     assert got == want
     R.clear_resident_cache()
+
+
+def test_ixfi_bytes_follow_the_field_order_of_faiss_index_write(tmp_path):
+    """`.faiss` layout of an IndexFlatIP, derived field by field from faiss 1.9's `impl/index_write.cpp` (the package is not
+    installable here, so this is the byte-level vector instead of a real file):
+        write_index(): IndexFlat branch   -> WRITE1(fourcc("IxFI"))            4 bytes, the characters in order
+        write_index_header(): WRITE1(d)            `int`                        4 bytes LE
+                              WRITE1(ntotal)       `idx_t` = int64              8
+                              WRITE1(dummy) x 2    `idx_t` = 1 << 20            8 + 8
+                              WRITE1(is_trained)   `bool`                       1
+                              WRITE1(metric_type)  `MetricType` enum (int), METRIC_INNER_PRODUCT = 0   4
+                              (metric_arg only when metric_type > 1: not for IP)
+        WRITEXBVECTOR(codes): size_t size = codes.size() / 4 (codes are the rows' bytes) -> number of float32   8
+                              then the raw bytes                                  4 * ntotal * d
+    i.e. a 45-byte prologue — the well-known size of flat faiss files, 45 + 4 * ntotal * d (a 1M x 128 IndexFlat is
+    512,000,045 bytes).  The expected bytes below are spelled out by hand, not produced by the module's struct string."""
+    import numpy as np
+
+    from rag_challenge_2_b200 import flat_index
+
+    class Rows:                                  # what write_index needs from an index: d, ntotal, reconstruct_n
+        d, ntotal = 3, 2
+        data = np.array([[1.0, -2.0, 0.5], [0.25, 3.0, -0.125]], dtype=np.float32)
+
+        def reconstruct_n(self, lo, n):
+            return self.data[lo: lo + n]
+
+    path = tmp_path / "two_rows.faiss"
+    flat_index.write_index(Rows(), path)
+    blob = path.read_bytes()
+    expected = (b"IxFI"
+                + bytes([3, 0, 0, 0])                                 # d
+                + bytes([2, 0, 0, 0, 0, 0, 0, 0])                     # ntotal
+                + bytes([0, 0, 0x10, 0, 0, 0, 0, 0]) * 2              # the two dummies, 1 << 20
+                + bytes([1])                                          # is_trained
+                + bytes([0, 0, 0, 0])                                 # METRIC_INNER_PRODUCT
+                + bytes([6, 0, 0, 0, 0, 0, 0, 0])                     # codes.size() / 4 = ntotal * d floats
+                + bytes.fromhex("0000803f" "000000c0" "0000003f" "0000803e" "00004040" "000000be"))
+    assert blob == expected and len(blob) == 45 + 4 * 2 * 3
+    d, rows = flat_index.read_index_rows(path)
+    assert d == 3 and np.array_equal(rows, Rows.data)
+    assert np.array_equal(stubs.read_ixfi(path).rows, Rows.data)
+    # an L2 flat index ("IxF2", metric 1) or a truncated file is refused, not misread
+    with open(tmp_path / "l2.faiss", "wb") as f:
+        f.write(b"IxF2" + expected[4:])
+    with pytest.raises(RuntimeError):
+        flat_index.read_index_rows(tmp_path / "l2.faiss")
+    with open(tmp_path / "short.faiss", "wb") as f:
+        f.write(expected[:-4])
+    with pytest.raises(RuntimeError):
+        flat_index.read_index_rows(tmp_path / "short.faiss")

@@ -20,7 +20,7 @@ dev = torch.device("cuda", 0)
 post = synth.token_postings_torch(0, n, 50_000, dev)
 idf, _ = synth.bm25_idf_from_df(post["df"].cpu().numpy(), n)
 bm = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"], torch.from_numpy(idf).to(dev),
-                             post["total_len"] / n, device=0)
+                             post["total_len"] / n, device=0, weight_bits=int(os.environ.get("B2R_BM25_BITS", "32")))
 df = post["df"].cpu().numpy()
 pool = synth.token_queries_np(64, vocab=50_000, seed=4243)
 batches = []
@@ -44,4 +44,5 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / (reps * len(batches))
 postings = sum(b[2] for b in batches) / len(batches)
 print(json.dumps({"n_docs": n, "nq": nq, "ms_per_launch": round(ms, 4), "postings_per_launch": int(postings),
-                  "GBps": round(postings * 8 / ms / 1e6, 1), "tunables": sys.argv[3:]}), flush=True)
+                  "GBps": round(postings * (4 + bm.n_postings()[1] // 8) / ms / 1e6, 1), "weight_bits": bm.n_postings()[1],
+                  "tunables": sys.argv[3:]}), flush=True)
