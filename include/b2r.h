@@ -40,6 +40,7 @@ extern "C" {
 #define B2R_ERR_UNSUPPORTED (-4) /* valid request outside what the kernels implement          */
 
 #define B2R_MAX_K 1024 /* largest k of the fused select (faiss-gpu caps at 2048)          */
+#define B2R_LAUNCH_OVERLAP_PREVIOUS 1u /* launch flag of the *_ex entry points, see b2r_flat_search_dev_ex */
 
 typedef struct b2r_flat b2r_flat; /* exact inner-product index  == faiss.IndexFlatIP          */
 typedef struct b2r_bm25 b2r_bm25; /* BM25Okapi postings index   == rank_bm25.BM25Okapi        */
@@ -74,6 +75,16 @@ int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, i
  * enqueued on `stream`.  id_offset is added to every valid id (global id of a row shard). */
 int b2r_flat_search_dev(b2r_flat* h, const float* q_dev, int nq, int k, float* D_dev,
                         int64_t* I_dev, int64_t id_offset, void* stream);
+/* Same, with launch flags.  B2R_LAUNCH_OVERLAP_PREVIOUS (defined below): a search of one or two queries (the scan
+ * kernel) is launched with programmatic stream serialization — its pass over the rows may start while the previous
+ * kernel of `stream` is still finishing, once that kernel has issued griddepcontrol.launch_dependents (this library's
+ * fusion / exchange kernels do so at their start; any other kernel releases it by exiting, i.e. ordinary stream
+ * order).  The scan writes nothing before the previous kernel has completed (griddepcontrol.wait ahead of its
+ * epilogue), so D_dev / I_dev and the workspace may be the ones that kernel still reads; q_dev must have been
+ * complete when the previous kernel STARTED.  A stream of hybrid steps uses this to hide the fusion / exchange kernel
+ * of step s — including its wait for the slowest rank — behind the first tiles of step s + 1. */
+int b2r_flat_search_dev_ex(b2r_flat* h, const float* q_dev, int nq, int k, float* D_dev,
+                           int64_t* I_dev, int64_t id_offset, void* stream, unsigned flags);
 /* index.reconstruct(i) / index.reconstruct_batch(ids)    src/retrieval.py:573;
  * generate_similarity_matrix.py:61.  out is host float32[m,d]; any id outside [0,ntotal)
  * fails with B2R_ERR_INVALID (faiss raises; the reference catches it, :574-576). */
@@ -143,7 +154,9 @@ int b2r_bm25_topk_dev(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* t
  * running (the flat scan kernels issue griddepcontrol.launch_dependents at their start; any other kernel
  * releases it when it exits, i.e. ordinary stream order).  Only for work that does not read what the previous
  * kernel writes — the hybrid path launches BM25 this way right behind the dense scan. */
+#ifndef B2R_LAUNCH_OVERLAP_PREVIOUS
 #define B2R_LAUNCH_OVERLAP_PREVIOUS 1u
+#endif
 int b2r_bm25_topk_dev_ex(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* term_offsets_dev,
                          const int32_t* term_offsets_host, int nq, int k, double* S_dev,
                          int64_t* I_dev, int64_t id_offset, void* stream, unsigned flags);

@@ -169,9 +169,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
   } else {
     // ======================= epilogue warps (both CTAs): statistics of the tile =======================
     // Warps 2-9: warp w reads TMEM lane quadrant w % 4 (a hardware rule) and one half of the 128 columns, so two
-    // warps share a quadrant.  Per 16-column chunk the sum and the sum of squares are formed in fp32 and added to the
-    // float64 totals once; interior tiles (every row below every column, all inside the matrix and the column range)
-    // skip the per-element masks.
+    // warps share a quadrant.  Per 16-column chunk the sum and the sum of squares are formed in fp32 (same order as
+    // before the drain / statistics split: results are unchanged) and added to the float64 totals once; interior tiles
+    // (every row below every column, all inside the matrix and the column range) skip the per-element masks.
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;  // 0: columns 0-63, 1: columns 64-127
     u32 ph_t = 0;
@@ -190,7 +190,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
       mbar_wait_cluster_tag(tm_full, ph_t, 700);
       tc_fence_after();
       const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(half * (N / 2));
-#pragma unroll 1
+      // (1) drain: this warp's 32 lanes x 64 columns of the four accumulators are combined into 64 registers per thread
+      // and the accumulators are handed back at once — the MMAs of the NEXT tile run while (2) does the statistics.
+      // (The accumulators fill all 512 TMEM columns, so they cannot be double-buffered in TMEM; registers can.)
+      float v[N / 2];
+#pragma unroll
       for (int c0 = 0; c0 < N / 2; c0 += 16) {
         float m0[16], m1[16], s0[16], s1[16];
         tc_ld16(taddr + c0, m0);
@@ -200,25 +204,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
           tc_ld16(taddr + 3 * N + c0, s1);
         }
         tc_wait_ld();
-        if (c0 + 16 >= N / 2) {  // this warp has read its part of the tile
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tm_empty, 0);
-        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[c0 + i] = (n_slabs > 1) ? (m0[i] + m1[i]) + (s0[i] + s1[i]) : m0[i] + s0[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tm_empty, 0);
+      // (2) statistics from registers
+#pragma unroll
+      for (int c0 = 0; c0 < N / 2; c0 += 16) {
         float csum = 0.f, csq = 0.f;
         int ccnt = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const long long col = col_base + half * (N / 2) + c0 + i;
           if (interior || (row < a.n && col < a.n && row < col && col >= a.col_lo && col < a.col_hi)) {
-            const float sc = (n_slabs > 1) ? (m0[i] + m1[i]) + (s0[i] + s1[i]) : m0[i] + s0[i];
-            const float v = fminf(1.0f, fmaxf(-1.0f, sc));
-            csum += v;
-            csq = fmaf(v, v, csq);
-            st_min = fminf(st_min, v);
-            st_max = fmaxf(st_max, v);
+            const float vv = fminf(1.0f, fmaxf(-1.0f, v[c0 + i]));
+            csum += vv;
+            csq = fmaf(vv, vv, csq);
+            st_min = fminf(st_min, vv);
+            st_max = fmaxf(st_max, vv);
             ++ccnt;
-            const int bin = min(static_cast<int>((v + 1.0f) * scale), last_bin);
+            const int bin = min(static_cast<int>((vv + 1.0f) * scale), last_bin);
             atomicAdd(&hist_s[bin], 1u);
           }
         }

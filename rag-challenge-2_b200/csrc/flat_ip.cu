@@ -306,6 +306,9 @@ __global__ void __launch_bounds__((CW + 1) * 32) flat_scan_tma_kernel(const Scan
       for (int i = cnt[qi] + lane; i < a.cap; i += 32) list[i] = 0;
     }
   }
+  // launched beside the tail of the previous kernel (B2R_LAUNCH_OVERLAP_PREVIOUS): nothing has been written so far;
+  // everything below writes workspace / results, so the previous kernel must have completed (no-op otherwise)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   // the stage ring is idle now (every issued copy was consumed): reuse it as select scratch
   scan_epilogue<NQ>(a, cand, CW, reinterpret_cast<u64*>(smem_raw), ctl);
@@ -383,6 +386,7 @@ __global__ void __launch_bounds__(NW * 32) flat_scan_generic_kernel(const ScanAr
     u64* list = cand + (static_cast<size_t>(qi) * NW + warp) * a.cap;
     for (int i = cnt[qi] + lane; i < a.cap; i += 32) list[i] = 0;
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // see flat_scan_tma_kernel: results are written after the previous kernel
   __syncthreads();
   scan_epilogue<NQ>(a, cand, NW, sel_buf, ctl);
 }
@@ -519,23 +523,37 @@ struct ScanPlan {
   bool tma;
   int dv, nq, cw, stages, tile_rows, cap, sel_cap, grid, threads;
   size_t smem;
+  bool pdl = false;  // launch with programmatic stream serialization (B2R_LAUNCH_OVERLAP_PREVIOUS)
 };
+
+// Launch a scan kernel, optionally BESIDE the tail of the previous kernel of the stream: the scan's main loop only
+// reads the rows and the query; everything it writes (partial lists, ticket, D / I) is written by its epilogue, which
+// starts with griddepcontrol.wait — i.e. after the previous kernel has completed.  A stream of hybrid steps then
+// overlaps the fusion / exchange kernel of step s (including its wait for the slowest rank) and the launch latency
+// with the first tiles of step s + 1.
+template <class Kern>
+static int launch_scan(Kern kern, const ScanPlan& p, const ScanArgs& a, cudaStream_t stream) {
+  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
+  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.grid);
+  cfg.blockDim = dim3(p.threads);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  B2R_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  B2R_CUDA(cudaGetLastError());
+  return B2R_OK;
+}
 
 template <int DV, int NQ>
 static int launch_tma_cw(const ScanPlan& p, const ScanArgs& a, cudaStream_t stream) {
-  if (p.cw == 8) {
-    auto kern = flat_scan_tma_kernel<DV, NQ, 8>;
-    B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    kern<<<p.grid, p.threads, p.smem, stream>>>(a);
-  } else {
-    auto kern = flat_scan_tma_kernel<DV, NQ, 4>;
-    B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-    B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    kern<<<p.grid, p.threads, p.smem, stream>>>(a);
-  }
-  B2R_CUDA(cudaGetLastError());
-  return B2R_OK;
+  if (p.cw == 8) return launch_scan(flat_scan_tma_kernel<DV, NQ, 8>, p, a, stream);
+  return launch_scan(flat_scan_tma_kernel<DV, NQ, 4>, p, a, stream);
 }
 
 template <int DV>
@@ -561,12 +579,7 @@ static int launch_tma(const ScanPlan& p, const ScanArgs& a, cudaStream_t stream)
 
 template <int NQ>
 static int launch_generic_nq(const ScanPlan& p, const ScanArgs& a, cudaStream_t stream) {
-  auto kern = flat_scan_generic_kernel<NQ, 8>;
-  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p.smem)));
-  B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<p.grid, p.threads, p.smem, stream>>>(a);
-  B2R_CUDA(cudaGetLastError());
-  return B2R_OK;
+  return launch_scan(flat_scan_generic_kernel<NQ, 8>, p, a, stream);
 }
 
 static int launch_generic(const ScanPlan& p, const ScanArgs& a, cudaStream_t stream) {
@@ -671,7 +684,7 @@ static int make_plan(const b2r_flat* h, int nq_left, int k, ScanPlan* p) {
 }
 
 static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, float* D_dev, int64_t* I_dev,
-                                int64_t id_offset, cudaStream_t stream) {
+                                int64_t id_offset, cudaStream_t stream, unsigned flags = 0u) {
   launch_counter() = 0;
   if (nq == 0) return B2R_OK;
   if (h->n == 0) {
@@ -737,6 +750,8 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
     a.I = reinterpret_cast<long long*>(I_dev) + static_cast<size_t>(done) * k;
     a.id_offset = id_offset;
     a.sel_cap = p.sel_cap;
+    // only the first kernel of a call may overlap the caller's previous kernel (the tensor-core path never does)
+    p.pdl = (flags & B2R_LAUNCH_OVERLAP_PREVIOUS) != 0u && done == 0 && !use_gemm;
     rc = p.tma ? launch_tma(p, a, stream) : launch_generic(p, a, stream);
     if (rc) return rc;
     ++launch_counter();
@@ -900,6 +915,17 @@ int b2r_flat_search_dev(b2r_flat* h, const float* q_dev, int nq, int k, float* D
   DeviceGuard g(h->device);
   if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_flat_search: cudaSetDevice failed");
   return flat_search_dev_impl(h, q_dev, nq, k, D_dev, I_dev, id_offset, static_cast<cudaStream_t>(stream));
+}
+
+int b2r_flat_search_dev_ex(b2r_flat* h, const float* q_dev, int nq, int k, float* D_dev, int64_t* I_dev,
+                           int64_t id_offset, void* stream, unsigned flags) {
+  if (!h) return fail(B2R_ERR_INVALID, "b2r_flat_search: NULL handle");
+  if (nq < 0 || k < 1) return fail(B2R_ERR_INVALID, "b2r_flat_search: need nq >= 0 and k >= 1");
+  if (k > B2R_MAX_K) return fail(B2R_ERR_UNSUPPORTED, "b2r_flat_search: k > B2R_MAX_K (1024)");
+  if (nq > 0 && (!q_dev || !D_dev || !I_dev)) return fail(B2R_ERR_INVALID, "b2r_flat_search: NULL buffer");
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_flat_search: cudaSetDevice failed");
+  return flat_search_dev_impl(h, q_dev, nq, k, D_dev, I_dev, id_offset, static_cast<cudaStream_t>(stream), flags);
 }
 
 int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, int64_t* I) {

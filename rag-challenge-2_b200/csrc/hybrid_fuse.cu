@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(256) hybrid_fuse_kernel(const float* __restric
                                                           long long* __restrict__ O, unsigned char* __restrict__ M,
                                                           int buf_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // a scan launched behind this kernel with B2R_LAUNCH_OVERLAP_PREVIOUS (the next hybrid step) may start its pass
+  // over the rows now; it writes nothing before this kernel has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   u64* buf = reinterpret_cast<u64*>(smem_raw);             // [buf_cap] keys
   double* red = reinterpret_cast<double*>(buf + buf_cap);  // [2] min / max
   const size_t q = blockIdx.x;
@@ -154,6 +157,9 @@ __global__ void __launch_bounds__(256) hybrid_exchange_fuse_kernel(const float* 
                                                                    long long* __restrict__ O) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int timed_out;
+  // the next step's scan (B2R_LAUNCH_OVERLAP_PREVIOUS) may start now: this kernel's wait for the slowest rank then
+  // costs nothing, the fast ranks are already streaming their next query
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int q = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) timed_out = 0;
   const int parity = static_cast<int>(x.step & 1u);

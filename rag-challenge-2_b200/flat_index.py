@@ -95,10 +95,12 @@ class FlatIPIndex:
         _lib.check(self._lib.b2r_flat_search_host(self._h, _lib.ptr(x), nq, k, _lib.ptr(D), _lib.ptr(I)))
         return D, I
 
-    def search_dev(self, q, k, D=None, I=None, id_offset=0, stream=None):
+    def search_dev(self, q, k, D=None, I=None, id_offset=0, stream=None, overlap_previous=False):
         """Resident search: q is a float32 CUDA tensor [nq, d]; returns CUDA tensors (D, I).
 
         Enqueued on `stream` (default: torch's current stream); nothing is synchronised.
+        overlap_previous: B2R_LAUNCH_OVERLAP_PREVIOUS — the scan (one or two queries) may start while the previous
+        kernel of the stream is finishing; q must have been complete when that kernel started (see include/b2r.h).
         """
         import torch
 
@@ -114,9 +116,9 @@ class FlatIPIndex:
         if stream is None:
             stream = torch.cuda.current_stream(q.device).cuda_stream
         _lib.check(
-            self._lib.b2r_flat_search_dev(
+            self._lib.b2r_flat_search_dev_ex(
                 self._h, C.c_void_p(q.data_ptr()), nq, k, C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
-                int(id_offset), C.c_void_p(stream),
+                int(id_offset), C.c_void_p(stream), 1 if overlap_previous else 0,
             )
         )
         return D, I

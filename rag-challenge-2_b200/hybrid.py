@@ -153,6 +153,9 @@ class ShardedSearcher:
         self.side_stream = None  # "streams" mode: a torch.cuda.Stream for BM25
         self.scan_stream = None  # high-priority stream for the scan while BM25 runs beside it (see search_hybrid)
         self.peer_exchange = None  # set to a PeerExchange to replace all-gather + merges + fusion by one kernel
+        self.pipeline = False      # True: consecutive search_hybrid steps are chained by programmatic dependent launch —
+                                   # the scan of step s + 1 starts while the fusion / exchange kernel of step s finishes
+                                   # (its queries must be resident before step s is enqueued; see b2r_flat_search_dev_ex)
         self.launches = 0      # kernels of this library enqueued by the last call
         self.collectives = 0   # collectives enqueued by the last call
 
@@ -212,7 +215,7 @@ class ShardedSearcher:
             # scan CTA (one per SM, statically assigned tiles) holds its SM.  With two streams both kernels
             # become runnable at the same instant, two BM25 CTAs can take an SM before its scan CTA arrives,
             # and that CTA — hence the whole scan — is delayed by a BM25 lifetime (measured: +70 us per step).
-            D, I = self.local_dense(q, k)
+            D, I = self.local_dense(q, k, overlap_previous=True) if self.pipeline else self.local_dense(q, k)
             self.launches += self._last_dense_launches()
             S, J = self.local_bm25(term_ids, term_offsets, k, overlap_previous=True)
         elif side is not None:
@@ -272,8 +275,8 @@ class HybridIndex:
     def __init__(self, flat, bm25=None, offset=0, group=None, world_size=None, overlap="pdl", exchange="nccl"):
         self.flat, self.bm25, self.offset = flat, bm25, int(offset)
 
-        def local_dense(q, k):
-            return flat.search_dev(q, k, id_offset=self.offset)
+        def local_dense(q, k, overlap_previous=False):
+            return flat.search_dev(q, k, id_offset=self.offset, overlap_previous=overlap_previous)
 
         local_dense.last_launches = flat.last_launch_count
 

@@ -203,3 +203,51 @@ def test_exchange_kernel_emulated(b2r, world, k, step):
     assert np.array_equal(F.cpu().numpy(), Fr)
     out_flags = dev.cpu().numpy()[2 * world * slot:].view(np.uint32).reshape(2, world, nq_max)
     assert np.all(out_flags[parity, 0, :nq] == step)       # rank 0 published its own flags
+
+
+def test_chained_steps_equal_unchained(b2r):
+    """A stream of hybrid steps chained by programmatic dependent launch (the scan of step s + 1 starts while the fusion
+    kernel of step s finishes; searcher.pipeline) returns, step for step, what the same steps return one after the other —
+    with outputs allocated per step from torch's caching allocator, i.e. with step s + 1's buffers aliasing step s's."""
+    import torch
+
+    from rag_challenge_2_b200 import hybrid, synth
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    n, d, V, k = 300_000, 1024, 5000, 30
+    rows = synth.dense_rows_torch(0, n, d, "cuda")
+    post = synth.token_postings_torch(0, n, V, "cuda", seed=91)
+    idf, _ = synth.bm25_idf_from_df(post["df"].cpu().numpy(), n)
+    bm = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"], torch.from_numpy(idf).cuda(),
+                                 post["total_len"] / n)
+    index = hybrid.HybridIndex(b2r.FlatIPIndex.from_device_tensor(rows), bm, 0, world_size=1)
+    nsteps = 48
+    q = synth.dense_queries_torch(nsteps, d, "cuda", rows, seed=92)
+    toks = synth.token_queries_np(nsteps, vocab=V, seed=93)
+    staged = [(q[i: i + 1].contiguous(), torch.tensor(toks[i], dtype=torch.int32, device="cuda"),
+               torch.tensor([0, len(toks[i])], dtype=torch.int32, device="cuda")) for i in range(nsteps)]
+    torch.cuda.synchronize()
+
+    def run(pipeline):
+        index.searcher.pipeline = pipeline
+        out = []
+        for qi, ti, oi in staged:
+            F, O = index.search_hybrid_dev(qi, ti, oi, k)
+            out.append((F.clone(), O.clone()))      # clones are enqueued behind the step, the originals are freed at once
+        torch.cuda.synchronize()
+        return out
+
+    plain = run(False)
+    for _ in range(3):
+        chained = run(True)
+        for (F0, O0), (F1, O1) in zip(plain, chained):
+            assert torch.equal(O0, O1) and torch.equal(F0, F1)
+    # two queries per step take the same kernels (K1 with NQ = 2)
+    index.searcher.pipeline = True
+    t2 = torch.tensor(toks[0] + toks[1], dtype=torch.int32, device="cuda")
+    o2 = torch.tensor([0, len(toks[0]), len(toks[0]) + len(toks[1])], dtype=torch.int32, device="cuda")
+    for _ in range(4):
+        F2, O2 = index.search_hybrid_dev(q[:2].contiguous(), t2, o2, k)
+    torch.cuda.synchronize()
+    assert torch.equal(O2[0], plain[0][1][0]) and torch.equal(O2[1], plain[1][1][0])
+    index.close()
