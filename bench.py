@@ -50,6 +50,8 @@ def parse_args():
                     help="how BM25 runs beside the scan: programmatic dependent launch (one stream) or two streams")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="do not chain consecutive steps by programmatic dependent launch (each step then starts after the previous one's last kernel has finished)")
+    ap.add_argument("--fake-bm25", action="store_true",
+                    help="experiment (wrong results): BM25 launches nothing and returns one fixed list — what is left is scan + fusion")
     ap.add_argument("--no-scan-priority", action="store_true", help="scan on the caller's stream instead of a high-priority one (experiment)")
     ap.add_argument("--no-bm25-events", action="store_true", help="do not time the BM25 kernel inside the step (experiment)")
     ap.add_argument("--tunable", action="append", default=[], help="library tunable key=value (experiments)")
@@ -577,6 +579,10 @@ def run_b200(args):
     pipelined = pdl and not args.no_pipeline
     inner_dense = index.searcher.local_dense
     inner_bm25 = index.searcher.local_bm25
+    if args.fake_bm25:
+        S_fix, J_fix = inner_bm25(staged[0][1], staged[0][2], args.k)
+        torch.cuda.synchronize()
+        inner_bm25 = index.searcher.local_bm25 = (lambda t, o, k, **kw: (S_fix, J_fix))
 
     def sync_all():
         torch.cuda.synchronize()

@@ -207,6 +207,22 @@ int b2r_hybrid_search_host(b2r_hybrid_ctx* ctx, b2r_flat* flat, b2r_bm25* bm25, 
                            void* const* peer_bufs, int rank, int world, int nq_max, int k_max, uint32_t step,
                            float* F, int64_t* O);
 
+/* The same step with everything resident (device pointers; enqueued on `stream`, nothing synchronised): the dense scan
+ * and BM25 launched beside it; for up to 4 queries and k <= 256 the LAST CTA of each query's BM25 grid waits for the
+ * scan (griddepcontrol.wait) and fuses — or, world > 1, exchanges + merges + fuses over peer_bufs — in place: two
+ * launches per step, no kernel launch between the end of the scan and the result.  Otherwise: scan, BM25, fusion /
+ * exchange kernel.  D/I [nq,k] dense hits, S/J [nq,k] BM25 hits, F/O [nq,k] fused results.  status: see
+ * b2r_hybrid_exchange_fuse_dev (may be NULL).  flags: B2R_LAUNCH_OVERLAP_PREVIOUS chains the step behind the previous
+ * step on this stream — its scan queues up behind the previous scan and streams while the previous step's tail
+ * (fusion, exchange, the wait for the slowest rank) completes; q_dev and the term buffers must not be produced by the
+ * previous step.  launches (optional): kernels enqueued. */
+int b2r_hybrid_step_dev(b2r_flat* flat, b2r_bm25* bm25, const float* q_dev, int nq,
+                        const int32_t* term_ids_dev, const int32_t* term_offsets_dev, int k,
+                        int64_t id_offset, void* const* peer_bufs, int rank, int world, int nq_max,
+                        int k_max, uint32_t step, uint32_t* status, float* D_dev, int64_t* I_dev,
+                        double* S_dev, int64_t* J_dev, float* F_dev, int64_t* O_dev, void* stream,
+                        unsigned flags, int* launches);
+
 /* ---- N x N cosine analysis ---------------------------------------------------------------- */
 /* compute_cosine_similarity_matrix + off-diagonal statistics
  *                             semantic_similarity_analysis/generate_similarity_matrix.py:84-98,162-171

@@ -54,6 +54,9 @@ SIGNATURES = {
     "b2r_hybrid_exchange_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "b2r_hybrid_exchange_fuse_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, C.c_int,
                                               C.c_int, C.c_int, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "b2r_hybrid_step_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.POINTER(_vp), C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint,
+                                     C.POINTER(C.c_int)]),
     "b2r_hybrid_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "b2r_hybrid_ctx_destroy": (C.c_int, [_vp]),
     "b2r_hybrid_ctx_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

@@ -1,5 +1,7 @@
 // api.cu — library-level plumbing of the C ABI: thread-local error string, tunables, version.
 #include <map>
+#include <tuple>
+#include <algorithm>
 #include <mutex>
 #include <string>
 
@@ -53,9 +55,40 @@ static std::map<std::string, int>& tunables() {
       {"exchange.timeout_ms", 0},  // bound on the exchange kernel's wait for its peers (default 10000 ms)
       {"bm25.cfg", 0},             // ring geometry of the streaming kernel (A/B runs; see bm25_stream_launch)
       {"bm25.ctas_per_sm", 0},     // cap on resident streaming-kernel CTAs per SM
+      {"hybrid.no_fused_tail", 0}, // 1: the hybrid step keeps its fusion / exchange kernel (no fused tail in the BM25 kernel)
       {"bm25.v1", 0},              // 1: use the doc-block kernel (binary searches, per-token barriers) instead of the streaming one
   };
   return t;
+}
+
+struct PoolWs {
+  unsigned char* base = nullptr;
+  size_t bytes = 0;
+};
+static std::mutex g_ws_mu;
+static std::map<std::tuple<int, cudaStream_t, int>, PoolWs>& ws_pool() {
+  static std::map<std::tuple<int, cudaStream_t, int>, PoolWs> m;
+  return m;
+}
+
+int ws_pool_get(int device, cudaStream_t stream, int kind, size_t bytes, size_t zero_prefix, unsigned char** base,
+                size_t* cap) {
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  PoolWs& ws = ws_pool()[std::make_tuple(device, stream, kind)];
+  if (ws.bytes < bytes) {
+    if (ws.base) {  // growing: earlier work on this stream may still be using the old buffer
+      B2R_CUDA(cudaStreamSynchronize(stream));
+      cudaFree(ws.base);
+      ws.base = nullptr;
+      ws.bytes = 0;
+    }
+    B2R_CUDA(cudaMalloc(&ws.base, bytes));
+    ws.bytes = bytes;
+    if (zero_prefix) B2R_CUDA(cudaMemsetAsync(ws.base, 0, std::min(zero_prefix, bytes), stream));
+  }
+  *base = ws.base;
+  if (cap) *cap = ws.bytes;
+  return B2R_OK;
 }
 
 int tunable(const char* key) {

@@ -36,6 +36,15 @@ int& launch_counter();  // thread-local: kernels enqueued by the last search on 
   } while (0)
 
 int tunable(const char* key);  // current value of a tunable (see b2r_tunable_set)
+
+// Kernel workspaces are shared by all index handles: one buffer per (device, stream, kind), grown on demand.  Work on
+// one stream is ordered, so every handle searching on that stream can use the same scratch; HBM spent on scratch
+// then scales with the number of streams in use (the callers' concurrency), not with the number of indexes — a
+// corpus of thousands of per-report indexes costs no more than one.  kind: 0 = flat scan / tensor-core scratch,
+// 1 = BM25 (separate because BM25 runs BESIDE the scan on the same stream).  The first `zero_prefix` bytes are
+// zeroed when the buffer is (re)allocated; the kernels leave them zero.  The caller has the device selected.
+int ws_pool_get(int device, cudaStream_t stream, int kind, size_t bytes, size_t zero_prefix, unsigned char** base,
+                size_t* cap);
 }  // namespace b2r
 // host-side range check of query term ids against an index (csrc/bm25.cu)
 extern "C" int bm25_check_terms(const b2r_bm25* h, const int32_t* term_ids, int n);

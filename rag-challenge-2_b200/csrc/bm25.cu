@@ -31,6 +31,7 @@
 #include <string.h>
 
 #include "b2r_common.cuh"
+#include "hybrid_fuse.cuh"
 
 namespace b2r {
 
@@ -94,11 +95,13 @@ struct Bm25Args {
   long long id_offset;
   double* dense;  // non-NULL: write scores of query q_base densely and skip the select
   int sel_cap;
+  HybridTail tail;  // what the last CTA of a query does after the scan in front of this kernel has completed
 };
 
 template <class W>
 __global__ void __launch_bounds__(kBm25Warps * 32) bm25_kernel(const Bm25Args<W> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (a.tail.trigger_next) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int B = a.block_docs;
@@ -219,12 +222,54 @@ __global__ void __launch_bounds__(kBm25Warps * 32) bm25_kernel(const Bm25Args<W>
     *s_last = (t == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
-  pdl_wait_for_previous_grid();
   if (*s_last == 0) return;
   __threadfence();
   // last CTA of this query: the accumulator area becomes the select scratch
   u128* sel = reinterpret_cast<u128*>(smem_raw);
   block_select_lists(a.partial + static_cast<size_t>(ql) * gridDim.x * k, gridDim.x, k, k, sel, a.sel_cap, ctl);
+  if (a.tail.mode != 0) {
+    // ---- fused tail (k <= 256): BM25 top-k -> shared memory, wait for the scan, then fuse / exchange in this CTA ----
+    const u128 key = tid < k ? sel[tid] : static_cast<u128>(0);
+    __syncthreads();
+    double* mS = reinterpret_cast<double*>(smem_raw);               // [256]
+    long long* mJ = reinterpret_cast<long long*>(smem_raw + 2048);  // [256]
+    float* mD = reinterpret_cast<float*>(smem_raw + 4096);          // [256]
+    long long* mI = reinterpret_cast<long long*>(smem_raw + 5120);  // [256]
+    unsigned char* scratch = smem_raw + 7168;
+    if (tid < k) {
+      mS[tid] = key == 0 ? -1.7976931348623157e308 : ordered_to_double(static_cast<u64>(key >> 64));
+      mJ[tid] = key == 0 ? -1 : static_cast<long long>(0xFFFFFFFFu - static_cast<u32>(key)) + a.id_offset;
+    }
+    if (tid == 0) {  // the control words are free again before anything of a chained next step can touch them
+      a.tickets[ql] = 0;
+      a.tau_g[ql] = 0;
+    }
+    // The merge above ran while the scan was still streaming; from here on the scan's results are needed.
+    pdl_wait_for_previous_grid();
+    const size_t o = static_cast<size_t>(qi) * k;
+    if (tid < k) {
+      if (a.S) {
+        a.S[o + tid] = mS[tid];
+        a.I[o + tid] = mJ[tid];
+      }
+      mD[tid] = __ldcg(a.tail.D + o + tid);
+      mI[tid] = __ldcg(a.tail.I + o + tid);
+    }
+    __syncthreads();
+    if (a.tail.mode == 1) {
+      int fcap = 2;
+      while (fcap < 2 * k) fcap <<= 1;
+      fuse_query(mD, mI, mS, mJ, k, k, k, a.tail.F + o, a.tail.O + o, nullptr, reinterpret_cast<u64*>(scratch), fcap,
+                 reinterpret_cast<double*>(scratch + static_cast<size_t>(fcap) * 8));
+    } else {
+      exchange_merge_fuse_query(mD, mI, mS, mJ, qi, k, a.tail.x, a.tail.F + o, a.tail.O + o, scratch);
+    }
+    return;
+  }
+  // Launched beside the scan: the merge above ran while the scan was still streaming; only the publication of the
+  // result waits for it, so that "after BM25" means "after the scan too" for the kernels that follow, and so that
+  // S / I may alias buffers the previous step's fusion kernel is still reading when steps are chained.
+  pdl_wait_for_previous_grid();
   for (int i = tid; i < k; i += nt) {
     const u128 key = sel[i];
     const size_t o = static_cast<size_t>(qi) * k + i;
@@ -846,20 +891,17 @@ struct b2r_bm25 {
   bool owns_doc_ids = true;
   int num_sms = 148;
   std::mutex mu;
-  std::map<cudaStream_t, Bm25Ws> stream_ws;
   // Host entry points are re-entrant: every call borrows a "lane" (its own stream, grow-only device + pinned
-  // staging, and — through stream_ws — its own kernel workspace), so concurrent callers of one index run
-  // concurrently (the reference calls one index from a thread pool, src/retrieval.py:1498-1504) and no call pays a
-  // cudaMalloc.  host_mu only guards the free list.
+  // staging, and — through the stream-keyed workspace pool — its own kernel workspace) from a pool shared by all
+  // BM25 indexes of the device, so concurrent callers of one index run concurrently (the reference calls one index
+  // from a thread pool, src/retrieval.py:1498-1504), no call pays a cudaMalloc, and scratch memory follows the
+  // callers' concurrency, not the number of indexes.
   struct HostLane {
     cudaStream_t stream = nullptr;
     unsigned char* dev = nullptr;
     unsigned char* pin = nullptr;
     size_t cap = 0;
   };
-  std::vector<HostLane*> free_lanes;
-  std::vector<HostLane*> all_lanes;
-  std::mutex host_mu;
 };
 
 namespace b2r {
@@ -868,13 +910,17 @@ static const size_t kBm25WsBytes = static_cast<size_t>(256) << 20;  // partial l
 static const size_t kBm25CtlBytes = 64 * 1024;                      // tickets[<=4096] + tau_g[<=4096]
 static const int kBm25MaxQPerLaunch = 4096;
 
+static std::mutex g_lane_mu;
+static std::map<int, std::vector<b2r_bm25::HostLane*>> g_free_lanes;  // per device
+
 static int bm25_lane_acquire(b2r_bm25* h, size_t bytes, b2r_bm25::HostLane** out) {
   b2r_bm25::HostLane* lane = nullptr;
   {
-    std::lock_guard<std::mutex> lock(h->host_mu);
-    if (!h->free_lanes.empty()) {
-      lane = h->free_lanes.back();
-      h->free_lanes.pop_back();
+    std::lock_guard<std::mutex> lock(g_lane_mu);
+    auto& pool = g_free_lanes[h->device];
+    if (!pool.empty()) {
+      lane = pool.back();
+      pool.pop_back();
     }
   }
   if (!lane) {
@@ -884,8 +930,6 @@ static int bm25_lane_acquire(b2r_bm25* h, size_t bytes, b2r_bm25::HostLane** out
       delete lane;
       return fail(B2R_ERR_CUDA, std::string("bm25: cudaStreamCreate: ") + cudaGetErrorString(e));
     }
-    std::lock_guard<std::mutex> lock(h->host_mu);
-    h->all_lanes.push_back(lane);
   }
   if (lane->cap < bytes) {
     if (lane->dev) cudaFree(lane->dev);
@@ -898,8 +942,8 @@ static int bm25_lane_acquire(b2r_bm25* h, size_t bytes, b2r_bm25::HostLane** out
     if (e != cudaSuccess) {
       if (lane->dev) cudaFree(lane->dev);
       lane->dev = nullptr;
-      std::lock_guard<std::mutex> lock(h->host_mu);
-      h->free_lanes.push_back(lane);
+      std::lock_guard<std::mutex> lock(g_lane_mu);
+      g_free_lanes[h->device].push_back(lane);
       return fail(e == cudaErrorMemoryAllocation ? B2R_ERR_NOMEM : B2R_ERR_CUDA, std::string("bm25: staging: ") + cudaGetErrorString(e));
     }
     lane->cap = cap;
@@ -909,27 +953,17 @@ static int bm25_lane_acquire(b2r_bm25* h, size_t bytes, b2r_bm25::HostLane** out
 }
 
 static void bm25_lane_release(b2r_bm25* h, b2r_bm25::HostLane* lane) {
-  std::lock_guard<std::mutex> lock(h->host_mu);
-  h->free_lanes.push_back(lane);
+  std::lock_guard<std::mutex> lock(g_lane_mu);
+  g_free_lanes[h->device].push_back(lane);
 }
 
 static int bm25_get_ws(b2r_bm25* h, cudaStream_t stream, Bm25Ws* out) {
-  std::lock_guard<std::mutex> lock(h->mu);
-  auto it = h->stream_ws.find(stream);
-  if (it != h->stream_ws.end()) {
-    *out = it->second;
-    return B2R_OK;
-  }
-  Bm25Ws ws;
-  // small corpora need far less than the cap: nq_launch * blocks * k * 16 with nq_launch <= 4096
+  // small corpora need far less than the cap: nq_launch * blocks * k * 16 with nq_launch <= 4096.  The buffer is the
+  // stream's shared BM25 workspace (ws_pool_get): it grows to the largest index searched on that stream.
   const long long blocks = std::max<long long>(1, (h->n_docs + 8191) / 8192);
   size_t want = kBm25CtlBytes + static_cast<size_t>(std::min<long long>(blocks, 1 << 20)) * B2R_MAX_K * 16 * 4;
-  ws.bytes = std::min(kBm25WsBytes + kBm25CtlBytes, std::max<size_t>(want, 8 << 20));
-  B2R_CUDA(cudaMalloc(&ws.base, ws.bytes));
-  B2R_CUDA(cudaMemsetAsync(ws.base, 0, kBm25CtlBytes, stream));
-  h->stream_ws[stream] = ws;
-  *out = ws;
-  return B2R_OK;
+  want = 2 * std::min(kBm25WsBytes + kBm25CtlBytes, std::max<size_t>(want, 8 << 20));  // two halves, see bm25_run
+  return ws_pool_get(h->device, stream, 1, want, want, &out->base, &out->bytes);
 }
 
 struct Bm25Plan {
@@ -1030,7 +1064,8 @@ static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term
   int rc = bm25_get_ws(h, stream, &ws);
   if (rc) return rc;
   const size_t per_q = static_cast<size_t>(h->n_blocks) * k * 16;
-  long long max_q = static_cast<long long>((ws.bytes - kBm25CtlBytes) / per_q);
+  // the first half of the stream's workspace only: the second half carries the doc-block kernel's alternate control words
+  long long max_q = static_cast<long long>(((ws.bytes / 2 & ~static_cast<size_t>(255)) - kBm25CtlBytes) / per_q);
   max_q = std::min<long long>(max_q, kBm25MaxQPerLaunch);
   if (max_q < 1) return fail(B2R_ERR_UNSUPPORTED, "bm25: workspace too small for one query (corpus x k too large)");
   for (int q0 = 0; q0 < nq; q0 += static_cast<int>(max_q)) {
@@ -1073,15 +1108,24 @@ static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term
 }
 
 // shared by topk (dense == nullptr) and scores (dense != nullptr, one query)
+// Consecutive doc-block launches on one stream alternate between the two halves of the stream's workspace: with
+// chained steps (HybridTail::trigger_next) the BM25 kernel of step s + 1 may start while the one of step s has not
+// finished its tail, and must not share partial lists or control words with it.
+static std::mutex g_parity_mu;
+static std::map<cudaStream_t, int> g_ws_parity;
+
 static int bm25_run(b2r_bm25* h, const int* term_ids_dev, const int* term_offsets_dev, int nq, int k, double* S_dev,
                     long long* I_dev, long long id_offset, double* dense_dev, cudaStream_t stream,
-                    bool overlap_prev = false) {
+                    bool overlap_prev = false, const HybridTail* tail = nullptr) {
   launch_counter() = 0;
   // Alone, the streaming kernel is ~1.6x faster (profiles/r01_bm25.md); launched BESIDE the flat scan its busy
   // consumer warps take more from the scan than the latency-bound doc-block kernel does, so the hybrid
   // single-query path keeps the latter (bm25.v1 = 2 forces the streaming kernel there too).
   const int v1 = tunable("bm25.v1");
   const bool use_stream = v1 == 2 || (v1 == 0 && !(overlap_prev && nq <= 4));
+  if (tail && (use_stream || k > kTailMaxK || dense_dev)) {
+    return fail(B2R_ERR_UNSUPPORTED, "bm25: the fused tail needs the doc-block kernel (<= 4 queries beside a scan) and k <= 256");
+  }
   if (use_stream && k <= kStreamMaxK) {
     return bm25_run_stream(h, term_ids_dev, term_offsets_dev, nq, k, S_dev, I_dev, id_offset, dense_dev, stream, overlap_prev);
   }
@@ -1092,9 +1136,17 @@ static int bm25_run(b2r_bm25* h, const int* term_ids_dev, const int* term_offset
   rc = bm25_get_ws(h, stream, &ws);
   if (rc) return rc;
   const size_t per_q = static_cast<size_t>(p.grid_x) * k * 16;
-  long long max_q = static_cast<long long>((ws.bytes - kBm25CtlBytes) / per_q);
+  const size_t half = (ws.bytes / 2) & ~static_cast<size_t>(255);
+  long long max_q = static_cast<long long>((half - kBm25CtlBytes) / per_q);
   max_q = std::min<long long>(std::min<long long>(max_q, kBm25MaxQPerLaunch), 65535);
   if (max_q < 1) return fail(B2R_ERR_UNSUPPORTED, "bm25: workspace too small for one query (corpus x k too large)");
+  if (tail && nq > max_q) return fail(B2R_ERR_UNSUPPORTED, "bm25: the fused tail needs all queries in one launch");
+  int parity;
+  {
+    std::lock_guard<std::mutex> lock(g_parity_mu);
+    parity = (g_ws_parity[stream] ^= 1);
+  }
+  unsigned char* ws_base = ws.base + static_cast<size_t>(parity) * half;
   for (int q0 = 0; q0 < nq; q0 += static_cast<int>(max_q)) {
     const int nql = static_cast<int>(std::min<long long>(max_q, nq - q0));
     Bm25Args<float> a;
@@ -1110,14 +1162,16 @@ static int bm25_run(b2r_bm25* h, const int* term_ids_dev, const int* term_offset
     a.k = k;
     a.cap = p.cap;
     a.n_sel_warps = p.n_sel_warps;
-    a.tickets = reinterpret_cast<u32*>(ws.base);
-    a.tau_g = reinterpret_cast<u64*>(ws.base + kBm25CtlBytes / 2);
-    a.partial = reinterpret_cast<u128*>(ws.base + kBm25CtlBytes);
+    a.tickets = reinterpret_cast<u32*>(ws_base);
+    a.tau_g = reinterpret_cast<u64*>(ws_base + kBm25CtlBytes / 2);
+    a.partial = reinterpret_cast<u128*>(ws_base + kBm25CtlBytes);
     a.S = S_dev;
     a.I = I_dev;
     a.id_offset = id_offset;
     a.dense = dense_dev;
     a.sel_cap = p.sel_cap;
+    if (tail) a.tail = *tail;
+    else memset(&a.tail, 0, sizeof(a.tail));
     if (h->weight_bits == 64) {
       Bm25Args<double> ad;
       memcpy(&ad, &a, sizeof(a));  // identical layout: only the weight pointer type differs
@@ -1132,6 +1186,14 @@ static int bm25_run(b2r_bm25* h, const int* term_ids_dev, const int* term_offset
 }
 
 }  // namespace b2r
+
+int bm25_topk_with_tail(b2r_bm25* h, const int32_t* term_ids_dev, const int32_t* term_offsets_dev, int nq, int k,
+                        double* S_dev, int64_t* J_dev, int64_t id_offset, cudaStream_t stream, bool overlap_prev,
+                        const b2r::HybridTail& tail) {
+  if (!h) return b2r::fail(B2R_ERR_INVALID, "bm25: NULL handle");
+  return b2r::bm25_run(h, term_ids_dev, term_offsets_dev, nq, k, S_dev, reinterpret_cast<long long*>(J_dev), id_offset, nullptr,
+                       stream, overlap_prev, &tail);
+}
 
 extern "C" {
 
@@ -1365,20 +1427,12 @@ int b2r_bm25_destroy(b2r_bm25* h) {
   if (!h) return B2R_OK;
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  for (auto& kv : h->stream_ws) {
-    if (kv.second.base) cudaFree(kv.second.base);
-  }
   if (h->indptr) cudaFree(h->indptr);
   if (h->doc_ids) cudaFree(h->doc_ids);
   if (h->weight) cudaFree(h->weight);
   if (h->idf) cudaFree(h->idf);
   if (h->skip) cudaFree(h->skip);
-  for (b2r_bm25::HostLane* lane : h->all_lanes) {
-    if (lane->dev) cudaFree(lane->dev);
-    if (lane->pin) cudaFreeHost(lane->pin);
-    if (lane->stream) cudaStreamDestroy(lane->stream);
-    delete lane;
-  }
+  // host lanes and kernel workspaces belong to the device-wide pools and outlive the handle
   delete h;
   return B2R_OK;
 }

@@ -462,9 +462,6 @@ struct b2r_flat {
   bool owns = true;
   int num_sms = 148;
   std::mutex mu;
-  std::map<cudaStream_t, Workspace> stream_ws;
-  std::vector<HostCtx*> free_ctx;
-  std::vector<HostCtx*> all_ctx;
   float* max_norm2 = nullptr;      // device scalar: max |row|^2 (error bound of the tf32 candidate pass)
   long long max_norm2_rows = -1;   // number of rows it was computed for
   bool want_bf16 = false;          // b2r_flat_set_candidate_bf16: keep a bf16 copy of the rows for the candidate pass
@@ -475,19 +472,8 @@ struct b2r_flat {
 namespace b2r {
 
 static int get_workspace(b2r_flat* h, cudaStream_t stream, Workspace* out) {
-  std::lock_guard<std::mutex> lock(h->mu);
-  auto it = h->stream_ws.find(stream);
-  if (it != h->stream_ws.end()) {
-    *out = it->second;
-    return B2R_OK;
-  }
-  Workspace ws;
-  ws.bytes = workspace_bytes();
-  B2R_CUDA(cudaMalloc(&ws.base, ws.bytes));
-  B2R_CUDA(cudaMemsetAsync(ws.base, 0, 256, stream));
-  h->stream_ws[stream] = ws;
-  *out = ws;
-  return B2R_OK;
+  // shared by every index searching on this stream (ws_pool_get): [256 B ticket area][partial keys][gemm scratch]
+  return ws_pool_get(h->device, stream, 0, workspace_bytes(), 256, &out->base, &out->bytes);
 }
 
 // max |row|^2 over the shard, computed once per index size on the searching stream
@@ -760,12 +746,20 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
   return B2R_OK;
 }
 
+// Host contexts (a stream + staging) are pooled per DEVICE, not per index: a host search borrows one for the call, so
+// the number of streams — and of the workspaces keyed by them — follows the callers' concurrency.  A retriever over
+// thousands of per-report indexes (src/retrieval.py builds one faiss index per report) then holds a handful of
+// contexts, not one per report.
+static std::mutex g_ctx_mu;
+static std::map<int, std::vector<HostCtx*>> g_free_ctx;
+
 static int acquire_ctx(b2r_flat* h, HostCtx** out) {
   {
-    std::lock_guard<std::mutex> lock(h->mu);
-    if (!h->free_ctx.empty()) {
-      *out = h->free_ctx.back();
-      h->free_ctx.pop_back();
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    auto& pool = g_free_ctx[h->device];
+    if (!pool.empty()) {
+      *out = pool.back();
+      pool.pop_back();
       return B2R_OK;
     }
   }
@@ -775,17 +769,13 @@ static int acquire_ctx(b2r_flat* h, HostCtx** out) {
     delete c;
     return fail(B2R_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
   }
-  {
-    std::lock_guard<std::mutex> lock(h->mu);
-    h->all_ctx.push_back(c);
-  }
   *out = c;
   return B2R_OK;
 }
 
 static void release_ctx(b2r_flat* h, HostCtx* c) {
-  std::lock_guard<std::mutex> lock(h->mu);
-  h->free_ctx.push_back(c);
+  std::lock_guard<std::mutex> lock(g_ctx_mu);
+  g_free_ctx[h->device].push_back(c);
 }
 
 static int ensure_ctx_buffers(HostCtx* c, size_t q_floats, size_t out_bytes) {
@@ -1025,17 +1015,7 @@ int b2r_flat_destroy(b2r_flat* h) {
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   if (h->rows_bf16) cudaFree(h->rows_bf16);
-  for (HostCtx* c : h->all_ctx) {
-    if (c->q_dev) cudaFree(c->q_dev);
-    if (c->q_pin) cudaFreeHost(c->q_pin);
-    if (c->out_dev) cudaFree(c->out_dev);
-    if (c->out_pin) cudaFreeHost(c->out_pin);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
-  }
-  for (auto& kv : h->stream_ws) {
-    if (kv.second.base) cudaFree(kv.second.base);
-  }
+  // host contexts and kernel workspaces belong to the device-wide pools and outlive the handle
   if (h->owns && h->rows) cudaFree(h->rows);
   if (h->max_norm2) cudaFree(h->max_norm2);
   delete h;

@@ -12,7 +12,7 @@
 #include <algorithm>
 #include <mutex>
 
-#include "b2r_common.cuh"
+#include "hybrid_fuse.cuh"
 
 struct b2r_hybrid_ctx {
   int device = 0;
@@ -29,6 +29,59 @@ struct b2r_hybrid_ctx {
 };
 
 using namespace b2r;
+
+// One hybrid step, everything resident, in TWO launches when it can: the dense scan, and BM25 launched beside it
+// whose last CTA per query — after griddepcontrol.wait, i.e. once the scan has completed — fuses (or exchanges,
+// merges and fuses) in place.  Falls back to scan, BM25, fusion / exchange kernel when the fused tail does not apply
+// (more than 4 queries, k > 256, a batch that goes to the tensor cores, the streaming BM25 kernel forced).
+// flags: B2R_LAUNCH_OVERLAP_PREVIOUS chains this step behind the previous one (see b2r_flat_search_dev_ex).
+static int hybrid_step_dev(b2r_flat* flat, b2r_bm25* bm25, const float* q_dev, int nq, const int32_t* tids_dev,
+                           const int32_t* offs_dev, int k, int64_t id_offset, void* const* peer_bufs, int rank, int world,
+                           int nq_max, int k_max, uint32_t step, uint32_t* status, float* D_dev, int64_t* I_dev, double* S_dev,
+                           int64_t* J_dev, float* F_dev, int64_t* O_dev, cudaStream_t stream, unsigned flags, int* launches) {
+  int rc = b2r_flat_search_dev_ex(flat, q_dev, nq, k, D_dev, I_dev, id_offset, stream, flags);
+  if (rc) return rc;
+  int n_launch = b2r_last_launch_count();
+  const bool fused_ok = nq <= 4 && k <= kTailMaxK && n_launch == 1 && !tunable("hybrid.no_fused_tail");
+  if (fused_ok) {
+    HybridTail tail;
+    memset(&tail, 0, sizeof(tail));
+    tail.mode = world > 1 ? 2 : 1;
+    tail.trigger_next = (flags & B2R_LAUNCH_OVERLAP_PREVIOUS) ? 1 : 0;
+    tail.D = D_dev;
+    tail.I = reinterpret_cast<const long long*>(I_dev);
+    tail.F = F_dev;
+    tail.O = reinterpret_cast<long long*>(O_dev);
+    if (world > 1) {
+      for (int p = 0; p < 8; ++p) tail.x.peers[p] = p < world ? static_cast<unsigned char*>(peer_bufs[p]) : nullptr;
+      tail.x.rank = rank;
+      tail.x.world = world;
+      tail.x.nq_max = nq_max;
+      tail.x.k_max = k_max;
+      tail.x.step = step;
+      tail.x.status = status;
+      const int tmo_ms = tunable("exchange.timeout_ms");
+      tail.x.timeout_ns = static_cast<unsigned long long>(tmo_ms > 0 ? tmo_ms : 10000) * 1000000ull;
+    }
+    rc = bm25_topk_with_tail(bm25, tids_dev, offs_dev, nq, k, S_dev, J_dev, id_offset, stream, true, tail);
+    if (rc == B2R_OK) {
+      if (launches) *launches = n_launch + b2r_last_launch_count();
+      return B2R_OK;
+    }
+    if (rc != B2R_ERR_UNSUPPORTED) return rc;  // UNSUPPORTED: nothing was launched, take the three-kernel path
+  }
+  rc = b2r_bm25_topk_dev_ex(bm25, tids_dev, offs_dev, nullptr, nq, k, S_dev, J_dev, id_offset, stream, B2R_LAUNCH_OVERLAP_PREVIOUS);
+  if (rc) return rc;
+  n_launch += b2r_last_launch_count();
+  if (world > 1) {
+    rc = b2r_hybrid_exchange_fuse_dev(D_dev, I_dev, S_dev, J_dev, nq, k, peer_bufs, rank, world, nq_max, k_max, step, F_dev, O_dev,
+                                      status, stream);
+  } else {
+    rc = b2r_hybrid_fuse_dev(D_dev, I_dev, S_dev, J_dev, nq, k, k, k, F_dev, O_dev, nullptr, stream);
+  }
+  if (launches) *launches = n_launch + 1;
+  return rc;
+}
 
 static int ctx_reserve(b2r_hybrid_ctx* c, size_t in_bytes, size_t nk) {
   if (c->in_cap < in_bytes) {
@@ -150,19 +203,11 @@ int b2r_hybrid_search_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, co
   double* S_dev = reinterpret_cast<double*>(mid + c->out_cap * 8);
   int64_t* J_dev = reinterpret_cast<int64_t*>(mid + c->out_cap * 16);
   float* D_dev = reinterpret_cast<float*>(mid + c->out_cap * 24);
-  rc = b2r_flat_search_dev(flat, q_dev, nq, k, D_dev, I_dev, id_offset, c->stream);
-  if (rc) return rc;
-  rc = b2r_bm25_topk_dev_ex(bm25, tids_dev, offs_dev, nullptr, nq, k, S_dev, J_dev, id_offset, c->stream,
-                            B2R_LAUNCH_OVERLAP_PREVIOUS);
-  if (rc) return rc;
   volatile uint32_t* status_host = reinterpret_cast<volatile uint32_t*>(c->out_pin + c->out_cap * 12);
-  if (world > 1) {
-    *status_host = 0;
-    rc = b2r_hybrid_exchange_fuse_dev(D_dev, I_dev, S_dev, J_dev, nq, k, peer_bufs, rank, world, nq_max, k_max, step, F_dev,
-                                      O_dev, reinterpret_cast<uint32_t*>(c->out_pin_dev + c->out_cap * 12), c->stream);
-  } else {
-    rc = b2r_hybrid_fuse_dev(D_dev, I_dev, S_dev, J_dev, nq, k, k, k, F_dev, O_dev, nullptr, c->stream);
-  }
+  *status_host = 0;
+  rc = hybrid_step_dev(flat, bm25, q_dev, nq, tids_dev, offs_dev, k, id_offset, peer_bufs, rank, world, nq_max, k_max, step,
+                       reinterpret_cast<uint32_t*>(c->out_pin_dev + c->out_cap * 12), D_dev, I_dev, S_dev, J_dev, F_dev, O_dev,
+                       c->stream, 0u, nullptr);
   if (rc) return rc;
   B2R_CUDA(cudaStreamSynchronize(c->stream));
   if (world > 1 && *status_host != 0) {
@@ -174,6 +219,30 @@ int b2r_hybrid_search_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, co
   c->last_h2d = h2d;
   c->last_d2h = nk * 12;
   return B2R_OK;
+}
+
+// The resident step (see hybrid_step_dev above): q_dev[nq,d], term ids / offsets, and all outputs live on the device;
+// D/I (dense hits), S/J (BM25 hits) and F/O (fused) are [nq,k].  world == 1: peer_bufs may be NULL.  status: see
+// b2r_hybrid_exchange_fuse_dev.  launches (optional) receives the number of kernels enqueued.
+int b2r_hybrid_step_dev(b2r_flat* flat, b2r_bm25* bm25, const float* q_dev, int nq, const int32_t* term_ids_dev,
+                        const int32_t* term_offsets_dev, int k, int64_t id_offset, void* const* peer_bufs, int rank, int world,
+                        int nq_max, int k_max, uint32_t step, uint32_t* status, float* D_dev, int64_t* I_dev, double* S_dev,
+                        int64_t* J_dev, float* F_dev, int64_t* O_dev, void* stream, unsigned flags, int* launches) {
+  if (!flat || !bm25) return fail(B2R_ERR_INVALID, "b2r_hybrid_step_dev: NULL handle");
+  if (nq < 1 || k < 1 || k > B2R_MAX_K) return fail(B2R_ERR_INVALID, "b2r_hybrid_step_dev: bad sizes");
+  if (!q_dev || !term_offsets_dev || !D_dev || !I_dev || !S_dev || !J_dev || !F_dev || !O_dev) return fail(B2R_ERR_INVALID, "b2r_hybrid_step_dev: NULL buffer");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(B2R_ERR_INVALID, "b2r_hybrid_step_dev: bad rank / world");
+  if (world > 1) {
+    if (!peer_bufs) return fail(B2R_ERR_INVALID, "b2r_hybrid_step_dev: world > 1 needs the peer buffers");
+    if (nq > nq_max || k > k_max || k > 256) return fail(B2R_ERR_INVALID, "b2r_hybrid_step_dev: nq / k exceed the exchange buffer geometry");
+    if (step == 0) return fail(B2R_ERR_INVALID, "b2r_hybrid_step_dev: step must be >= 1");
+  }
+  int64_t n_rows = 0;
+  int rc = b2r_flat_ntotal(flat, &n_rows);
+  if (rc) return rc;
+  if (id_offset < 0 || id_offset + n_rows >= 0xFFFFFFF0LL) return fail(B2R_ERR_UNSUPPORTED, "b2r_hybrid_step_dev: global ids must stay below 2^32-16");
+  return hybrid_step_dev(flat, bm25, q_dev, nq, term_ids_dev, term_offsets_dev, k, id_offset, peer_bufs, rank, world, nq_max, k_max,
+                         step, status, D_dev, I_dev, S_dev, J_dev, F_dev, O_dev, static_cast<cudaStream_t>(stream), flags, launches);
 }
 
 }  // extern "C"

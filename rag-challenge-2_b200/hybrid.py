@@ -301,13 +301,54 @@ class HybridIndex:
             self.searcher.peer_exchange = PeerExchange(torch.device("cuda", flat.device), group)
         self._pinned = {}
         self._ctx = None   # b2r_hybrid_ctx of the one-call host step
+        self._own_callables = (self.searcher.local_dense, self.searcher.local_bm25)
 
     # resident API -----------------------------------------------------------------------------------
     def search_dev(self, q, k):
         return self.searcher.search_dense(q, k)
 
     def search_hybrid_dev(self, q, term_ids, term_offsets, k):
-        return self.searcher.search_hybrid(q, term_ids, term_offsets, k)
+        """Resident hybrid step.  With the dependent-launch overlap (and, on several ranks, the peer exchange) the step is
+        ONE C call (b2r_hybrid_step_dev): scan + BM25 beside it, whose last CTA per query fuses / exchanges in place —
+        two launches for up to 2 queries; searcher.pipeline chains consecutive steps.  Anything else (NCCL exchange,
+        two-stream overlap, injected callables) runs the step from Python (ShardedSearcher.search_hybrid)."""
+        s = self.searcher
+        native = (self.bm25 is not None and s.overlap == "pdl" and (s.world_size == 1 or s.peer_exchange is not None)
+                  and (s.local_dense, s.local_bm25) == self._own_callables and int(k) <= 256)
+        if not native:
+            return s.search_hybrid(q, term_ids, term_offsets, k)
+        import torch
+
+        lib = _lib.load()
+        nq, k = int(q.shape[0]), int(k)
+        nk = nq * k
+        buf = torch.empty(40 * nk, dtype=torch.uint8, device=q.device)   # one allocation: I, S, J, O (8 B) then D, F (4 B)
+        I = buf[: 8 * nk].view(torch.int64).view(nq, k)
+        S = buf[8 * nk: 16 * nk].view(torch.float64).view(nq, k)
+        J = buf[16 * nk: 24 * nk].view(torch.int64).view(nq, k)
+        O = buf[24 * nk: 32 * nk].view(torch.int64).view(nq, k)
+        D = buf[32 * nk: 36 * nk].view(torch.float32).view(nq, k)
+        F = buf[36 * nk: 40 * nk].view(torch.float32).view(nq, k)
+        px = s.peer_exchange
+        if px is not None:
+            arr = (C.c_void_p * len(px.ptrs))(*[C.c_void_p(int(p)) for p in px.ptrs])
+            ex = (arr, px.rank, px.world, px.nq_max, px.k_max, px.step + 1, C.c_void_p(px.status.data_ptr()))
+        else:
+            ex = (None, 0, 1, 0, 0, 0, None)
+        self.bm25._ensure_built()
+        n_launch = C.c_int(0)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        _lib.check(lib.b2r_hybrid_step_dev(self.flat._h, self.bm25._h, C.c_void_p(q.data_ptr()), nq,
+                                           C.c_void_p(term_ids.data_ptr()), C.c_void_p(term_offsets.data_ptr()), k,
+                                           self.offset, *ex, C.c_void_p(D.data_ptr()), C.c_void_p(I.data_ptr()),
+                                           C.c_void_p(S.data_ptr()), C.c_void_p(J.data_ptr()), C.c_void_p(F.data_ptr()),
+                                           C.c_void_p(O.data_ptr()), C.c_void_p(stream), 1 if s.pipeline else 0,
+                                           C.byref(n_launch)))
+        if px is not None:
+            px.step += 1
+        s.launches, s.collectives = int(n_launch.value), 0
+        self.last_parts = (D, I, S, J)
+        return F, O
 
     # host API: the call a user makes (numpy in, numpy out; copies inside) ------------------------------
     def _staging(self, nbytes, nk):

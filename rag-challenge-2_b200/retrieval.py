@@ -226,6 +226,10 @@ def _load_report_cached(document_path: Path, index_path: Path, device: int):
         raise ValueError("does not match the expected schema")
     vector_db = flat_index.read_index(index_path, device=device)
     with _CACHE_LOCK:
+        # a rewritten report supersedes its older entries (same paths and device, other mtime / size): drop them, or
+        # every re-ingestion would leave one more resident copy of the rows in HBM
+        for old in [k for k in _REPORT_CACHE if k[0] == key[0] and k[3] == key[3] and k[6] == key[6] and k != key]:
+            del _REPORT_CACHE[old]
         _REPORT_CACHE[key] = {"document": document, "vector_db": vector_db}
     return document, vector_db
 

@@ -251,3 +251,102 @@ def test_chained_steps_equal_unchained(b2r):
     torch.cuda.synchronize()
     assert torch.equal(O2[0], plain[0][1][0]) and torch.equal(O2[1], plain[1][1][0])
     index.close()
+
+
+@pytest.mark.parametrize("world,k,step,nq", [(1, 30, 1, 1), (3, 30, 2, 2), (8, 30, 5, 1), (8, 100, 8, 2), (4, 7, 3, 2)])
+def test_fused_tail_step_emulated_ranks(b2r, world, k, step, nq):
+    """b2r_hybrid_step_dev: scan + BM25 whose last CTA per query fuses (world 1) or exchanges + merges + fuses in place
+    (world > 1, the other ranks emulated as in test_exchange_kernel_emulated: their slots and flags pre-filled in one
+    buffer that stands for every rank's symmetric buffer).  Checked against the oracle applied to this rank's real hits
+    and the emulated ranks' lists; D / I / S / J must equal the separate searches."""
+    import ctypes as C
+
+    import torch
+
+    from rag_challenge_2_b200 import _lib, synth
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    n, d, V = 40_000, 1024, 3000
+    nq_max, k_max = 8, 128
+    rows = synth.dense_rows_torch(0, n, d, "cuda", seed=300 + world)
+    flat = b2r.FlatIPIndex.from_device_tensor(rows)
+    post = synth.token_postings_torch(0, n, V, "cuda", seed=301)
+    idf, _ = synth.bm25_idf_from_df(post["df"].cpu().numpy(), n)
+    bm = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"], torch.from_numpy(idf).cuda(),
+                                 post["total_len"] / n)
+    q = synth.dense_queries_torch(nq, d, "cuda", rows, seed=302)
+    toks = synth.token_queries_np(nq, vocab=V, seed=303)
+    offs = np.zeros(nq + 1, np.int32)
+    np.cumsum([len(t) for t in toks], out=offs[1:])
+    tids = torch.from_numpy(np.concatenate(toks).astype(np.int32)).cuda()
+    toffs = torch.from_numpy(offs).cuda()
+    D0, I0 = flat.search_dev(q, k)
+    S0, J0 = bm.topk_dev(tids, toffs, k)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(world * 100 + k)
+    D = np.zeros((world, nq, k), np.float32)
+    S = np.zeros((world, nq, k))
+    I = np.zeros((world, nq, k), np.int64)
+    J = np.zeros((world, nq, k), np.int64)
+    D[0], I[0], S[0], J[0] = D0.cpu().numpy(), I0.cpu().numpy(), S0.cpu().numpy(), J0.cpu().numpy()
+    for r in range(1, world):
+        D[r] = -np.sort(-(rng.random((nq, k)).astype(np.float32) * float(D[0].max()) * 1.2), axis=1)
+        S[r] = -np.sort(-(rng.random((nq, k)) * float(S[0].max()) * 1.2), axis=1)
+        for qi in range(nq):
+            I[r, qi] = rng.choice(n, k, replace=False) + n * r
+            J[r, qi] = rng.choice(n, k, replace=False) + n * r
+    if world > 1:
+        J[1, 0, :3] = I[0, 0, :3]                # found by both retrievers, on different ranks
+        I[world - 1, 0, k // 2:] = -1            # a ragged list
+    nbytes = int(_lib.load().b2r_hybrid_exchange_bytes(nq_max, k_max, world))
+    buf = np.zeros(nbytes, dtype=np.uint8)
+    nk = nq_max * k_max
+    slot = nk * 28
+    parity = step & 1
+    for r in range(1, world):
+        base = (parity * world + r) * slot
+        buf[base: base + nk * 4].view(np.float32).reshape(nq_max, k_max)[:nq, :k] = D[r]
+        buf[base + nk * 4: base + nk * 12].view(np.int64).reshape(nq_max, k_max)[:nq, :k] = I[r]
+        buf[base + nk * 12: base + nk * 20].view(np.float64).reshape(nq_max, k_max)[:nq, :k] = S[r]
+        buf[base + nk * 20: base + nk * 28].view(np.int64).reshape(nq_max, k_max)[:nq, :k] = J[r]
+    buf[2 * world * slot:].view(np.uint32).reshape(2, world, nq_max)[parity, 1:, :] = step
+    dev = torch.from_numpy(buf).cuda()
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = {name: torch.empty((nq, k), dtype=dt, device="cuda") for name, dt in
+           (("D", torch.float32), ("I", torch.int64), ("S", torch.float64), ("J", torch.int64), ("F", torch.float32), ("O", torch.int64))}
+    arr = (C.c_void_p * world)(*[C.c_void_p(dev.data_ptr())] * world)
+    n_launch = C.c_int(0)
+    for flags in (0, 1):                          # plain, and launched as a chained step
+        for t in out.values():
+            t.zero_()
+        if world > 1:                             # rank 0's own flags of this step are cleared between the two runs
+            dev[2 * world * slot:].view(torch.int32).view(2, world, nq_max)[parity, 0, :] = 0
+        torch.cuda.synchronize()
+        _lib.check(_lib.load().b2r_hybrid_step_dev(
+            flat._h, bm._h, C.c_void_p(q.data_ptr()), nq, C.c_void_p(tids.data_ptr()), C.c_void_p(toffs.data_ptr()), k, 0,
+            arr if world > 1 else None, 0, world, nq_max, k_max, step, C.c_void_p(status.data_ptr()),
+            *[C.c_void_p(out[name].data_ptr()) for name in ("D", "I", "S", "J", "F", "O")],
+            C.c_void_p(torch.cuda.current_stream().cuda_stream), flags, C.byref(n_launch)))
+        torch.cuda.synchronize()
+        assert n_launch.value == 2 and int(status.item()) == 0
+        assert torch.equal(out["D"], D0) and torch.equal(out["I"], I0) and torch.equal(out["S"], S0) and torch.equal(out["J"], J0)
+        Dm, Im = oracle.merge_lists_ref(D, I, k, np.float32(-3.4028235e38))
+        Sm, Jm = oracle.merge_lists_ref(S, J, k, -1.7976931348623157e308)
+        Fr, Or, _ = oracle.hybrid_fuse_ref(Dm, Im, Sm, Jm, k)
+        assert np.array_equal(out["O"].cpu().numpy(), Or)
+        assert np.array_equal(out["F"].cpu().numpy(), Fr)
+    # the three-kernel path gives the same answer
+    _lib.tunable_set("hybrid.no_fused_tail", 1)
+    try:
+        if world > 1:
+            dev[2 * world * slot:].view(torch.int32).view(2, world, nq_max)[parity, 0, :] = 0
+        F3, O3 = torch.empty_like(out["F"]), torch.empty_like(out["O"])
+        _lib.check(_lib.load().b2r_hybrid_step_dev(
+            flat._h, bm._h, C.c_void_p(q.data_ptr()), nq, C.c_void_p(tids.data_ptr()), C.c_void_p(toffs.data_ptr()), k, 0,
+            arr if world > 1 else None, 0, world, nq_max, k_max, step, C.c_void_p(status.data_ptr()),
+            *[C.c_void_p(out[name].data_ptr()) for name in ("D", "I", "S", "J")], C.c_void_p(F3.data_ptr()),
+            C.c_void_p(O3.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream), 0, C.byref(n_launch)))
+        torch.cuda.synchronize()
+    finally:
+        _lib.tunable_set("hybrid.no_fused_tail", 0)
+    assert n_launch.value >= 3 and torch.equal(F3, out["F"]) and torch.equal(O3, out["O"])
