@@ -71,6 +71,9 @@ int b2r_flat_rows_dev(const b2r_flat* h, const float** out);
 /* D, I = index.search(x=float32[nq,d], k=k)              src/retrieval.py:622,730,1140,1165,1261,1423
  * q, D[nq*k], I[nq*k] are host buffers.  Synchronous, thread-safe. */
 int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, int64_t* I);
+/* Concurrent callers of b2r_flat_search_host on one index are combined: requests that arrive while a search is in
+ * flight are run together as one batch (one pass over the rows for all of them).  Counts batches / requests so far. */
+int b2r_flat_combine_stats(b2r_flat* h, int64_t* batches, int64_t* requests);
 /* Same search with everything resident: q_dev[nq,d], D_dev[nq,k], I_dev[nq,k] on the device,
  * enqueued on `stream`.  id_offset is added to every valid id (global id of a row shard). */
 int b2r_flat_search_dev(b2r_flat* h, const float* q_dev, int nq, int k, float* D_dev,

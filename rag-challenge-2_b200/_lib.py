@@ -43,6 +43,7 @@ SIGNATURES = {
     "b2r_flat_rows_dev": (C.c_int, [_vp, C.POINTER(_vp)]),
     "b2r_flat_search_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "b2r_flat_search_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp]),
+    "b2r_flat_combine_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b2r_flat_search_dev_ex": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, _vp, C.c_uint]),
     "b2r_flat_reconstruct": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "b2r_flat_set_candidate_bf16": (C.c_int, [_vp, C.c_int]),

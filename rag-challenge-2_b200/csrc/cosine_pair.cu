@@ -23,7 +23,7 @@ namespace b2r {
 static const int kCosThreads = 320;   // producer, MMA, 8 epilogue warps (two per TMEM lane quadrant)
 static const int kCosN = 128;        // columns per tile
 static const int kCosSuper = 2048;   // rows / columns of an L2 super-tile
-static const int kCosStages = 4;   // 4 x 48 KiB ring + 32 KiB histogram: all of the 227 KiB; three stages of look-ahead cover the L2 latency (r02)
+static const int kCosStages = 3;   // a 4th stage (all 227 KiB) was measured: no gain (r02) — the ring is not what limits this kernel
 
 struct CosArgs {
   long long n;

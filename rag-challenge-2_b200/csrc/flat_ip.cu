@@ -18,6 +18,8 @@
 //
 // Algorithmic bytes per launch: 4 * n * d  (+ 4*nq*d query, + 12*nq*k result) — see DESIGN.md.
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -464,6 +466,24 @@ struct b2r_flat {
   std::mutex mu;
   float* max_norm2 = nullptr;      // device scalar: max |row|^2 (error bound of the tf32 candidate pass)
   long long max_norm2_rows = -1;   // number of rows it was computed for
+  // Concurrent host callers are COMBINED: a caller that finds a search of this index in flight queues its request; the
+  // caller in charge ("leader") then runs everything queued as ONE batch — one pass over the rows for all of them
+  // instead of one pass each (the reference fans (report, query) pairs out over a thread pool onto the same index
+  // object, src/retrieval.py:1498-1504).  A lone caller never waits.
+  struct HostReq {
+    const float* q;
+    int nq, k;
+    float* D;
+    int64_t* I;
+    int rc = 0;
+    bool done = false;
+    std::string err;
+  };
+  std::mutex bq_mu;
+  std::condition_variable bq_cv;
+  std::deque<HostReq*> bq;
+  bool bq_leader = false;
+  long long combined_batches = 0, combined_requests = 0;  // statistics (b2r_flat_combine_stats)
   bool want_bf16 = false;          // b2r_flat_set_candidate_bf16: keep a bf16 copy of the rows for the candidate pass
   void* rows_bf16 = nullptr;
   long long bf16_rows = -1;        // number of rows the copy covers
@@ -918,24 +938,24 @@ int b2r_flat_search_dev_ex(b2r_flat* h, const float* q_dev, int nq, int k, float
   return flat_search_dev_impl(h, q_dev, nq, k, D_dev, I_dev, id_offset, static_cast<cudaStream_t>(stream), flags);
 }
 
-int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, int64_t* I) {
-  if (!h) return fail(B2R_ERR_INVALID, "b2r_flat_search: NULL handle");
-  if (nq < 0 || k < 1) return fail(B2R_ERR_INVALID, "b2r_flat_search: need nq >= 0 and k >= 1");
-  if (k > B2R_MAX_K) return fail(B2R_ERR_UNSUPPORTED, "b2r_flat_search: k > B2R_MAX_K (1024)");
-  if (nq == 0) return B2R_OK;
-  if (!q || !D || !I) return fail(B2R_ERR_INVALID, "b2r_flat_search: NULL buffer");
-  DeviceGuard g(h->device);
-  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_flat_search: cudaSetDevice failed");
+// one staged batch for several host requests with the same k: queries back to back in, results scattered out
+static int flat_search_host_batch(b2r_flat* h, const std::vector<b2r_flat::HostReq*>& batch, int k) {
   HostCtx* c = nullptr;
   int rc = acquire_ctx(h, &c);
   if (rc) return rc;
-  const size_t q_floats = static_cast<size_t>(nq) * h->d;
-  const size_t nk = static_cast<size_t>(nq) * k;
+  size_t nq = 0;
+  for (const b2r_flat::HostReq* r : batch) nq += static_cast<size_t>(r->nq);
+  const size_t q_floats = nq * h->d;
+  const size_t nk = nq * k;
   const size_t d_bytes = (nk * sizeof(float) + 255) & ~static_cast<size_t>(255);
   const size_t out_bytes = d_bytes + nk * sizeof(int64_t);
   rc = ensure_ctx_buffers(c, q_floats, out_bytes);
   if (rc == B2R_OK) {
-    memcpy(c->q_pin, q, q_floats * sizeof(float));
+    size_t at = 0;
+    for (const b2r_flat::HostReq* r : batch) {
+      memcpy(c->q_pin + at * h->d, r->q, static_cast<size_t>(r->nq) * h->d * sizeof(float));
+      at += static_cast<size_t>(r->nq);
+    }
     // small results (the retriever's case: a few queries x top-n) are written by the kernels straight into mapped
     // pinned host memory — one copy operation (~10 us of a ~55 us call) less; large ones go through a device buffer
     const bool zero_copy = out_bytes <= 256 * 1024;
@@ -944,7 +964,7 @@ int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, i
     int64_t* I_dev = reinterpret_cast<int64_t*>(out_base + d_bytes);
     cudaError_t e = cudaMemcpyAsync(c->q_dev, c->q_pin, q_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-      rc = flat_search_dev_impl(h, c->q_dev, nq, k, D_dev, I_dev, 0, c->stream);
+      rc = flat_search_dev_impl(h, c->q_dev, static_cast<int>(nq), k, D_dev, I_dev, 0, c->stream);
       if (rc == B2R_OK) {
         if (!zero_copy) e = cudaMemcpyAsync(c->out_pin, c->out_dev, out_bytes, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -952,12 +972,86 @@ int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, i
     }
     if (rc == B2R_OK && e != cudaSuccess) rc = fail(B2R_ERR_CUDA, std::string("b2r_flat_search_host: ") + cudaGetErrorString(e));
     if (rc == B2R_OK) {
-      memcpy(D, c->out_pin, nk * sizeof(float));
-      memcpy(I, c->out_pin + d_bytes, nk * sizeof(int64_t));
+      at = 0;
+      for (const b2r_flat::HostReq* r : batch) {
+        memcpy(r->D, c->out_pin + at * k * sizeof(float), static_cast<size_t>(r->nq) * k * sizeof(float));
+        memcpy(r->I, c->out_pin + d_bytes + at * k * sizeof(int64_t), static_cast<size_t>(r->nq) * k * sizeof(int64_t));
+        at += static_cast<size_t>(r->nq);
+      }
     }
   }
   release_ctx(h, c);
   return rc;
+}
+
+int b2r_flat_search_host(b2r_flat* h, const float* q, int nq, int k, float* D, int64_t* I) {
+  if (!h) return fail(B2R_ERR_INVALID, "b2r_flat_search: NULL handle");
+  if (nq < 0 || k < 1) return fail(B2R_ERR_INVALID, "b2r_flat_search: need nq >= 0 and k >= 1");
+  if (k > B2R_MAX_K) return fail(B2R_ERR_UNSUPPORTED, "b2r_flat_search: k > B2R_MAX_K (1024)");
+  if (nq == 0) return B2R_OK;
+  if (!q || !D || !I) return fail(B2R_ERR_INVALID, "b2r_flat_search: NULL buffer");
+  DeviceGuard g(h->device);
+  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_flat_search: cudaSetDevice failed");
+  b2r_flat::HostReq me;
+  me.q = q;
+  me.nq = nq;
+  me.k = k;
+  me.D = D;
+  me.I = I;
+  if (tunable("flat.no_combine")) {
+    std::vector<b2r_flat::HostReq*> one(1, &me);
+    return flat_search_host_batch(h, one, k);
+  }
+  std::unique_lock<std::mutex> lk(h->bq_mu);
+  h->bq.push_back(&me);
+  // somebody is searching: wait until my request has been served, or until the leadership is free
+  h->bq_cv.wait(lk, [&] { return me.done || !h->bq_leader; });
+  if (me.done) {
+    lk.unlock();
+    return me.rc == B2R_OK ? B2R_OK : fail(me.rc, me.err);
+  }
+  h->bq_leader = true;
+  int my_rc = B2R_OK;
+  while (!me.done) {
+    // everything queued with the front request's k (at most 1024 queries) runs as one batch
+    std::vector<b2r_flat::HostReq*> batch;
+    const int kk = h->bq.front()->k;
+    int total = 0;
+    for (auto it = h->bq.begin(); it != h->bq.end();) {
+      if ((*it)->k == kk && (batch.empty() || total + (*it)->nq <= 1024)) {
+        total += (*it)->nq;
+        batch.push_back(*it);
+        it = h->bq.erase(it);
+      } else {
+        ++it;
+      }
+    }
+    lk.unlock();
+    const int rc = flat_search_host_batch(h, batch, kk);
+    const std::string err = rc == B2R_OK ? std::string() : last_error_ref();
+    lk.lock();
+    ++h->combined_batches;
+    h->combined_requests += static_cast<long long>(batch.size());
+    for (b2r_flat::HostReq* r : batch) {
+      r->rc = rc;
+      r->err = err;
+      r->done = true;  // (my own request included: that ends the loop)
+    }
+    if (me.done) my_rc = me.rc;
+    h->bq_cv.notify_all();
+  }
+  h->bq_leader = false;  // whoever is still queued takes over
+  h->bq_cv.notify_all();
+  lk.unlock();
+  return my_rc == B2R_OK ? B2R_OK : fail(my_rc, me.err);
+}
+
+int b2r_flat_combine_stats(b2r_flat* h, int64_t* batches, int64_t* requests) {
+  if (!h) return fail(B2R_ERR_INVALID, "b2r_flat_combine_stats: NULL handle");
+  std::lock_guard<std::mutex> lk(h->bq_mu);
+  if (batches) *batches = h->combined_batches;
+  if (requests) *requests = h->combined_requests;
+  return B2R_OK;
 }
 
 int b2r_flat_reconstruct(b2r_flat* h, const int64_t* ids, int m, float* out) {

@@ -234,3 +234,50 @@ def test_linearity_and_self_match_large(b2r):
     kth = D[:, -1:]
     better = (full > kth + 1e-5).sum(1)
     assert torch.all(better <= 29)
+
+
+def test_concurrent_host_callers_are_combined(b2r):
+    """src/retrieval.py:1498-1504 fans (report, query) pairs out over a thread pool onto one index object.  Host callers
+    that arrive while a search of the index is in flight are run together as ONE batch (one pass over the rows): every
+    caller gets its own answer — the ids of a lone search, scores to fp32 rounding (a combined batch may take the
+    tensor-core path, which rescores in fp32) — and fewer batches than requests reach the GPU."""
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+
+    from rag_challenge_2_b200 import _lib
+
+    xb = unit_rows(300_000, 1024, 61)
+    index = b2r.FlatIPIndex(1024)
+    index.add(xb)
+    xq = queries_for(xb, 64, 62)
+    alone = [index.search(xq[i: i + 1], 30) for i in range(64)]
+    b0, r0 = C.c_int64(0), C.c_int64(0)
+    _lib.check(_lib.load().b2r_flat_combine_stats(index._h, C.byref(b0), C.byref(r0)))
+
+    def work(i):
+        j = i % 64
+        if i % 5 == 0:                                    # a two-query request and another k in the mix
+            return j, index.search(xq[[j, (j + 1) % 64]], 30), 2
+        if i % 7 == 0:
+            return j, index.search(xq[j: j + 1], 10), 1
+        return j, index.search(xq[j: j + 1], 30), 1
+
+    with ThreadPoolExecutor(max_workers=16) as pool:
+        results = list(pool.map(work, range(400)))
+    for j, (D, I), nq in results:
+        k = D.shape[1]
+        assert np.array_equal(I[0], alone[j][1][0][:k]) and np.allclose(D[0], alone[j][0][0][:k], rtol=2e-6, atol=1e-7)
+        if nq == 2:
+            j2 = (j + 1) % 64
+            assert np.array_equal(I[1], alone[j2][1][0]) and np.allclose(D[1], alone[j2][0][0], rtol=2e-6, atol=1e-7)
+    b1, r1 = C.c_int64(0), C.c_int64(0)
+    _lib.check(_lib.load().b2r_flat_combine_stats(index._h, C.byref(b1), C.byref(r1)))
+    assert r1.value - r0.value == 400 and 0 < b1.value - b0.value < 400, (b1.value - b0.value, r1.value - r0.value)
+    print("combined:", r1.value - r0.value, "requests in", b1.value - b0.value, "batches")
+    _lib.tunable_set("flat.no_combine", 1)                # the switch: every caller on its own again
+    try:
+        with ThreadPoolExecutor(max_workers=8) as pool:
+            for j, (D, I), nq in pool.map(work, range(40)):
+                assert np.array_equal(I[0], alone[j][1][0][:D.shape[1]])
+    finally:
+        _lib.tunable_set("flat.no_combine", 0)

@@ -60,6 +60,28 @@ for it in range(4):
     Fb, Ob = nccl.search_hybrid_dev(q[:1], t1, o1, k)
     torch.cuda.synchronize()
     ok &= bool(torch.equal(Oa, Ob) and torch.equal(Fa, Fb) and torch.equal(Oa[0], O1[0]) and torch.equal(Fa[0], F1[0]))
+# a stream of distinct single-query steps, CHAINED by programmatic dependent launch (the scan of step s + 1 queues
+# behind step s, whose BM25 kernel's last CTA exchanges + merges + fuses in place): step for step the un-chained answers
+per_q = []
+for j in range(nq):
+    tj = torch.from_numpy(np.asarray(toks[j], np.int32)).to(dev)
+    oj = torch.tensor([0, len(toks[j])], dtype=torch.int32, device=dev)
+    Fr, Or = nccl.search_hybrid_dev(q[j: j + 1].contiguous(), tj, oj, k)
+    per_q.append((q[j: j + 1].contiguous(), tj, oj, Fr.clone(), Or.clone()))
+torch.cuda.synchronize()
+dist.barrier()
+peer.searcher.pipeline = True
+outs = []
+for it in range(60):
+    qj, tj, oj, _, _ = per_q[it % nq]
+    Fc, Oc = peer.search_hybrid_dev(qj, tj, oj, k)
+    outs.append((Fc.clone(), Oc.clone()))
+torch.cuda.synchronize()
+peer.searcher.peer_exchange.check()
+for it, (Fc, Oc) in enumerate(outs):
+    ok &= bool(torch.equal(Oc, per_q[it % nq][4]) and torch.equal(Fc, per_q[it % nq][3]))
+chained_ok = ok
+peer.searcher.pipeline = False
 Fh, Oh = peer.search_hybrid(q.cpu().numpy(), toks, k)  # host API on every rank (SPMD)
 ok &= bool(np.array_equal(Oh, O1.cpu().numpy()) and np.array_equal(Fh, F1.cpu().numpy()))
 if rank == 0:
@@ -70,7 +92,8 @@ if rank == 0:
     F0, O0 = whole.search_hybrid_dev(q, tids, toffs, k)
     torch.cuda.synchronize()
     same = bool(torch.equal(O0, O1) and torch.equal(F0, F1))
-    print("sharded == unsharded:", same, "| peer == nccl == host API:", ok, "| top1", O1[:4, 0].tolist())
+    print("sharded == unsharded:", same, "| peer == nccl == host API:", ok, "| chained steps == un-chained:", chained_ok,
+          "| launches per single-query step:", peer.searcher.launches, "| top1", O1[:4, 0].tolist())
     ok &= same
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
