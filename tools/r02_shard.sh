@@ -17,6 +17,6 @@ done
 # the hybrid step at shard size: where do the microseconds above the scan go?
 for variant in "" "--no-overlap" "--tunable bm25.v1=2" "--tunable bm25.v1=1"; do
   timeout 300 python bench.py --rows 1250048 --steps 300 --warmup 10 --no-cpu-baseline --no-extras $variant \
-    | python -c "import json,sys; d=json.loads(sys.stdin.readline()); print(json.dumps({'variant': '$variant', 'ms_per_step': d['ms_per_step'], 'e2e_ms': d['e2e']['ms_per_step'], 'scan_ms': d['roofline']['kernel_ms'], 'dense_single_ms': d['extras']['dense_single_query']['ms']}))" \
+    | python -c "import json,sys; d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]); print(json.dumps({'variant': '$variant', 'ms_per_step': d['ms_per_step'], 'e2e_ms': d['e2e']['ms_per_step'], 'scan_ms': d['roofline']['kernel_ms'], 'dense_single_ms': d['extras']['dense_single_query']['ms']}))" \
     | tee -a "$OUT/shard_breakdown.jsonl"
 done
