@@ -388,11 +388,10 @@ struct Bm25StreamArgs {
 };
 
 struct StreamMeta {
-  long long p_begin, p_end;  // valid posting range of this token inside the item's block
-  long long base;            // posting index of element 0 of the stage (16-byte aligned start)
   double idf;
-  int count;                 // elements in the stage
+  int fv, lv;                // valid elements of the stage: [fv, lv) (the copy window is 16-byte aligned, hence wider)
   int flags;                 // 1: last stage of the token, 2: last stage of the item
+  int pad;
 };
 
 template <class W>
@@ -458,8 +457,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
       if (t1 == t0) {  // a query without known tokens: one empty stage closes the item
         if (lane == 0) {
           mbar_wait_wd(&empty[s], ph ^ 1u);
-          meta[s].count = 0;
-          meta[s].p_begin = meta[s].p_end = meta[s].base = 0;
+          meta[s].fv = meta[s].lv = 0;
           meta[s].idf = 0.0;
           meta[s].flags = 3;
           mbar_arrive(&full[s]);
@@ -528,11 +526,9 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
             if (lane == 0) {
               mbar_wait_wd(&empty[s], ph ^ 1u);
               StreamMeta& m = meta[s];
-              m.p_begin = q0;
-              m.p_end = q1;
-              m.base = c0;
               m.idf = qidf;
-              m.count = cnt;
+              m.fv = static_cast<int>(max(q0 - c0, 0LL));
+              m.lv = static_cast<int>(min(q1 - c0, static_cast<long long>(cnt)));
               m.flags = (last_chunk ? 1 : 0) | ((last_chunk && last_token) ? 2 : 0);
               unsigned char* st = ring + static_cast<size_t>(s) * kStageBytes;
               if (cnt > 0) {
@@ -567,28 +563,30 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
   u32* s_cnt = reinterpret_cast<u32*>(ctl);        // [0] candidates, [1] selected, [2] threshold bin, [3] above
   u64* s_mn = ctl + 2;
   u64* s_mx = ctl + 3;
+  // item -> (query, block) without a 64-bit division per item: the coordinates advance with the stride
+  int ql = static_cast<int>(item_lo / a.n_blocks);
+  int b = static_cast<int>(item_lo - static_cast<long long>(ql) * a.n_blocks);
+  const int step_q = static_cast<int>(item_step / a.n_blocks);
+  const int step_b = static_cast<int>(item_step - static_cast<long long>(step_q) * a.n_blocks);
+  const bool no_acc = (a.debug_skip & 2) != 0;
   for (long long item = item_lo; item < item_hi; item += item_step) {
-    const int ql = static_cast<int>(item / a.n_blocks);
-    const int b = static_cast<int>(item - static_cast<long long>(ql) * a.n_blocks);
-    const long long lo = static_cast<long long>(b) * kStreamBlk;
-    const int nb = static_cast<int>(min(a.n_docs, lo + kStreamBlk) - lo);
+    const int lo_i = b * kStreamBlk;
+    const long long lo = lo_i;
+    const int nb = static_cast<int>(min(a.n_docs - lo, static_cast<long long>(kStreamBlk)));
     // the query's threshold is fetched now and used after the accumulation (its latency hides behind the stages; a
     // slightly stale value is only a lower bound that is a little lower)
     const u64 taug_early = a.dense ? 0ull : *(reinterpret_cast<volatile u64*>(a.tau_g) + ql);
     // ---- accumulate: stages arrive in token order (acc is zero: cleared at start / by the previous select) ----
     for (;;) {
       mbar_wait_wd(&full[s], ph);
-      const StreamMeta m = meta[s];
-      const unsigned char* st = ring + static_cast<size_t>(s) * kStageBytes;
-      const int* ids = reinterpret_cast<const int*>(st);
-      const W* ws = reinterpret_cast<const W*>(st + kStreamChunk * 4);
-      for (int i = ct; i < m.count; i += 256) {
-        const long long p = m.base + i;
-        if (p >= m.p_begin && p < m.p_end && !(a.debug_skip & 2)) {
-          const int dl = ids[i] - static_cast<int>(lo);
-          // explicit rn intrinsics: no FMA contraction, numpy forms idf*w and the sum separately
-          acc[dl] = __dadd_rn(acc[dl], __dmul_rn(m.idf, static_cast<double>(ws[i])));
-        }
+      const double idf = meta[s].idf;
+      const int fv = meta[s].fv, lv = no_acc ? 0 : meta[s].lv, fl = meta[s].flags;
+      const int* ids = reinterpret_cast<const int*>(ring + static_cast<size_t>(s) * kStageBytes);
+      const W* ws = reinterpret_cast<const W*>(ring + static_cast<size_t>(s) * kStageBytes + kStreamChunk * 4);
+      for (int i = fv + ct; i < lv; i += 256) {
+        const int dl = ids[i] - lo_i;
+        // explicit rn intrinsics: no FMA contraction, numpy forms idf*w and the sum separately
+        acc[dl] = __dadd_rn(acc[dl], __dmul_rn(idf, static_cast<double>(ws[i])));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
@@ -596,8 +594,15 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
         s = 0;
         ph ^= 1u;
       }
-      if (m.flags & 1) named_bar_sync_256();  // token boundary: the next token may touch the same documents
-      if (m.flags & 2) break;
+      if (fl & 1) named_bar_sync_256();  // token boundary: the next token may touch the same documents
+      if (fl & 2) break;
+    }
+    const int ql_now = ql, b_now = b;  // advance the coordinates for the next item (every path below may `continue`)
+    b += step_b;
+    ql += step_q;
+    if (b >= a.n_blocks) {
+      b -= a.n_blocks;
+      ++ql;
     }
     if (a.dense) {
       for (int i = ct; i < kStreamBlk; i += 256) {
@@ -609,24 +614,39 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
     }
 
     // ---- fused select: best k of this block among the documents that can still matter ----
+    // Fast path (the usual case after a query's first wave): compare the float64 scores with the threshold AS DOUBLES —
+    // three instructions per document; the ordered-bit keys are only formed when some document of the block survives.
     const int k = a.k;
     const u64 taug = (a.debug_skip & 1) ? ~0ull : taug_early;
-    u64 sk[kStreamBlk / 256];
+    // ordered bits -> double is monotonic; 0 means "no threshold yet" (below every score), ~0 is above every score
+    const double tau_d = taug == 0ull ? -__longlong_as_double(0x7FF0000000000000LL)
+                                      : (taug == ~0ull ? __longlong_as_double(0x7FF0000000000000LL) : ordered_to_double(taug));
+    double sv[kStreamBlk / 256];
     u32 act = 0;  // bit i: document i * 256 + ct is a live candidate
 #pragma unroll
     for (int i = 0; i < kStreamBlk / 256; ++i) {
       const int dcl = i * 256 + ct;
-      sk[i] = double_to_ordered(acc[dcl]);
+      sv[i] = acc[dcl];
       acc[dcl] = 0.0;  // ready for the next item (this thread is the only reader of these entries)
-      if (dcl < nb && sk[i] >= taug) act |= 1u << i;
+      if (sv[i] >= tau_d) act |= 1u << i;
     }
-    u128* dst = a.partial + (static_cast<size_t>(ql) * a.n_blocks + b) * k;
+    if (nb < kStreamBlk) {  // the corpus ends inside this block
+#pragma unroll
+      for (int i = 0; i < kStreamBlk / 256; ++i) {
+        if (i * 256 + ct >= nb) act &= ~(1u << i);
+      }
+    }
+    if (taug == ~0ull) act = 0;
+    u128* dst = a.partial + (static_cast<size_t>(ql_now) * a.n_blocks + b_now) * k;
     // ONE barrier decides the usual case (after the first wave of a query no document of a block reaches tau_g): it
     // also orders this item's accumulator reads / clears before the next item's updates
     if (!named_bar_red_or_256(act != 0u)) {
       for (int i = ct; i < k; i += 256) dst[i] = 0;
       continue;
     }
+    u64 sk[kStreamBlk / 256];
+#pragma unroll
+    for (int i = 0; i < kStreamBlk / 256; ++i) sk[i] = double_to_ordered(sv[i]);
     if (ct == 0) {
       s_cnt[0] = 0;
       s_cnt[1] = 0;
@@ -772,7 +792,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
     for (int i = ct; i < k; i += 256) dst[i] = i < p2 ? sel[i] : static_cast<u128>(0);
     if (ct == 0 && n_sel >= k) {
       // k documents of this block score >= sel[k - 1]: nothing below it can enter the query's top k
-      atomicMax(a.tau_g + ql, static_cast<u64>(sel[k - 1] >> 64));
+      atomicMax(a.tau_g + ql_now, static_cast<u64>(sel[k - 1] >> 64));
     }
     named_bar_sync_256();  // the list area is reused by the next item
   }
