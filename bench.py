@@ -674,7 +674,12 @@ def run_b200(args):
     index.searcher.local_bm25 = inner_bm25
 
     # ---- e2e: host buffers in, host buffers out, through the public API ---------------------------------
+    # Every step copies its inputs host -> device from pinned staging and delivers its result to host memory inside the
+    # timed region.  Headline: the next question is SUBMITTED while the previous one is still on the GPU (two in flight:
+    # search_hybrid_submit / _collect — what a caller answering questions from a pool does); also reported: one blocking
+    # call at a time.
     host_batches = [(staged[i][0].cpu().numpy(), staged[i][3]) for i in range(n_batches)]
+    can_submit = index.bm25 is not None and (world == 1 or index.searcher.peer_exchange is not None)
     for i in range(min(args.warmup, 3)):
         index.search_hybrid(host_batches[i % n_batches][0], host_batches[i % n_batches][1], args.k)
     sync_all()
@@ -685,7 +690,20 @@ def run_b200(args):
         Fh, Oh = index.search_hybrid(x, toks, args.k)
     g1.record()
     sync_all()
-    ms_e2e = g0.elapsed_time(g1)
+    ms_e2e_sync = g0.elapsed_time(g1)
+    ms_e2e = ms_e2e_sync
+    if can_submit:
+        g0.record()
+        pending = index.search_hybrid_submit(host_batches[0][0], host_batches[0][1], args.k)
+        for i in range(1, args.steps):
+            x, toks = host_batches[i % n_batches]
+            nxt = index.search_hybrid_submit(x, toks, args.k)
+            Fh, Oh = index.search_hybrid_collect(pending)
+            pending = nxt
+        Fh, Oh = index.search_hybrid_collect(pending)
+        g1.record()
+        sync_all()
+        ms_e2e = g0.elapsed_time(g1)  # both events are recorded on an idle stream with nothing outstanding: wall time
     h2d, d2h = index.last_h2d_bytes, index.last_d2h_bytes
     sampler.stop()
 
@@ -708,10 +726,10 @@ def run_b200(args):
         extras[name] = {"ms": msx, "local_rows": hi - lo, "queries_per_s_local_shard": nqx / msx * 1e3,
                         "GBps_equiv": 4.0 * (hi - lo) * args.dim / msx / 1e6}
 
-    times = torch.tensor([ms_total, ms_e2e, scan_ms, ms_unpipelined], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, ms_e2e, scan_ms, ms_unpipelined, ms_e2e_sync], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, scan_ms, ms_unpipelined = times.tolist()
+    ms_total, ms_e2e, scan_ms, ms_unpipelined, ms_e2e_sync = times.tolist()
 
     if rank == 0:
         value = args.nq * args.steps / (ms_total / 1e3)
@@ -724,7 +742,12 @@ def run_b200(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "in_flight": (2 if can_submit else 1),
+                    "how": ("HybridIndex.search_hybrid_submit / _collect: numpy in, numpy out, the next question submitted while the "
+                            "previous one is on the GPU; every step's H2D copy and result delivery inside the timed region"
+                            if can_submit else "HybridIndex.search_hybrid, one blocking call per step"),
+                    "one_call_at_a_time": {"value": args.nq * args.steps / (ms_e2e_sync / 1e3), "ms_per_step": ms_e2e_sync / args.steps}},
             "gpu_launches": int(launches), "collectives": int(collectives), "exchange": exchange,
             "roofline": {"bound": "hbm", "kernel": "flat_scan_tma_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(hi - lo, args.dim),

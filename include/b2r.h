@@ -209,6 +209,16 @@ int b2r_hybrid_search_host(b2r_hybrid_ctx* ctx, b2r_flat* flat, b2r_bm25* bm25, 
                            const int32_t* term_ids, const int32_t* term_offsets, int k, int64_t id_offset,
                            void* const* peer_bufs, int rank, int world, int nq_max, int k_max, uint32_t step,
                            float* F, int64_t* O);
+/* The same call in two halves, so that a caller with several questions pending (the reference answers questions from a
+ * thread pool, src/questions_processing.py:1123-1125) keeps the GPU busy: submit copies the inputs into one of the
+ * context's two staging slots, enqueues the H2D copy and the step and returns a ticket; collect waits for that step and
+ * copies F / O out.  At most two submissions may be outstanding per context; they execute in submission order on the
+ * context's stream, and with world > 1 every rank must submit the same sequence.  search_host == submit + collect. */
+int b2r_hybrid_submit_host(b2r_hybrid_ctx* ctx, b2r_flat* flat, b2r_bm25* bm25, const float* q, int nq, int d,
+                           const int32_t* term_ids, const int32_t* term_offsets, int k, int64_t id_offset,
+                           void* const* peer_bufs, int rank, int world, int nq_max, int k_max, uint32_t step,
+                           int* ticket);
+int b2r_hybrid_collect_host(b2r_hybrid_ctx* ctx, int ticket, float* F, int64_t* O);
 
 /* The same step with everything resident (device pointers; enqueued on `stream`, nothing synchronised): the dense scan
  * and BM25 launched beside it; for up to 4 queries and k <= 256 the LAST CTA of each query's BM25 grid waits for the

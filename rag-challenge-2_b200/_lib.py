@@ -63,6 +63,9 @@ SIGNATURES = {
     "b2r_hybrid_ctx_bytes": (C.c_int, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "b2r_hybrid_search_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int64,
                                         C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _vp, _vp]),
+    "b2r_hybrid_submit_host": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int64,
+                                        C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int)]),
+    "b2r_hybrid_collect_host": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "b2r_topk_merge_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int]),
     "b2r_bm25_create": (C.c_int, [C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_double,
                                   C.c_double, C.c_int, C.POINTER(_vp)]),

@@ -14,17 +14,32 @@
 
 #include "hybrid_fuse.cuh"
 
-struct b2r_hybrid_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
+// Two slots of staging per context: a caller may SUBMIT the next question while the previous one is still on the GPU
+// (b2r_hybrid_submit_host / b2r_hybrid_collect_host) — both are enqueued on the context's one stream, so the GPU goes
+// from one step to the next without waiting for the host.  b2r_hybrid_search_host is submit + collect.
+static const int kHybridSlots = 2;
+
+struct HybridSlot {
   unsigned char* in_pin = nullptr;
   unsigned char* in_dev = nullptr;
   size_t in_cap = 0;
-  unsigned char* out_pin = nullptr;  // mapped pinned host memory: the fusion kernel stores F / O straight into it
+  unsigned char* out_pin = nullptr;      // mapped pinned host memory: the fusion stores F / O straight into it
   unsigned char* out_pin_dev = nullptr;  // device alias of out_pin
-  unsigned char* out_dev = nullptr;  // intermediate lists [I int64][S double][J int64][D float]
-  size_t out_cap = 0;                // in (nq * k) units
-  std::mutex mu;                     // one step at a time per context (create one context per host thread)
+  unsigned char* out_dev = nullptr;      // intermediate lists [I int64][S double][J int64][D float]
+  size_t out_cap = 0;                    // in (nq * k) units
+  cudaEvent_t done = nullptr;
+  bool busy = false;
+  size_t nk = 0, h2d = 0;
+  int world = 1;
+  uint32_t step = 0;
+};
+
+struct b2r_hybrid_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  HybridSlot slot[kHybridSlots];
+  int next = 0;
+  std::mutex mu;                     // submissions / collections of one context are serialised
   size_t last_h2d = 0, last_d2h = 0;
 };
 
@@ -83,7 +98,7 @@ static int hybrid_step_dev(b2r_flat* flat, b2r_bm25* bm25, const float* q_dev, i
   return rc;
 }
 
-static int ctx_reserve(b2r_hybrid_ctx* c, size_t in_bytes, size_t nk) {
+static int slot_reserve(HybridSlot* c, size_t in_bytes, size_t nk) {
   if (c->in_cap < in_bytes) {
     const size_t cap = std::max<size_t>(in_bytes, 1 << 16);
     if (c->in_pin) cudaFreeHost(c->in_pin);
@@ -105,6 +120,7 @@ static int ctx_reserve(b2r_hybrid_ctx* c, size_t in_bytes, size_t nk) {
     B2R_CUDA(cudaMalloc(&c->out_dev, cap * 28));
     c->out_cap = cap;
   }
+  if (!c->done) B2R_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
   return B2R_OK;
 }
 
@@ -133,10 +149,13 @@ int b2r_hybrid_ctx_destroy(b2r_hybrid_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamDestroy(c->stream);
   }
-  if (c->in_pin) cudaFreeHost(c->in_pin);
-  if (c->in_dev) cudaFree(c->in_dev);
-  if (c->out_pin) cudaFreeHost(c->out_pin);
-  if (c->out_dev) cudaFree(c->out_dev);
+  for (HybridSlot& sl : c->slot) {
+    if (sl.in_pin) cudaFreeHost(sl.in_pin);
+    if (sl.in_dev) cudaFree(sl.in_dev);
+    if (sl.out_pin) cudaFreeHost(sl.out_pin);
+    if (sl.out_dev) cudaFree(sl.out_dev);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   delete c;
   return B2R_OK;
 }
@@ -148,19 +167,18 @@ int b2r_hybrid_ctx_bytes(const b2r_hybrid_ctx* c, size_t* h2d, size_t* d2h) {
   return B2R_OK;
 }
 
-int b2r_hybrid_search_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, const float* q, int nq, int d,
+int b2r_hybrid_submit_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, const float* q, int nq, int d,
                            const int32_t* term_ids, const int32_t* term_offsets, int k, int64_t id_offset,
-                           void* const* peer_bufs, int rank, int world, int nq_max, int k_max, uint32_t step, float* F,
-                           int64_t* O) {
-  if (!c || !flat || !bm25) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: NULL handle");
-  if (nq < 1 || d < 1 || k < 1 || k > B2R_MAX_K) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: bad sizes");
-  if (!q || !term_offsets || !F || !O) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: NULL buffer");
+                           void* const* peer_bufs, int rank, int world, int nq_max, int k_max, uint32_t step, int* ticket) {
+  if (!c || !flat || !bm25 || !ticket) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: NULL handle");
+  if (nq < 1 || d < 1 || k < 1 || k > B2R_MAX_K) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: bad sizes");
+  if (!q || !term_offsets) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: NULL buffer");
   int fd = 0;
   int rc = b2r_flat_dim(flat, &fd);
   if (rc) return rc;
-  if (fd != d) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: query width does not match the index");
+  if (fd != d) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: query width does not match the index");
   const int n_terms = term_offsets[nq];
-  if (term_offsets[0] != 0 || n_terms < 0 || (n_terms > 0 && !term_ids)) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: bad term offsets");
+  if (term_offsets[0] != 0 || n_terms < 0 || (n_terms > 0 && !term_ids)) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: bad term offsets");
   // everything that can be rejected is rejected HERE, before anything is enqueued: in the multi-GPU step a rank that
   // fails after its peers launched leaves them waiting (for exchange.timeout_ms) on a kernel that never comes
   rc = bm25_check_terms(bm25, term_ids, n_terms);
@@ -168,57 +186,95 @@ int b2r_hybrid_search_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, co
   int64_t n_rows = 0;
   rc = b2r_flat_ntotal(flat, &n_rows);
   if (rc) return rc;
-  if (id_offset < 0 || id_offset + n_rows >= 0xFFFFFFF0LL) return fail(B2R_ERR_UNSUPPORTED, "b2r_hybrid_search_host: global ids must stay below 2^32-16 (the fusion packs them in 32 bits)");
-  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: bad rank / world");
+  if (id_offset < 0 || id_offset + n_rows >= 0xFFFFFFF0LL) return fail(B2R_ERR_UNSUPPORTED, "b2r_hybrid_submit_host: global ids must stay below 2^32-16 (the fusion packs them in 32 bits)");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: bad rank / world");
   if (world > 1) {
-    if (!peer_bufs) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: world > 1 needs the peer buffers");
+    if (!peer_bufs) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: world > 1 needs the peer buffers");
     for (int p = 0; p < world; ++p)
-      if (!peer_bufs[p]) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: NULL peer buffer");
-    if (nq > nq_max || k > k_max || k > 256) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: nq / k exceed the exchange buffer geometry");
-    if (step == 0) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: step must be >= 1");
+      if (!peer_bufs[p]) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: NULL peer buffer");
+    if (nq > nq_max || k > k_max || k > 256) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: nq / k exceed the exchange buffer geometry");
+    if (step == 0) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: step must be >= 1");
   }
   DeviceGuard g(c->device);
-  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_hybrid_search_host: cudaSetDevice failed");
+  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_hybrid_submit_host: cudaSetDevice failed");
   std::lock_guard<std::mutex> lock(c->mu);
+  HybridSlot* sl = &c->slot[c->next];
+  if (sl->busy) return fail(B2R_ERR_INVALID, "b2r_hybrid_submit_host: both slots of this context are in flight: collect one first");
   const size_t qb = static_cast<size_t>(nq) * d * 4, ob = (static_cast<size_t>(nq) + 1) * 4;
   const size_t tb = static_cast<size_t>(std::max(n_terms, 1)) * 4;
   const size_t in_bytes = qb + ob + tb;
   const size_t nk = static_cast<size_t>(nq) * k;
-  rc = ctx_reserve(c, in_bytes, nk);
+  rc = slot_reserve(sl, in_bytes, nk);
   if (rc) return rc;
-  memcpy(c->in_pin, q, qb);
-  memcpy(c->in_pin + qb, term_offsets, ob);
-  if (n_terms) memcpy(c->in_pin + qb + ob, term_ids, static_cast<size_t>(n_terms) * 4);
+  memcpy(sl->in_pin, q, qb);
+  memcpy(sl->in_pin + qb, term_offsets, ob);
+  if (n_terms) memcpy(sl->in_pin + qb + ob, term_ids, static_cast<size_t>(n_terms) * 4);
   const size_t h2d = qb + ob + static_cast<size_t>(n_terms) * 4;
-  B2R_CUDA(cudaMemcpyAsync(c->in_dev, c->in_pin, h2d, cudaMemcpyHostToDevice, c->stream));
-  const float* q_dev = reinterpret_cast<const float*>(c->in_dev);
-  const int32_t* offs_dev = reinterpret_cast<const int32_t*>(c->in_dev + qb);
-  const int32_t* tids_dev = reinterpret_cast<const int32_t*>(c->in_dev + qb + ob);
-  // results: the fusion kernel writes O[nq*k] int64 and F[nq*k] float directly into mapped pinned host memory
+  B2R_CUDA(cudaMemcpyAsync(sl->in_dev, sl->in_pin, h2d, cudaMemcpyHostToDevice, c->stream));
+  const float* q_dev = reinterpret_cast<const float*>(sl->in_dev);
+  const int32_t* offs_dev = reinterpret_cast<const int32_t*>(sl->in_dev + qb);
+  const int32_t* tids_dev = reinterpret_cast<const int32_t*>(sl->in_dev + qb + ob);
+  // results: the fusion writes O[nq*k] int64 and F[nq*k] float directly into mapped pinned host memory
   // (12 * nq * k bytes of posted PCIe writes instead of two device->host copy operations)
-  int64_t* O_dev = reinterpret_cast<int64_t*>(c->out_pin_dev);
-  float* F_dev = reinterpret_cast<float*>(c->out_pin_dev + nk * 8);
-  unsigned char* mid = c->out_dev;
+  int64_t* O_dev = reinterpret_cast<int64_t*>(sl->out_pin_dev);
+  float* F_dev = reinterpret_cast<float*>(sl->out_pin_dev + nk * 8);
+  unsigned char* mid = sl->out_dev;
   int64_t* I_dev = reinterpret_cast<int64_t*>(mid);
-  double* S_dev = reinterpret_cast<double*>(mid + c->out_cap * 8);
-  int64_t* J_dev = reinterpret_cast<int64_t*>(mid + c->out_cap * 16);
-  float* D_dev = reinterpret_cast<float*>(mid + c->out_cap * 24);
-  volatile uint32_t* status_host = reinterpret_cast<volatile uint32_t*>(c->out_pin + c->out_cap * 12);
-  *status_host = 0;
+  double* S_dev = reinterpret_cast<double*>(mid + sl->out_cap * 8);
+  int64_t* J_dev = reinterpret_cast<int64_t*>(mid + sl->out_cap * 16);
+  float* D_dev = reinterpret_cast<float*>(mid + sl->out_cap * 24);
+  *reinterpret_cast<volatile uint32_t*>(sl->out_pin + sl->out_cap * 12) = 0;
   rc = hybrid_step_dev(flat, bm25, q_dev, nq, tids_dev, offs_dev, k, id_offset, peer_bufs, rank, world, nq_max, k_max, step,
-                       reinterpret_cast<uint32_t*>(c->out_pin_dev + c->out_cap * 12), D_dev, I_dev, S_dev, J_dev, F_dev, O_dev,
+                       reinterpret_cast<uint32_t*>(sl->out_pin_dev + sl->out_cap * 12), D_dev, I_dev, S_dev, J_dev, F_dev, O_dev,
                        c->stream, 0u, nullptr);
   if (rc) return rc;
-  B2R_CUDA(cudaStreamSynchronize(c->stream));
-  if (world > 1 && *status_host != 0) {
-    return fail(B2R_ERR_CUDA, "b2r_hybrid_search_host: the exchange timed out waiting for rank " + std::to_string(*status_host - 1) +
-                                  " (step " + std::to_string(step) + "): a peer failed or the ranks are out of lockstep");
-  }
-  memcpy(O, c->out_pin, nk * 8);
-  memcpy(F, c->out_pin + nk * 8, nk * 4);
-  c->last_h2d = h2d;
-  c->last_d2h = nk * 12;
+  B2R_CUDA(cudaEventRecord(sl->done, c->stream));
+  sl->busy = true;
+  sl->nk = nk;
+  sl->h2d = h2d;
+  sl->world = world;
+  sl->step = step;
+  *ticket = c->next;
+  c->next = (c->next + 1) % kHybridSlots;
   return B2R_OK;
+}
+
+int b2r_hybrid_collect_host(b2r_hybrid_ctx* c, int ticket, float* F, int64_t* O) {
+  if (!c || !F || !O) return fail(B2R_ERR_INVALID, "b2r_hybrid_collect_host: NULL argument");
+  if (ticket < 0 || ticket >= kHybridSlots) return fail(B2R_ERR_INVALID, "b2r_hybrid_collect_host: bad ticket");
+  DeviceGuard g(c->device);
+  if (!g.ok) return fail(B2R_ERR_CUDA, "b2r_hybrid_collect_host: cudaSetDevice failed");
+  HybridSlot* sl = &c->slot[ticket];
+  {
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!sl->busy) return fail(B2R_ERR_INVALID, "b2r_hybrid_collect_host: nothing was submitted under this ticket");
+  }
+  cudaError_t e = cudaEventSynchronize(sl->done);
+  std::lock_guard<std::mutex> lock(c->mu);
+  sl->busy = false;
+  if (e != cudaSuccess) return fail(B2R_ERR_CUDA, std::string("b2r_hybrid_collect_host: ") + cudaGetErrorString(e));
+  const uint32_t status = *reinterpret_cast<volatile uint32_t*>(sl->out_pin + sl->out_cap * 12);
+  if (sl->world > 1 && status != 0) {
+    return fail(B2R_ERR_CUDA, "b2r_hybrid_collect_host: the exchange timed out waiting for rank " + std::to_string(status - 1) +
+                                  " (step " + std::to_string(sl->step) + "): a peer failed or the ranks are out of lockstep");
+  }
+  memcpy(O, sl->out_pin, sl->nk * 8);
+  memcpy(F, sl->out_pin + sl->nk * 8, sl->nk * 4);
+  c->last_h2d = sl->h2d;
+  c->last_d2h = sl->nk * 12;
+  return B2R_OK;
+}
+
+int b2r_hybrid_search_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, const float* q, int nq, int d,
+                           const int32_t* term_ids, const int32_t* term_offsets, int k, int64_t id_offset,
+                           void* const* peer_bufs, int rank, int world, int nq_max, int k_max, uint32_t step, float* F,
+                           int64_t* O) {
+  if (!F || !O) return fail(B2R_ERR_INVALID, "b2r_hybrid_search_host: NULL buffer");
+  int ticket = -1;
+  int rc = b2r_hybrid_submit_host(c, flat, bm25, q, nq, d, term_ids, term_offsets, k, id_offset, peer_bufs, rank, world, nq_max,
+                                  k_max, step, &ticket);
+  if (rc) return rc;
+  return b2r_hybrid_collect_host(c, ticket, F, O);
 }
 
 // The resident step (see hybrid_step_dev above): q_dev[nq,d], term ids / offsets, and all outputs live on the device;

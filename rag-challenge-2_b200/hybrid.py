@@ -383,8 +383,18 @@ class HybridIndex:
         return self._search_hybrid_py(x, queries_term_ids, k)
 
     def _search_hybrid_c(self, x, queries_term_ids, k):
+        return self.search_hybrid_collect(self.search_hybrid_submit(x, queries_term_ids, k))
+
+    def search_hybrid_submit(self, x, queries_term_ids, k):
+        """First half of search_hybrid: stages the inputs, enqueues the H2D copy and the step, returns a ticket at once.
+        Up to two submissions may be outstanding (the next question is submitted while the previous one is still on the
+        GPU, so the device goes from step to step without waiting for the host); collect them in submission order.
+        With several ranks every rank must submit the same sequence.  (One rank, or the peer-memory exchange.)"""
         import numpy as np
 
+        s = self.searcher
+        if self.bm25 is None or not (s.world_size == 1 or s.peer_exchange is not None):
+            raise RuntimeError("search_hybrid_submit needs a BM25 index and, on several ranks, the peer-memory exchange")
         lib = _lib.load()
         if self._ctx is None:
             h = C.c_void_p()
@@ -396,9 +406,6 @@ class HybridIndex:
         np.cumsum([len(t) for t in queries_term_ids], out=offs[1:])
         tids = (np.concatenate([np.asarray(t, np.int32) for t in queries_term_ids]) if offs[-1]
                 else np.zeros(1, np.int32)).astype(np.int32, copy=False)
-        F = np.empty((nq, k), dtype=np.float32)
-        O = np.empty((nq, k), dtype=np.int64)
-        s = self.searcher
         px = s.peer_exchange
         if px is not None:
             import torch
@@ -409,13 +416,23 @@ class HybridIndex:
         else:
             args = (None, 0, 1, 0, 0, 0)
         self.bm25._ensure_built()
-        _lib.check(lib.b2r_hybrid_search_host(self._ctx, self.flat._h, self.bm25._h, _lib.ptr(x), nq, d, _lib.ptr(tids),
-                                              _lib.ptr(offs), int(k), self.offset, *args, _lib.ptr(F), _lib.ptr(O)))
+        ticket = C.c_int(-1)
+        _lib.check(lib.b2r_hybrid_submit_host(self._ctx, self.flat._h, self.bm25._h, _lib.ptr(x), nq, d, _lib.ptr(tids),
+                                              _lib.ptr(offs), int(k), self.offset, *args, C.byref(ticket)))
         if px is not None:
             px.step += 1   # only after the call succeeded: a rejected call enqueued nothing (the checks come first)
-        h2d, d2h = C.c_size_t(0), C.c_size_t(0)
-        lib.b2r_hybrid_ctx_bytes(self._ctx, C.byref(h2d), C.byref(d2h))
-        self.last_h2d_bytes, self.last_d2h_bytes = int(h2d.value), int(d2h.value)
+        self.last_h2d_bytes = 4 * nq * d + 4 * (nq + 1) + 4 * int(offs[-1])
+        self.last_d2h_bytes = 12 * nq * int(k)
+        return (int(ticket.value), nq, int(k))
+
+    def search_hybrid_collect(self, ticket):
+        """Second half: waits for the submitted step and returns (F float32[nq,k], O int64[nq,k])."""
+        import numpy as np
+
+        t, nq, k = ticket
+        F = np.empty((nq, k), dtype=np.float32)
+        O = np.empty((nq, k), dtype=np.int64)
+        _lib.check(_lib.load().b2r_hybrid_collect_host(self._ctx, t, _lib.ptr(F), _lib.ptr(O)))
         return F, O
 
     def close(self):

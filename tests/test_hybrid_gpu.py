@@ -350,3 +350,42 @@ def test_fused_tail_step_emulated_ranks(b2r, world, k, step, nq):
     finally:
         _lib.tunable_set("hybrid.no_fused_tail", 0)
     assert n_launch.value >= 3 and torch.equal(F3, out["F"]) and torch.equal(O3, out["O"])
+
+
+def test_submit_collect_two_in_flight(b2r):
+    """search_hybrid_submit / _collect: the next question is submitted while the previous one is on the GPU; answers equal
+    the blocking call's, a third outstanding submission is refused, tickets are collected in order."""
+    import torch
+
+    from rag_challenge_2_b200 import _lib, hybrid, synth
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    n, d, V, k = 120_000, 1024, 4000, 30
+    rows = synth.dense_rows_torch(0, n, d, "cuda", seed=401)
+    post = synth.token_postings_torch(0, n, V, "cuda", seed=402)
+    idf, _ = synth.bm25_idf_from_df(post["df"].cpu().numpy(), n)
+    bm = BM25Okapi.from_postings(post["indptr"], post["doc_ids"], post["tf"], post["doc_len"], torch.from_numpy(idf).cuda(),
+                                 post["total_len"] / n)
+    index = hybrid.HybridIndex(b2r.FlatIPIndex.from_device_tensor(rows), bm, 0, world_size=1)
+    q = synth.dense_queries_torch(12, d, "cuda", rows, seed=403).cpu().numpy()
+    toks = synth.token_queries_np(12, vocab=V, seed=404)
+    want = [index.search_hybrid(q[i: i + 1], [toks[i]], k) for i in range(12)]
+    pending = index.search_hybrid_submit(q[0:1], [toks[0]], k)
+    got = []
+    for i in range(1, 12):
+        nxt = index.search_hybrid_submit(q[i: i + 1], [toks[i]], k)
+        got.append(index.search_hybrid_collect(pending))
+        pending = nxt
+    got.append(index.search_hybrid_collect(pending))
+    for (F, O), (Fw, Ow) in zip(got, want):
+        assert np.array_equal(O, Ow) and np.array_equal(F, Fw)
+    t0 = index.search_hybrid_submit(q[0:1], [toks[0]], k)
+    t1 = index.search_hybrid_submit(q[1:2], [toks[1]], k)
+    with pytest.raises(_lib.B2RError):
+        index.search_hybrid_submit(q[2:3], [toks[2]], k)          # both slots in flight
+    F0, O0 = index.search_hybrid_collect(t0)
+    F1, O1 = index.search_hybrid_collect(t1)
+    assert np.array_equal(O0, want[0][1]) and np.array_equal(O1, want[1][1])
+    with pytest.raises(_lib.B2RError):
+        index.search_hybrid_collect(t0)                            # nothing outstanding under that ticket
+    index.close()
