@@ -28,6 +28,7 @@ struct HybridSlot {
   unsigned char* out_dev = nullptr;      // intermediate lists [I int64][S double][J int64][D float]
   size_t out_cap = 0;                    // in (nq * k) units
   cudaEvent_t done = nullptr;
+  cudaEvent_t in_ready = nullptr;        // the slot's inputs have arrived in in_dev (recorded on the copy stream)
   bool busy = false;
   size_t nk = 0, h2d = 0;
   int world = 1;
@@ -37,6 +38,7 @@ struct HybridSlot {
 struct b2r_hybrid_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;    // H2D copies of the NEXT question overlap the step that is running
   HybridSlot slot[kHybridSlots];
   int next = 0;
   std::mutex mu;                     // submissions / collections of one context are serialised
@@ -121,6 +123,7 @@ static int slot_reserve(HybridSlot* c, size_t in_bytes, size_t nk) {
     c->out_cap = cap;
   }
   if (!c->done) B2R_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+  if (!c->in_ready) B2R_CUDA(cudaEventCreateWithFlags(&c->in_ready, cudaEventDisableTiming));
   return B2R_OK;
 }
 
@@ -134,6 +137,7 @@ int b2r_hybrid_ctx_create(int device, b2r_hybrid_ctx** out) {
   b2r_hybrid_ctx* c = new b2r_hybrid_ctx();
   c->device = device;
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete c;
     return fail(B2R_ERR_CUDA, std::string("b2r_hybrid_ctx_create: ") + cudaGetErrorString(e));
@@ -149,12 +153,17 @@ int b2r_hybrid_ctx_destroy(b2r_hybrid_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamDestroy(c->stream);
   }
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
   for (HybridSlot& sl : c->slot) {
     if (sl.in_pin) cudaFreeHost(sl.in_pin);
     if (sl.in_dev) cudaFree(sl.in_dev);
     if (sl.out_pin) cudaFreeHost(sl.out_pin);
     if (sl.out_dev) cudaFree(sl.out_dev);
     if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.in_ready) cudaEventDestroy(sl.in_ready);
   }
   delete c;
   return B2R_OK;
@@ -210,7 +219,11 @@ int b2r_hybrid_submit_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, co
   memcpy(sl->in_pin + qb, term_offsets, ob);
   if (n_terms) memcpy(sl->in_pin + qb + ob, term_ids, static_cast<size_t>(n_terms) * 4);
   const size_t h2d = qb + ob + static_cast<size_t>(n_terms) * 4;
-  B2R_CUDA(cudaMemcpyAsync(sl->in_dev, sl->in_pin, h2d, cudaMemcpyHostToDevice, c->stream));
+  // the copy runs on its own stream, so the inputs of this question travel while the previous question's step is still
+  // executing; the step waits for the event, not for the copy engine's turn behind the previous kernels
+  B2R_CUDA(cudaMemcpyAsync(sl->in_dev, sl->in_pin, h2d, cudaMemcpyHostToDevice, c->copy_stream));
+  B2R_CUDA(cudaEventRecord(sl->in_ready, c->copy_stream));
+  B2R_CUDA(cudaStreamWaitEvent(c->stream, sl->in_ready, 0));
   const float* q_dev = reinterpret_cast<const float*>(sl->in_dev);
   const int32_t* offs_dev = reinterpret_cast<const int32_t*>(sl->in_dev + qb);
   const int32_t* tids_dev = reinterpret_cast<const int32_t*>(sl->in_dev + qb + ob);
@@ -226,7 +239,7 @@ int b2r_hybrid_submit_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, co
   *reinterpret_cast<volatile uint32_t*>(sl->out_pin + sl->out_cap * 12) = 0;
   rc = hybrid_step_dev(flat, bm25, q_dev, nq, tids_dev, offs_dev, k, id_offset, peer_bufs, rank, world, nq_max, k_max, step,
                        reinterpret_cast<uint32_t*>(sl->out_pin_dev + sl->out_cap * 12), D_dev, I_dev, S_dev, J_dev, F_dev, O_dev,
-                       c->stream, 0u, nullptr);
+                       c->stream, tunable("hybrid.host_chain") ? B2R_LAUNCH_OVERLAP_PREVIOUS : 0u, nullptr);
   if (rc) return rc;
   B2R_CUDA(cudaEventRecord(sl->done, c->stream));
   sl->busy = true;
