@@ -252,6 +252,33 @@ int b2r_cosine_stats_dev(const float* rows_dev, int64_t n, int d, int64_t row_be
                          double* stats_dev, unsigned long long* hist_dev, int n_bins, int k,
                          float* topk_S_dev, int64_t* topk_I_dev, int device, void* stream);
 
+/* ---- index build on the GPU ------------------------------------------------------------------ */
+/* BM25Okapi([chunk.split() ...]) after host tokenisation, from a token stream       src/ingestion.py:19-22
+ * token_ids[total] (term ids of all documents back to back), doc_offsets[n_docs + 1]; all pointers are device
+ * pointers, everything is enqueued on `stream`.  Phase 1 writes every document's unique (term, tf) pairs over its own
+ * token slots (pair_term / pair_tf [total]), n_unique / doc_len [n_docs], df [n_terms] (caller zeroes it),
+ * first_pos [n_terms] (caller fills it with INT64_MAX; receives pos_offset + the index of every term's first token —
+ * rank_bm25 averages the idf values in first-seen order), cell [n_terms][ceil(n_docs / 4096) + 1] (caller zeroes it;
+ * left holding every term's posting offset of every 4096-document block), indptr [n_terms + 1], and *error_flag
+ * (1: a document has more than 1024 tokens, 2: a term id is out of range — the outputs are then unusable).
+ * Phase 2 places the postings: doc_ids / tf [indptr[n_terms]], ascending document ids inside a term; cursor is a
+ * zeroed scratch shaped like cell. */
+int b2r_bm25_build_count_dev(const int32_t* token_ids, const int64_t* doc_offsets, int64_t n_docs,
+                             int32_t n_terms, int64_t pos_offset, int32_t* pair_term, int32_t* pair_tf,
+                             int32_t* n_unique, int32_t* doc_len, uint64_t* df, int64_t* first_pos,
+                             uint32_t* cell, int64_t* indptr, int32_t* error_flag, void* stream);
+int b2r_bm25_build_place_dev(const int64_t* doc_offsets, int64_t n_docs, int32_t n_terms,
+                             const int32_t* pair_term, const int32_t* pair_tf, const int32_t* n_unique,
+                             const int64_t* indptr, const uint32_t* cell, uint32_t* cursor,
+                             int32_t* doc_ids, int32_t* tf, void* stream);
+/* Down-sampled heat map of the N x N cosine matrix      generate_similarity_matrix.py:124-160 (plots the full matrix)
+ * bounds[p + 1]: ascending row boundaries of the p pixel groups; tiles[p, p] = mean of clip(Xn Xn^T) over the rows of
+ * group a and the columns of group b, the diagonal of the matrix taken as 1.  Scratch: div[n] float32, pooled[p, d] and
+ * self_dot[p] float64. */
+int b2r_cosine_heatmap_dev(const float* rows_dev, int64_t n, int d, const int64_t* bounds_dev, int p,
+                           float* div_dev, double* pooled_dev, double* self_dot_dev, float* tiles_dev,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

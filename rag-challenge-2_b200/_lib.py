@@ -55,6 +55,10 @@ SIGNATURES = {
     "b2r_hybrid_exchange_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "b2r_hybrid_exchange_fuse_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, C.c_int,
                                               C.c_int, C.c_int, C.c_uint32, _vp, _vp, _vp, _vp]),
+    "b2r_bm25_build_count_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                          _vp]),
+    "b2r_bm25_build_place_dev": (C.c_int, [_vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2r_cosine_heatmap_dev": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "b2r_hybrid_step_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.POINTER(_vp), C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint,
                                      C.POINTER(C.c_int)]),

@@ -39,37 +39,87 @@ def corpus_statistics(nd, corpus_size, epsilon=0.25):
     return idf, average_idf
 
 
-def token_stream_statistics(token_ids, doc_offsets, n_terms, epsilon=0.25, device=None, group=None):
-    """Tokenised corpus -> CSR postings + rank_bm25 statistics with torch ops on `device` (CUDA in the product;
-    the CPU is only used by the gloo plumbing test).  Returns dict(indptr, doc_ids, tf, doc_len tensors; idf
-    float64 numpy [n_terms] (0 for terms that never occur); avgdl; average_idf; corpus_size)."""
+def _postings_from_tokens_cuda(tok, offs, n_terms, pos_offset):
+    """CSR postings of a tokenised corpus with this library's kernels (csrc/index_build.cu): per-document warp sort ->
+    unique (term, tf) pairs, df / first positions / per-block counts by atomics, block offsets by a scan, placement in
+    document order.  tok int32 CUDA [total], offs int64 CUDA [n_docs + 1].  Returns None when a document is longer than
+    the warp sort takes (1024 tokens): the caller then uses the torch sort path."""
     import torch
 
-    tok = torch.as_tensor(token_ids).to(device=device, dtype=torch.int64).reshape(-1)
-    offs = torch.as_tensor(doc_offsets).to(device=device, dtype=torch.int64).reshape(-1)
+    lib = _lib.load()
+    dev = tok.device
     n_docs = int(offs.shape[0]) - 1
-    lens = offs[1:] - offs[:-1]
-    doc_of = torch.repeat_interleave(torch.arange(n_docs, device=tok.device), lens)
-    key, _ = torch.sort(tok * max(n_docs, 1) + doc_of)
-    uniq, counts = torch.unique_consecutive(key, return_counts=True)
-    term = uniq // max(n_docs, 1)
-    doc_ids = (uniq - term * max(n_docs, 1)).to(torch.int32)
-    df = torch.bincount(term, minlength=n_terms)
-    indptr = torch.zeros(n_terms + 1, dtype=torch.int64, device=tok.device)
-    indptr[1:] = torch.cumsum(df, 0)
-    # rank_bm25 sums the idf values in first-seen (dict insertion) order: global position of each term's first token
-    first = torch.full((n_terms,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=tok.device)
-    pos = torch.arange(tok.shape[0], dtype=torch.int64, device=tok.device)
+    total = int(tok.shape[0])
+    n_blocks = (n_docs + 4095) // 4096
+    pair_term = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    pair_tf = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    n_unique = torch.empty(n_docs, dtype=torch.int32, device=dev)
+    doc_len = torch.empty(n_docs, dtype=torch.int32, device=dev)
+    df = torch.zeros(n_terms, dtype=torch.int64, device=dev)
+    first = torch.full((n_terms,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+    cell = torch.zeros(n_terms * (n_blocks + 1), dtype=torch.int32, device=dev)
+    indptr = torch.empty(n_terms + 1, dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    with torch.cuda.device(dev):
+        _lib.check(lib.b2r_bm25_build_count_dev(p(tok), p(offs), n_docs, int(n_terms), int(pos_offset), p(pair_term), p(pair_tf),
+                                                p(n_unique), p(doc_len), p(df), p(first), p(cell), p(indptr), p(err), stream))
+        code = int(err.item())
+        if code == 1:
+            return None
+        if code == 2:
+            raise ValueError("token id outside [0, n_terms)")
+        n_post = int(indptr[-1].item())
+        doc_ids = torch.empty(max(n_post, 1), dtype=torch.int32, device=dev)
+        tf = torch.empty(max(n_post, 1), dtype=torch.int32, device=dev)
+        cursor = torch.zeros_like(cell)
+        _lib.check(lib.b2r_bm25_build_place_dev(p(offs), n_docs, int(n_terms), p(pair_term), p(pair_tf), p(n_unique), p(indptr),
+                                                p(cell), p(cursor), p(doc_ids), p(tf), stream))
+    return {"indptr": indptr, "doc_ids": doc_ids[:n_post], "tf": tf[:n_post], "doc_len": doc_len, "df": df, "first": first}
+
+
+def token_stream_statistics(token_ids, doc_offsets, n_terms, epsilon=0.25, device=None, group=None, use_kernels=True):
+    """Tokenised corpus -> CSR postings + rank_bm25 statistics on `device`.  On CUDA the postings come from this library's
+    build kernels (_postings_from_tokens_cuda); the torch sort / unique formulation below is the CPU path of the gloo
+    plumbing test and the fallback for documents longer than 1024 tokens (use_kernels=False forces it: the tests compare
+    the two).  Returns dict(indptr, doc_ids, tf, doc_len tensors; idf float64 numpy [n_terms] (0 for terms that never
+    occur); avgdl; average_idf; corpus_size)."""
+    import torch
+
+    tok = torch.as_tensor(token_ids).to(device=device).reshape(-1)
+    offs = torch.as_tensor(doc_offsets).to(device=device, dtype=torch.int64).reshape(-1).contiguous()
+    n_docs = int(offs.shape[0]) - 1
     totals = torch.tensor([int(tok.shape[0]), n_docs], dtype=torch.int64, device=tok.device)
+    pos_offset = 0
     if group is not None:
         import torch.distributed as dist
 
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         sizes = [torch.zeros(2, dtype=torch.int64, device=tok.device) for _ in range(world)]
         dist.all_gather(sizes, totals, group=group)
-        pos = pos + sum(int(sz[0]) for sz in sizes[:rank])   # documents are sharded in rank order
+        pos_offset = sum(int(sz[0]) for sz in sizes[:rank])   # documents are sharded in rank order
         totals = torch.stack(sizes).sum(0)
-    first.scatter_reduce_(0, tok, pos, reduce="amin", include_self=True)
+    built = None
+    if use_kernels and tok.is_cuda and n_docs > 0:
+        built = _postings_from_tokens_cuda(tok.to(torch.int32).contiguous(), offs, n_terms, pos_offset)
+    if built is not None:
+        indptr, doc_ids, counts, lens, df, first = (built[k] for k in ("indptr", "doc_ids", "tf", "doc_len", "df", "first"))
+    else:
+        tok = tok.to(torch.int64)
+        lens = offs[1:] - offs[:-1]
+        doc_of = torch.repeat_interleave(torch.arange(n_docs, device=tok.device), lens)
+        key, _ = torch.sort(tok * max(n_docs, 1) + doc_of)
+        uniq, counts = torch.unique_consecutive(key, return_counts=True)
+        term = uniq // max(n_docs, 1)
+        doc_ids = (uniq - term * max(n_docs, 1)).to(torch.int32)
+        df = torch.bincount(term, minlength=n_terms)
+        indptr = torch.zeros(n_terms + 1, dtype=torch.int64, device=tok.device)
+        indptr[1:] = torch.cumsum(df, 0)
+        # rank_bm25 sums the idf values in first-seen (dict insertion) order: global position of each term's first token
+        first = torch.full((n_terms,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=tok.device)
+        pos = torch.arange(tok.shape[0], dtype=torch.int64, device=tok.device) + pos_offset
+        first.scatter_reduce_(0, tok, pos, reduce="amin", include_self=True)
     if group is not None:
         dist.all_reduce(df, group=group)
         dist.all_reduce(first, op=dist.ReduceOp.MIN, group=group)

@@ -141,21 +141,23 @@ def heatmap_tiles(rows, pixels=512):
     [p, p] with p = min(pixels, N), and the group boundaries."""
     import torch
 
-    n = int(rows.shape[0])
+    n, d = int(rows.shape[0]), int(rows.shape[1])
     p = max(1, min(int(pixels), n))
-    xn = rows / (rows.norm(dim=1, keepdim=True) + 1e-8)
-    bounds = torch.div(torch.arange(p + 1, device=rows.device, dtype=torch.int64) * n, p, rounding_mode="floor")
-    sizes = (bounds[1:] - bounds[:-1]).to(torch.float64)
-    group = torch.bucketize(torch.arange(n, device=rows.device), bounds[1:], right=True)
-    pooled = torch.zeros((p, rows.shape[1]), dtype=torch.float64, device=rows.device)
-    pooled.index_add_(0, group, xn.to(torch.float64))
-    gram = pooled @ pooled.T                                   # sums over the tile: a plain p x p GEMM
-    # diagonal tiles: the reference overwrites S[i, i] (= |xn_i|^2) with 1
-    self_dot = torch.zeros(p, dtype=torch.float64, device=rows.device)
-    self_dot.index_add_(0, group, (xn.to(torch.float64) ** 2).sum(1))
-    gram[torch.arange(p), torch.arange(p)] += sizes - self_dot
-    tiles = gram / (sizes[:, None] * sizes[None, :])
-    return tiles.clamp_(-1.0, 1.0).to(torch.float32), bounds
+    bounds = torch.div(torch.arange(p + 1, device=rows.device, dtype=torch.int64) * n, p, rounding_mode="floor").contiguous()
+    if not (rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous()):
+        raise ValueError("heatmap_tiles needs a contiguous float32 CUDA tensor [n, d]")
+    # three kernels of this library (csrc/index_build.cu): divisors |x| + 1e-8, float64 pooled sums per group, Gram
+    div = torch.empty(n, dtype=torch.float32, device=rows.device)
+    pooled = torch.empty((p, d), dtype=torch.float64, device=rows.device)
+    self_dot = torch.empty(p, dtype=torch.float64, device=rows.device)
+    tiles = torch.empty((p, p), dtype=torch.float32, device=rows.device)
+    stream = torch.cuda.current_stream(rows.device).cuda_stream
+    with torch.cuda.device(rows.device):
+        _lib.check(_lib.load().b2r_cosine_heatmap_dev(C.c_void_p(rows.data_ptr()), n, d, C.c_void_p(bounds.data_ptr()), p,
+                                                      C.c_void_p(div.data_ptr()), C.c_void_p(pooled.data_ptr()),
+                                                      C.c_void_p(self_dot.data_ptr()), C.c_void_p(tiles.data_ptr()),
+                                                      C.c_void_p(stream)))
+    return tiles, bounds
 
 
 class SimilarityMatrixGenerator:

@@ -344,3 +344,39 @@ def test_concurrent_host_callers_share_one_index(b2r):
             Sw, Iw = want[r[1]]
             assert np.array_equal(S[0], Sw[0]) and np.array_equal(I[0], Iw[0])
             assert np.array_equal(S[1], Sw[0]) and np.array_equal(I[1], Iw[0])
+
+
+@pytest.mark.parametrize("n_docs,vocab", [(1, 50), (4095, 300), (4097, 2000), (20000, 5000)])
+def test_build_kernels_equal_the_sort_formulation(b2r, n_docs, vocab):
+    """The library's build kernels (per-document warp sort, block counts, placement in document order) produce exactly
+    the CSR postings, df-derived idf and statistics of the torch sort / unique formulation — doc ids ascending inside every
+    term, block boundaries (4095 / 4097 documents) included; documents of more than 1024 tokens fall back to it."""
+    import torch
+
+    from rag_challenge_2_b200.bm25 import token_stream_statistics
+
+    s = synth(b2r)
+    rng = np.random.default_rng(n_docs)
+    lens = rng.integers(1, 400, n_docs)
+    if n_docs > 10:
+        lens[3] = 1024                                            # the longest document the warp sort takes
+        lens[7] = 1
+    offs = np.zeros(n_docs + 1, np.int64)
+    np.cumsum(lens, out=offs[1:])
+    tok = np.minimum(rng.zipf(1.2, int(offs[-1])) - 1, vocab - 1).astype(np.int32)
+    a = token_stream_statistics(tok, offs, vocab, device=torch.device("cuda", 0))
+    b = token_stream_statistics(tok, offs, vocab, device=torch.device("cuda", 0), use_kernels=False)
+    for key in ("indptr", "doc_ids", "tf", "doc_len"):
+        assert torch.equal(a[key].cpu().long(), b[key].cpu().long()), key
+    assert np.array_equal(a["idf"], b["idf"]) and a["avgdl"] == b["avgdl"] and a["average_idf"] == b["average_idf"]
+    # a document beyond the warp sort's capacity: same answer through the fallback
+    lens2 = lens.copy()
+    lens2[0] = 1500
+    offs2 = np.zeros(n_docs + 1, np.int64)
+    np.cumsum(lens2, out=offs2[1:])
+    tok2 = np.minimum(rng.zipf(1.2, int(offs2[-1])) - 1, vocab - 1).astype(np.int32)
+    c = token_stream_statistics(tok2, offs2, vocab, device=torch.device("cuda", 0))
+    d = token_stream_statistics(tok2, offs2, vocab, device=torch.device("cuda", 0), use_kernels=False)
+    assert torch.equal(c["doc_ids"].cpu(), d["doc_ids"].cpu()) and torch.equal(c["tf"].cpu(), d["tf"].cpu())
+    with pytest.raises(ValueError):
+        token_stream_statistics(np.array([0, vocab], np.int32), np.array([0, 2], np.int64), vocab, device=torch.device("cuda", 0))
