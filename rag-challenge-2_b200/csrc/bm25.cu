@@ -357,13 +357,12 @@ __device__ __forceinline__ void consumer_sort_desc(K* a, int n, int ct) {
 //              global threshold tau_g (k-th best score any finished block has published), reduced to the best k
 //              by a histogram select on the ordered score bits (equal scores: ascending id), sorted, written to
 //              the per-(query, block) list; bm25_merge_kernel (one CTA per query) merges the lists.
-// Shared memory: 32 KiB accumulators + 6 x 8 KiB (12 KiB with float64 weights) ring + 8 KiB histogram + 8 KiB
-// list = 97 KiB, two CTAs per SM.
+// Shared memory: 32 KiB accumulators + ring + 8 KiB histogram + 8 KiB list; float32 weights: 6 stages x 512 postings x
+// 8 B = 24 KiB -> 73 KiB, three CTAs per SM; float64 weights: 6 x 512 x 12 B = 36 KiB -> 85 KiB, two (see bm25_stream_launch).
 // Algorithmic bytes per query: sum_t df_t * (4 + sizeof(weight)); the block index adds 8 B per (token, block).
 // ----------------------------------------------------------------------------------------------
 static const int kStreamBlk = 4096;       // documents per work item (block index granularity)
-static const int kStreamChunk = 1024;     // postings per ring stage
-static const int kStreamStages = 6;
+// ring geometry (postings per stage, stages): template parameters of the kernel, chosen in bm25_stream_launch
 static const int kStreamSelCap = 512;     // candidate list (u128 keys)
 static const int kStreamMaxK = 384;       // k + 64 spill keys must fit the list
 static const int kStreamThreads = 9 * 32; // 8 consumer warps + producer warp
@@ -394,23 +393,23 @@ struct StreamMeta {
   int pad;
 };
 
-template <class W>
-__global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25StreamArgs<W> a) {
+template <class W, int CHUNK, int STAGES, int MINB>
+__global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const Bm25StreamArgs<W> a) {
   extern __shared__ __align__(128) unsigned char stream_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int kStageBytes = kStreamChunk * (4 + static_cast<int>(sizeof(W)));
+  constexpr int kStageBytes = CHUNK * (4 + static_cast<int>(sizeof(W)));
   double* acc = reinterpret_cast<double*>(stream_smem);                                   // [kStreamBlk]
   unsigned char* ring = stream_smem + kStreamBlk * sizeof(double);                        // [stages][ids | weights]
-  StreamMeta* meta = reinterpret_cast<StreamMeta*>(ring + kStreamStages * kStageBytes);  // [stages]
-  u64* full = reinterpret_cast<u64*>(meta + kStreamStages);
-  u64* empty = full + kStreamStages;
-  u64* ctl = empty + kStreamStages;                                                    // [8] select control words
+  StreamMeta* meta = reinterpret_cast<StreamMeta*>(ring + STAGES * kStageBytes);  // [stages]
+  u64* full = reinterpret_cast<u64*>(meta + STAGES);
+  u64* empty = full + STAGES;
+  u64* ctl = empty + STAGES;                                                    // [8] select control words
   u32* hist = reinterpret_cast<u32*>(ctl + 8);                                         // [kSelBins]
   u128* sel = reinterpret_cast<u128*>(
       (reinterpret_cast<uintptr_t>(hist + kSelBins) + 15) & ~static_cast<uintptr_t>(15));  // [kStreamSelCap]
 
   if (tid == 0) {
-    for (int s = 0; s < kStreamStages; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 8);
     }
@@ -462,7 +461,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
           meta[s].flags = 3;
           mbar_arrive(&full[s]);
         }
-        if (++s == kStreamStages) {
+        if (++s == STAGES) {
           s = 0;
           ph ^= 1u;
         }
@@ -520,7 +519,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
           const long long a1 = (q1 + 3) & ~3LL;
           long long c0 = a0;
           do {
-            const long long c1 = min(a1, c0 + kStreamChunk);
+            const long long c1 = min(a1, c0 + CHUNK);
             const int cnt = static_cast<int>(c1 - c0);
             const bool last_chunk = c1 >= a1;
             if (lane == 0) {
@@ -534,13 +533,13 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
               if (cnt > 0) {
                 mbar_arrive_expect_tx(&full[s], static_cast<u32>(cnt) * (4u + static_cast<u32>(sizeof(W))));
                 bulk_g2s(st, a.doc_ids + c0, static_cast<u32>(cnt) * 4u, &full[s], policy);
-                bulk_g2s(st + kStreamChunk * 4, a.weight + c0, static_cast<u32>(cnt) * static_cast<u32>(sizeof(W)), &full[s],
+                bulk_g2s(st + CHUNK * 4, a.weight + c0, static_cast<u32>(cnt) * static_cast<u32>(sizeof(W)), &full[s],
                          policy);
               } else {
                 mbar_arrive(&full[s]);
               }
             }
-            if (++s == kStreamStages) {
+            if (++s == STAGES) {
               s = 0;
               ph ^= 1u;
             }
@@ -582,7 +581,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
       const double idf = meta[s].idf;
       const int fv = meta[s].fv, lv = no_acc ? 0 : meta[s].lv, fl = meta[s].flags;
       const int* ids = reinterpret_cast<const int*>(ring + static_cast<size_t>(s) * kStageBytes);
-      const W* ws = reinterpret_cast<const W*>(ring + static_cast<size_t>(s) * kStageBytes + kStreamChunk * 4);
+      const W* ws = reinterpret_cast<const W*>(ring + static_cast<size_t>(s) * kStageBytes + CHUNK * 4);
       for (int i = fv + ct; i < lv; i += 256) {
         const int dl = ids[i] - lo_i;
         // explicit rn intrinsics: no FMA contraction, numpy forms idf*w and the sum separately
@@ -590,7 +589,7 @@ __global__ void __launch_bounds__(kStreamThreads) bm25_stream_kernel(const Bm25S
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
-      if (++s == kStreamStages) {
+      if (++s == STAGES) {
         s = 0;
         ph ^= 1u;
       }
@@ -1049,17 +1048,17 @@ static int bm25_launch_t(b2r_bm25* h, const Bm25Plan& p, Bm25Args<W> a, int nq_l
   return B2R_OK;
 }
 
-template <class W>
-static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<W> a, cudaStream_t stream, bool overlap_prev) {
+template <class W, int CHUNK, int STAGES, int MINB>
+static int bm25_stream_launch_cfg(b2r_bm25* h, Bm25StreamArgs<W> a, cudaStream_t stream, bool overlap_prev) {
   a.weight = static_cast<const W*>(h->weight);
-  auto kern = bm25_stream_kernel<W>;
-  const size_t smem = kStreamBlk * sizeof(double) + static_cast<size_t>(kStreamStages) * kStreamChunk * (4 + sizeof(W)) +
-                      kStreamStages * sizeof(StreamMeta) + 2 * kStreamStages * 8 + 8 * 8 + kSelBins * 4 + 16 +
+  auto kern = bm25_stream_kernel<W, CHUNK, STAGES, MINB>;
+  const size_t smem = kStreamBlk * sizeof(double) + static_cast<size_t>(STAGES) * CHUNK * (4 + sizeof(W)) +
+                      STAGES * sizeof(StreamMeta) + 2 * STAGES * 8 + 8 * 8 + kSelBins * 4 + 16 +
                       static_cast<size_t>(kStreamSelCap) * 16;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const long long n_items = static_cast<long long>(a.nq_launch) * a.n_blocks;
-  int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024))));
+  int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(MINB, (227 * 1024) / (smem + 1024))));
   if (tunable("bm25.ctas_per_sm") > 0) per_sm = std::min(per_sm, tunable("bm25.ctas_per_sm"));
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_items, static_cast<long long>(h->num_sms) * per_sm)));
   cudaLaunchConfig_t cfg = {};
@@ -1075,6 +1074,23 @@ static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<W> a, cudaStream_t str
   B2R_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   B2R_CUDA(cudaGetLastError());
   return B2R_OK;
+}
+
+// Ring geometry (postings per stage, stages) and resident CTAs per SM.  The kernel waits more than it issues
+// (profiles/r02_bm25.md), so a third CTA per SM pays even though 72 registers per thread spill a little in the rare
+// select path: float32 weights 4.59 -> 4.22 ms for 64 queries over 10M documents with 512-posting stages x 6 (73 KiB).
+// float64 weights (12 B / posting): 512 x 6 = 85 KiB, two CTAs (the 1024-posting stages of r01 left room for one).
+// bm25.cfg = 1 / 2 select the alternatives.
+static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<float> a, cudaStream_t stream, bool overlap_prev) {
+  switch (tunable("bm25.cfg")) {
+    case 1: return bm25_stream_launch_cfg<float, 1024, 6, 2>(h, a, stream, overlap_prev);
+    case 2: return bm25_stream_launch_cfg<float, 512, 8, 2>(h, a, stream, overlap_prev);
+    default: return bm25_stream_launch_cfg<float, 512, 6, 3>(h, a, stream, overlap_prev);
+  }
+}
+static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<double> a, cudaStream_t stream, bool overlap_prev) {
+  if (tunable("bm25.cfg") == 1) return bm25_stream_launch_cfg<double, 1024, 6, 2>(h, a, stream, overlap_prev);
+  return bm25_stream_launch_cfg<double, 512, 6, 2>(h, a, stream, overlap_prev);
 }
 
 static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term_offsets_dev, int nq, int k, double* S_dev,
@@ -1109,9 +1125,9 @@ static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term
     if (h->weight_bits == 64) {
       Bm25StreamArgs<double> ad;
       memcpy(&ad, &a, sizeof(a));  // identical layout: only the weight pointer type differs
-      rc = bm25_stream_launch<double>(h, ad, stream, overlap_prev && q0 == 0);
+      rc = bm25_stream_launch(h, ad, stream, overlap_prev && q0 == 0);
     } else {
-      rc = bm25_stream_launch<float>(h, a, stream, overlap_prev && q0 == 0);
+      rc = bm25_stream_launch(h, a, stream, overlap_prev && q0 == 0);
     }
     if (rc) return rc;
     ++launch_counter();
