@@ -34,6 +34,7 @@ static std::map<std::string, int>& tunables() {
       {"flat.consumer_warps", 0},  // 4 or 8
       {"flat.max_nq", 0},          // cap on queries sharing one pass (1, 2 or 4)
       {"flat.force_generic", 0},   // 1: use the non-TMA kernel even for templated widths
+      {"flat.dynamic_tiles", 0},   // scan tile order: 0 default (dynamic, chunks of 4 tiles), -1 static (t mod grid), n chunk size
       {"flat.no_combine", 0},      // 1: concurrent host callers of one index are not combined into one batch
       {"flat.no_gemm", 0},         // 1: never use the tensor-core batch kernel
       {"flat.gemm_min_nq", 0},     // smallest batch that goes to the tensor-core kernel (default 5)
@@ -66,6 +67,7 @@ static std::map<std::string, int>& tunables() {
 struct PoolWs {
   unsigned char* base = nullptr;
   size_t bytes = 0;
+  uint32_t seq = 0;
 };
 static std::mutex g_ws_mu;
 static std::map<std::tuple<int, cudaStream_t, int>, PoolWs>& ws_pool() {
@@ -86,11 +88,25 @@ int ws_pool_get(int device, cudaStream_t stream, int kind, size_t bytes, size_t 
     }
     B2R_CUDA(cudaMalloc(&ws.base, bytes));
     ws.bytes = bytes;
+    ws.seq = 0;  // the new buffer's counters start from zero
     if (zero_prefix) B2R_CUDA(cudaMemsetAsync(ws.base, 0, std::min(zero_prefix, bytes), stream));
   }
   *base = ws.base;
   if (cap) *cap = ws.bytes;
   return B2R_OK;
+}
+
+uint32_t ws_pool_advance(int device, cudaStream_t stream, int kind, uint32_t count) {
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  PoolWs& ws = ws_pool()[std::make_tuple(device, stream, kind)];
+  const uint32_t before = ws.seq;
+  ws.seq += count;
+  return before;
+}
+
+std::mutex& ws_launch_mutex() {
+  static std::mutex m;
+  return m;
 }
 
 int tunable(const char* key) {

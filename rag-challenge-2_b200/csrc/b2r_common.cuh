@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 #include "b2r.h"
@@ -45,6 +46,11 @@ int tunable(const char* key);  // current value of a tunable (see b2r_tunable_se
 // zeroed when the buffer is (re)allocated; the kernels leave them zero.  The caller has the device selected.
 int ws_pool_get(int device, cudaStream_t stream, int kind, size_t bytes, size_t zero_prefix, unsigned char** base,
                 size_t* cap);
+// A monotonically increasing 32-bit sequence per workspace (wraps): returns the value before adding `count`.  The scan
+// kernels' dynamic tile counter is never reset — a launch subtracts the sequence value it was given — so the caller must
+// take the value and enqueue its kernel while holding ws_launch_mutex() (launch order == sequence order).
+uint32_t ws_pool_advance(int device, cudaStream_t stream, int kind, uint32_t count);
+std::mutex& ws_launch_mutex();
 }  // namespace b2r
 // host-side range check of query term ids against an index (csrc/bm25.cu)
 extern "C" int bm25_check_terms(const b2r_bm25* h, const int32_t* term_ids, int n);

@@ -42,7 +42,9 @@ struct ScanArgs {
   int tile_rows;
   long long n_tiles;
   u64* partial;       // [NQ][gridDim.x][k] per-CTA sorted keys
-  u32* ticket;        // self-resetting arrival counter
+  u32* ticket;        // self-resetting arrival counter; ticket[1] is the dynamic tile counter (chunks handed out so far)
+  int dyn_chunk;      // > 0: tiles are handed out dynamically in chunks of this many tiles (after a first static round)
+  u32 dyn_base;       // value of the (never reset) tile counter at which this launch's hand-outs begin
   float* D;           // [nq, k]
   long long* I;       // [nq, k]
   long long id_offset;
@@ -117,7 +119,7 @@ __device__ __forceinline__ void scan_epilogue(const ScanArgs& a, u64* cand, int 
                     a.id_offset);
     __syncthreads();
   }
-  if (tid == 0) *a.ticket = 0;  // ready for the next launch on this workspace
+  if (tid == 0) *a.ticket = 0;  // ready for the next launch on this workspace (ticket[1], the tile counter, keeps counting)
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -140,7 +142,8 @@ __global__ void __launch_bounds__((CW + 1) * 32) flat_scan_tma_kernel(const Scan
   u64* full = reinterpret_cast<u64*>(smem_raw + static_cast<size_t>(a.stages) * tile_bytes);
   u64* empty = full + a.stages;
   u64* ctl = empty + a.stages;  // 4 x u64 control words
-  u64* cand = ctl + 4;          // [NQ][CW][cap]
+  long long* tile_of = reinterpret_cast<long long*>(ctl + 4);  // [stages] tile index of the stage (-1: no more tiles)
+  u64* cand = reinterpret_cast<u64*>(tile_of + a.stages);      // [NQ][CW][cap]
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -157,18 +160,53 @@ __global__ void __launch_bounds__((CW + 1) * 32) flat_scan_tma_kernel(const Scan
       const u64 policy = l2_policy_evict_first();
       int s = 0;
       u32 ph = 0;
-      for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      // Tile order.  Static: tile t -> CTA t mod grid.  Dynamic (dyn_chunk > 0): chunks of dyn_chunk consecutive tiles; every
+      // CTA starts with chunk blockIdx.x and then takes the next unassigned chunk from a global counter, fetched one
+      // chunk ahead so that the atomic's latency hides behind the copies of the current chunk.  The fastest SMs then
+      // take more tiles and no CTA is left finishing alone (measured: -12 us on a 1.25M-row shard, -1.7 % at 10M rows).
+      // The counter is never reset: exactly max(n_chunks, grid) hand-outs happen per launch (every CTA's last fetch is
+      // the one that tells it to stop), so the host gives each launch the counter value it starts from (dyn_base) — a
+      // chained next launch may begin while this one's last CTA is still selecting.
+      const int G = a.dyn_chunk;
+      const long long n_chunks = G > 0 ? (a.n_tiles + G - 1) / G : 0;
+      long long chunk = blockIdx.x, next_chunk = 0;
+      if (G > 0) next_chunk = static_cast<long long>(gridDim.x) + static_cast<u32>(atomicAdd(a.ticket + 1, 1u) - a.dyn_base);
+      long long t = G > 0 ? chunk * G : static_cast<long long>(blockIdx.x);
+      int in_chunk = 0;
+      for (;;) {
+        if (G > 0) {
+          if (in_chunk == G || t >= a.n_tiles) {  // chunk exhausted: move to the prefetched one, prefetch another
+            chunk = next_chunk;
+            if (chunk >= n_chunks) break;
+            next_chunk = static_cast<long long>(gridDim.x) + static_cast<u32>(atomicAdd(a.ticket + 1, 1u) - a.dyn_base);
+            t = chunk * G;
+            in_chunk = 0;
+          }
+        } else if (t >= a.n_tiles) {
+          break;
+        }
         mbar_wait(&empty[s], ph ^ 1u);
         const long long row0 = t * a.tile_rows;
         const long long rows = min(static_cast<long long>(a.tile_rows), a.n - row0);
         const u32 bytes = static_cast<u32>(rows) * static_cast<u32>(d) * 4u;
+        tile_of[s] = t;
         mbar_arrive_expect_tx(&full[s], bytes);
         bulk_g2s(stage0 + static_cast<size_t>(s) * tile_floats, a.xb + row0 * d, bytes, &full[s], policy);
         if (++s == a.stages) {
           s = 0;
           ph ^= 1u;
         }
+        if (G > 0) {
+          ++t;
+          ++in_chunk;
+        } else {
+          t += gridDim.x;
+        }
       }
+      // end marker for the consumers
+      mbar_wait(&empty[s], ph ^ 1u);
+      tile_of[s] = -1;
+      mbar_arrive(&full[s]);
     }
   } else {
     // ---------------- consumers ----------------
@@ -194,8 +232,10 @@ __global__ void __launch_bounds__((CW + 1) * 32) flat_scan_tma_kernel(const Scan
     const int vi = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     const int my_q = vi % NQ, my_r = vi / NQ;
     u64 tau_mine = 0;
-    for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    for (;;) {
       mbar_wait(&full[s], ph);
+      const long long t = tile_of[s];
+      if (t < 0) break;
       const float* tile = stage0 + static_cast<size_t>(s) * tile_floats;
       const long long row0 = t * a.tile_rows;
       const int rows = static_cast<int>(min(static_cast<long long>(a.tile_rows), a.n - row0));
@@ -631,7 +671,7 @@ static int make_plan(const b2r_flat* h, int nq_left, int k, ScanPlan* p) {
     if (stages <= 0) stages = nq == 1 ? 4 : 3;
     for (;;) {
       const size_t cand = static_cast<size_t>(nq) * p->cw * p->cap * sizeof(u64);
-      const size_t fixed = static_cast<size_t>(2 * stages + 4) * sizeof(u64) + cand + 128;
+      const size_t fixed = static_cast<size_t>(3 * stages + 4) * sizeof(u64) + cand + 128;  // barriers, ctl, tile_of
       const size_t ring = static_cast<size_t>(stages) * tile_rows * row_bytes;
       const size_t total = ring + fixed;
       const size_t budget = kSmemLimit / ctas_per_sm - 1024;  // 1 KiB per-CTA system reservation
@@ -750,6 +790,9 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
     a.stages = p.stages;
     a.tile_rows = p.tile_rows;
     a.n_tiles = (h->n + p.tile_rows - 1) / p.tile_rows;
+    const int dyn = tunable("flat.dynamic_tiles");   // 0: default (on, chunks of 2 tiles), < 0: static order, > 0: chunk size
+    a.dyn_chunk = (!p.tma || dyn < 0) ? 0 : (dyn == 0 ? 2 : dyn);
+    a.dyn_base = 0;
     a.ticket = reinterpret_cast<u32*>(ws.base);
     a.partial = reinterpret_cast<u64*>(ws.base + 256);
     a.D = D_dev + static_cast<size_t>(done) * k;
@@ -758,7 +801,17 @@ static int flat_search_dev_impl(b2r_flat* h, const float* q_dev, int nq, int k, 
     a.sel_cap = p.sel_cap;
     // only the first kernel of a call may overlap the caller's previous kernel (the tensor-core path never does)
     p.pdl = (flags & B2R_LAUNCH_OVERLAP_PREVIOUS) != 0u && done == 0 && !use_gemm;
-    rc = p.tma ? launch_tma(p, a, stream) : launch_generic(p, a, stream);
+    if (a.dyn_chunk > 0) {
+      // sequence value and launch under one lock: the kernels must run in the order their counter bases were taken
+      std::lock_guard<std::mutex> lock(ws_launch_mutex());
+      const long long n_chunks = (a.n_tiles + a.dyn_chunk - 1) / a.dyn_chunk;
+      const uint32_t handouts = static_cast<uint32_t>(std::max<long long>(n_chunks, p.grid));
+      a.dyn_base = ws_pool_advance(h->device, stream, 0, handouts);
+      rc = launch_tma(p, a, stream);
+      if (rc) ws_pool_advance(h->device, stream, 0, 0u - handouts);  // nothing was enqueued: the counter did not move
+    } else {
+      rc = p.tma ? launch_tma(p, a, stream) : launch_generic(p, a, stream);
+    }
     if (rc) return rc;
     ++launch_counter();
     done += a.nq;
