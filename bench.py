@@ -693,6 +693,12 @@ def run_b200(args):
     ms_e2e_sync = g0.elapsed_time(g1)
     ms_e2e = ms_e2e_sync
     if can_submit:
+        for _ in range(2):  # untimed: the two-in-flight pattern once through both staging slots
+            a_t = index.search_hybrid_submit(host_batches[0][0], host_batches[0][1], args.k)
+            b_t = index.search_hybrid_submit(host_batches[1 % n_batches][0], host_batches[1 % n_batches][1], args.k)
+            index.search_hybrid_collect(a_t)
+            index.search_hybrid_collect(b_t)
+        sync_all()
         g0.record()
         pending = index.search_hybrid_submit(host_batches[0][0], host_batches[0][1], args.k)
         for i in range(1, args.steps):
