@@ -57,6 +57,7 @@ static std::map<std::string, int>& tunables() {
       {"exchange.timeout_ms", 0},  // bound on the exchange kernel's wait for its peers (default 10000 ms)
       {"bm25.cfg", 0},             // ring geometry of the streaming kernel (A/B runs; see bm25_stream_launch)
       {"bm25.ctas_per_sm", 0},     // cap on resident streaming-kernel CTAs per SM
+      {"hybrid.no_copy_stream", 0},// 1: the host step's H2D copy goes on the step's own stream (experiment)
       {"hybrid.host_chain", 0},    // 1: the host step (submit / collect) also chains consecutive steps by dependent launch (experiment)
       {"hybrid.no_fused_tail", 0}, // 1: the hybrid step keeps its fusion / exchange kernel (no fused tail in the BM25 kernel)
       {"bm25.v1", 0},              // 1: use the doc-block kernel (binary searches, per-token barriers) instead of the streaming one

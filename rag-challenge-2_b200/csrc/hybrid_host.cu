@@ -221,9 +221,13 @@ int b2r_hybrid_submit_host(b2r_hybrid_ctx* c, b2r_flat* flat, b2r_bm25* bm25, co
   const size_t h2d = qb + ob + static_cast<size_t>(n_terms) * 4;
   // the copy runs on its own stream, so the inputs of this question travel while the previous question's step is still
   // executing; the step waits for the event, not for the copy engine's turn behind the previous kernels
-  B2R_CUDA(cudaMemcpyAsync(sl->in_dev, sl->in_pin, h2d, cudaMemcpyHostToDevice, c->copy_stream));
-  B2R_CUDA(cudaEventRecord(sl->in_ready, c->copy_stream));
-  B2R_CUDA(cudaStreamWaitEvent(c->stream, sl->in_ready, 0));
+  if (tunable("hybrid.no_copy_stream")) {
+    B2R_CUDA(cudaMemcpyAsync(sl->in_dev, sl->in_pin, h2d, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    B2R_CUDA(cudaMemcpyAsync(sl->in_dev, sl->in_pin, h2d, cudaMemcpyHostToDevice, c->copy_stream));
+    B2R_CUDA(cudaEventRecord(sl->in_ready, c->copy_stream));
+    B2R_CUDA(cudaStreamWaitEvent(c->stream, sl->in_ready, 0));
+  }
   const float* q_dev = reinterpret_cast<const float*>(sl->in_dev);
   const int32_t* offs_dev = reinterpret_cast<const int32_t*>(sl->in_dev + qb);
   const int32_t* tids_dev = reinterpret_cast<const int32_t*>(sl->in_dev + qb + ob);
