@@ -34,7 +34,7 @@ static std::map<std::string, int>& tunables() {
       {"flat.consumer_warps", 0},  // 4 or 8
       {"flat.max_nq", 0},          // cap on queries sharing one pass (1, 2 or 4)
       {"flat.force_generic", 0},   // 1: use the non-TMA kernel even for templated widths
-      {"flat.dynamic_tiles", 0},   // scan tile order: 0 default (dynamic, chunks of 4 tiles), -1 static (t mod grid), n chunk size
+      {"flat.dynamic_tiles", 0},   // scan tile order: 0 default (dynamic, chunks of 2 tiles), -1 static (t mod grid), n chunk size
       {"flat.no_combine", 0},      // 1: concurrent host callers of one index are not combined into one batch
       {"flat.no_gemm", 0},         // 1: never use the tensor-core batch kernel
       {"flat.gemm_min_nq", 0},     // smallest batch that goes to the tensor-core kernel (default 5)

@@ -8,8 +8,8 @@
 //
 // Layout in HBM: indptr int64[V+1]; doc_ids int32[P] ascending inside each term; weight[P]
 // = tf*(k1+1)/(tf + k1*(1-b+b*dl/avgdl)) computed once at build time in float64 with exactly the
-// operation order numpy uses, stored as float32 (8 B / posting, the default) or float64
-// (12 B / posting, scores then equal rank_bm25's bit for bit); idf float64[V].
+// operation order numpy uses, stored as float64 (12 B / posting, the default: scores equal rank_bm25's bit for bit) or,
+// as an explicit opt-in, float32 (8 B / posting, within 1e-6 relative); idf float64[V].
 //
 // Kernel: doc-range partitioned.  CTA (x = doc block, y = query) owns `block_docs` consecutive
 // documents with a float64 accumulator each in shared memory.  For every query token it binary-

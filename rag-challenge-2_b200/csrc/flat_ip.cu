@@ -2,8 +2,9 @@
 // plays in the reference: src/ingestion.py:79-84 builds it, src/retrieval.py:1140 searches it).
 //
 // Kernel K1 `flat_scan_tma_kernel` (HBM-bound, one pass over the rows per launch):
-//   * persistent CTAs, grid = SMs x resident CTAs; tile t (tile_rows consecutive rows, one
-//     contiguous span of the row-major matrix) goes to CTA t mod grid
+//   * persistent CTAs, grid = SMs x resident CTAs; a tile is tile_rows consecutive rows (one contiguous span of the
+//     row-major matrix); tiles are handed out dynamically in chunks of 2 from a global counter (the first chunk of every
+//     CTA is static), so the SMs that stream faster take more tiles and the kernel does not end with a straggler
 //   * one producer lane per CTA streams tiles global->shared with 1-D bulk async copies
 //     (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) through a ring of `stages` buffers
 //     guarded by full/empty mbarriers
