@@ -6,11 +6,14 @@
 // the limiter instead of shared memory:
 //   * the rows are normalised AND split once (hi = rna_tf32(xn), lo = xn - hi) into two arrays, so the scan kernel
 //     has no transform warps: every operand reaches shared memory by TMA;
-//   * tile = 256 rows (128 per CTA of the pair) x 128 columns (64 per CTA), M = 256 x N = 128 MMAs: the pair shares
-//     the column operand, which halves its shared-memory reads per SM (the single-CTA N = 64 kernel re-reads the
-//     128-row operand for every 64 columns and is bound by the 128 B/clk shared-memory port);
-//   * four TMEM accumulators per tile (hi*hi and the cross terms, each split 2-way over K) as before — the tensor
-//     core truncates when it accumulates, so long chains and mixed magnitudes are kept apart;
+//   * tile = 256 rows (128 per CTA of the pair) x 256 columns (128 per CTA), M = 256 x N = 256 MMAs: the pair shares
+//     the column operand.  Operand traffic decides this kernel: a tf32 MMA of K = 8 reads 4 KiB of rows and N x 32 B of
+//     columns per SM; at N = 128 (r01) that is 8 KiB per 67 tensor cycles = 122 B/clk against the 128 B/clk shared-memory
+//     port — the tensor pipe measured 53 % active —, at N = 256 it is 12 KiB per 134 cycles = 92 B/clk;
+//   * two TMEM accumulators per tile, 2 x 256 columns = all of TMEM: hi*hi, and the cross terms lo*hi + hi*lo kept apart
+//     from it (the tensor core truncates when it accumulates, so the small terms must not be added to the large running
+//     sum).  r01's 2-way split of each over K (four accumulators) does not fit at N = 256; the chains are 128 MMAs long
+//     instead of 64, still inside the 1e-5 bar (tests/test_cosine_gpu.py, N = 200k against float64);
 //   * tiles are visited in L2-sized super-tiles (2048 x 2048) so that both operands of a tile come from L2.
 #include <algorithm>
 #include <mutex>
@@ -21,7 +24,7 @@
 namespace b2r {
 
 static const int kCosThreads = 320;   // producer, MMA, 8 epilogue warps (two per TMEM lane quadrant)
-static const int kCosN = 128;        // columns per tile
+static const int kCosN = 256;        // columns per tile
 static const int kCosSuper = 2048;   // rows / columns of an L2 super-tile
 static const int kCosStages = 3;   // a 4th stage (all 227 KiB) was measured: no gain (r02) — the ring is not what limits this kernel
 
@@ -69,9 +72,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   constexpr u32 kSubBytes = kTileM * kSlabK * 4;   // 16 KiB: 128 rows of one K-slab
-  constexpr u32 kBBytes = NH * kSlabK * 4;         // 8 KiB: this CTA's 64 columns
+  constexpr u32 kBBytes = NH * kSlabK * 4;         // 16 KiB: this CTA's 128 columns
   constexpr u32 kStage = 2 * kSubBytes + 2 * kBBytes;  // A_hi | A_lo | B_hi | B_lo
-  constexpr u32 kTmemCols = 4 * N;                 // main even / odd, small even / odd
+  constexpr u32 kTmemCols = 2 * N;                 // main (hi*hi), small (lo*hi + hi*lo)
+  static_assert(kTmemCols == 512, "the accumulators fill TMEM");
   const int n_slabs = a.d / kSlabK;
   const u32 rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -138,9 +142,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
         mbar_wait_cluster_tag(tm_empty, ph_t ^ 1u, 200);
         tc_fence_after();
         for (int sl = 0; sl < n_slabs; ++sl) {
-          const u32 d_main = tmem_base + static_cast<u32>((sl & 1) * N);
-          const u32 d_small = tmem_base + static_cast<u32>((2 + (sl & 1)) * N);
-          const bool first = sl < 2;
+          const u32 d_main = tmem_base;
+          const u32 d_small = tmem_base + static_cast<u32>(N);
+          const bool first = sl == 0;
           mbar_wait_cluster_tag(&full[s], ph_s, 400 + s);
           tc_fence_after();
           const u32 st = smem_u32(ring + static_cast<size_t>(s) * kStage);
@@ -173,7 +177,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
     // before the drain / statistics split: results are unchanged) and added to the float64 totals once; interior tiles
     // (every row below every column, all inside the matrix and the column range) skip the per-element masks.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;  // 0: columns 0-63, 1: columns 64-127
+    const int half = (warp - 2) >> 2;  // 0: columns 0-127, 1: columns 128-255
     u32 ph_t = 0;
     double st_sum = 0.0, st_sq = 0.0;
     unsigned long long st_cnt = 0;
@@ -190,22 +194,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCosThreads, 1)
       mbar_wait_cluster_tag(tm_full, ph_t, 700);
       tc_fence_after();
       const u32 taddr = tmem_base + (static_cast<u32>(quad * 32) << 16) + static_cast<u32>(half * (N / 2));
-      // (1) drain: this warp's 32 lanes x 64 columns of the four accumulators are combined into 64 registers per thread
+      // (1) drain: this warp's 32 lanes x 128 columns of the two accumulators are combined into 128 registers per thread
       // and the accumulators are handed back at once — the MMAs of the NEXT tile run while (2) does the statistics.
       // (The accumulators fill all 512 TMEM columns, so they cannot be double-buffered in TMEM; registers can.)
       float v[N / 2];
 #pragma unroll
       for (int c0 = 0; c0 < N / 2; c0 += 16) {
-        float m0[16], m1[16], s0[16], s1[16];
+        float m0[16], s0[16];
         tc_ld16(taddr + c0, m0);
-        tc_ld16(taddr + 2 * N + c0, s0);
-        if (n_slabs > 1) {
-          tc_ld16(taddr + N + c0, m1);
-          tc_ld16(taddr + 3 * N + c0, s1);
-        }
+        tc_ld16(taddr + N + c0, s0);
         tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[c0 + i] = (n_slabs > 1) ? (m0[i] + m1[i]) + (s0[i] + s1[i]) : m0[i] + s0[i];
+        for (int i = 0; i < 16; ++i) v[c0 + i] = m0[i] + s0[i];
       }
       tc_fence_before();
       __syncwarp();

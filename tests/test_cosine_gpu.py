@@ -92,7 +92,7 @@ def test_heatmap_tiles_match_tile_means_of_the_matrix(b2r):
 @pytest.mark.parametrize("n,d", [(4096, 64), (4500, 1024), (6001, 96)])
 def test_stats_cta_pair_kernel(b2r, n, d):
     """n >= 4096: the CTA-pair 3xTF32 kernel (csrc/cosine_pair.cu); same bar, and the same numbers as the single-CTA
-    kernel up to fp32 accumulation order."""
+    kernel up to the accumulation chains."""
     import torch
 
     from rag_challenge_2_b200 import _lib, cosine
@@ -110,9 +110,12 @@ def test_stats_cta_pair_kernel(b2r, n, d):
         old = cosine.cosine_stats(rows)
     finally:
         _lib.tunable_set("cosine.no_pair", 0)
-    assert got["count"] == old["count"] and got["max_similarity"] == old["max_similarity"]
-    assert abs(got["avg_similarity"] - old["avg_similarity"]) <= 1e-6 * abs(old["avg_similarity"]) + 1e-9
-    # column shards at boundaries that are not multiples of the 128-column tile
+    # the pair kernel accumulates each product in one chain of 128 MMAs (two accumulators at N = 256), the single-CTA
+    # kernel in two chains of 64: the tensor core truncates when it accumulates, so they differ by a few 1e-7 — both
+    # inside the 1e-5 bar against the float64 reference checked above
+    assert got["count"] == old["count"] and abs(got["max_similarity"] - old["max_similarity"]) <= 2e-6
+    assert abs(got["avg_similarity"] - old["avg_similarity"]) <= 1e-5 * abs(old["avg_similarity"]) + 1e-8
+    # column shards at boundaries that are not multiples of the 256-column tile
     parts = [cosine.cosine_stats(rows, lo, hi, finalize=False) for lo, hi in ((0, 1000), (1000, 4097 if n > 4097 else 3000), (4097 if n > 4097 else 3000, n))]
     stats = sum(p[0].cpu().numpy()[[0, 1, 4]] for p in parts)
     hist = sum(p[1].cpu().numpy() for p in parts)
