@@ -292,7 +292,10 @@ static std::mutex g_cos_mu;
 static CosScratch g_cos_scratch[16];
 
 bool cosine_pair_supported(long long n, int d, int n_bins, int num_sms) {
-  return n >= 4096 && d % kSlabK == 0 && n_bins <= 8192 && num_sms >= 2 && !tunable("cosine.no_pair");
+  // d <= 1024: one accumulation chain per product is d / 8 MMAs long and the tensor core truncates at every step —
+  // measured 5.5e-6 on a similarity of 1.0 at d = 1024, inside the 1e-5 bar; wider rows go to the single-CTA kernel,
+  // which splits every chain in two
+  return n >= 4096 && d % kSlabK == 0 && d <= 1024 && n_bins <= 8192 && num_sms >= 2 && !tunable("cosine.no_pair");
 }
 
 int cosine_stats_run_pair(const float* rows_dev, long long n, int d, long long col_begin, long long col_end,

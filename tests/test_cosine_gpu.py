@@ -111,9 +111,10 @@ def test_stats_cta_pair_kernel(b2r, n, d):
     finally:
         _lib.tunable_set("cosine.no_pair", 0)
     # the pair kernel accumulates each product in one chain of 128 MMAs (two accumulators at N = 256), the single-CTA
-    # kernel in two chains of 64: the tensor core truncates when it accumulates, so they differ by a few 1e-7 — both
-    # inside the 1e-5 bar against the float64 reference checked above
-    assert got["count"] == old["count"] and abs(got["max_similarity"] - old["max_similarity"]) <= 2e-6
+    # kernel in two chains of 64: the tensor core truncates when it accumulates, so they differ by a few 1e-6 at d = 1024
+    # (a similarity of 1.0 comes out as 0.9999945 / 0.9999973) — both inside the 1e-5 bar against the float64 reference
+    # checked above
+    assert got["count"] == old["count"] and abs(got["max_similarity"] - old["max_similarity"]) <= 6e-6
     assert abs(got["avg_similarity"] - old["avg_similarity"]) <= 1e-5 * abs(old["avg_similarity"]) + 1e-8
     # column shards at boundaries that are not multiples of the 256-column tile
     parts = [cosine.cosine_stats(rows, lo, hi, finalize=False) for lo, hi in ((0, 1000), (1000, 4097 if n > 4097 else 3000), (4097 if n > 4097 else 3000, n))]
