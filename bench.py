@@ -438,15 +438,19 @@ def config_extras(args, flat, bm25, rows, df, dev, hbm_peak):
         for i, (year, m) in enumerate(zip(years, sizes)):
             lo = (700 + 130 * i) * synth.ROW_BLOCK                      # seeded blocks disjoint from the main corpus
             r = synth.dense_rows_torch(lo, lo + int(m), d, dev)
-            reports.append(synth.synthetic_year_report(f"J{year}", company, int(m), pkg.FlatIPIndex.from_device_tensor(r)))
+            reports.append(synth.synthetic_year_report(f"J{year}", company, int(m), pkg.FlatIPIndex.from_device_tensor(r),
+                                                       materialise=True))   # real chunk / page lists, as loaded from JSON
         rt = retrieval.VectorRetriever.from_reports(reports, qwen=retrieval.HashEmbedder(d), parallel_workers=8)
         questions = [f"{years[i % 6]}\u5e74{company}\u7684\u7b2c{i}\u4e2a\u8d22\u52a1\u6307\u6807\u662f\u591a\u5c11\uff1f" for i in range(127)]
         kw = dict(top_n=args.k, use_hyde=False, use_multi_query=False)
-        out = {"dbs": 6, "rows_per_db": [int(m) for m in sizes], "questions": 127, "n_gpus": 1}
+        out = {"dbs": 6, "rows_per_db": [int(m) for m in sizes], "questions": 127, "n_gpus": 1,
+               "chunk_records": "materialised lists (6.6M chunk dictionaries on the host)",
+               "record_helper": "C (_b2r_records)" if retrieval._b2r_records is not None else "python loops"}
         for name, sel in (("all_years", None), ("three_years", [2023, 2024, 2025])):
             rt.retrieve_batch(company, questions, selected_years=sel, **kw)
-            best = 1e30
-            for _ in range(3):
+            best, got = 1e30, None
+            for _ in range(5):
+                got = None   # the previous batch's records are released before the clock starts, not inside the call
                 t0 = time.perf_counter()
                 got = rt.retrieve_batch(company, questions, selected_years=sel, **kw)
                 best = min(best, time.perf_counter() - t0)

@@ -19,3 +19,7 @@ done
 for p in "${pids[@]}"; do wait "$p"; done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "${objs[@]}"
 echo "built $OUT"
+# host-side CPython helper (record dictionaries of the batched retrieval path); plain C, no CUDA
+PYINC="$(python -c 'import sysconfig; print(sysconfig.get_paths()["include"])')"
+gcc -O2 -fPIC -shared -Wall -I"$PYINC" "$PKG/csrc/host_records.c" -o "$PKG/_b2r_records.so" -lm
+echo "built $PKG/_b2r_records.so"

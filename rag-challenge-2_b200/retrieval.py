@@ -19,9 +19,11 @@ callbacks, timing keys and error behaviour as the reference, so `src/questions_p
 Reference line numbers in the docstrings refer to src/retrieval.py of the reference checkout.
 """
 import csv
+import gc
 import hashlib
 import json
 import logging
+import operator
 import re
 import threading
 import time
@@ -33,8 +35,14 @@ import numpy as np
 from . import flat_index
 from .bm25 import BM25Okapi, load_bm25_pickle  # noqa: F401  (BM25Okapi re-exported)
 
+try:  # CPython helper built by build.sh (csrc/host_records.c): the record loops of _RawHits.records in C
+    from . import _b2r_records
+except ImportError:  # not built: the Python loops below produce the same records (tests/test_host_records.py)
+    _b2r_records = None
+
 _log = logging.getLogger(__name__)
 
+_BY_SIMILARITY = operator.itemgetter("vector_similarity")
 _YEAR_IN_QUESTION = re.compile(r"(20\d{2})年")
 _YEAR_IN_NAME = re.compile(r"[J]?(20\d{2})")
 
@@ -314,6 +322,17 @@ class BM25Retriever:
         """[retrieve_by_company_name(q) for q in queries] with ONE fused scoring + top-k launch per report for all the
         questions routed to it (reference :194-295 scores one query at a time).  `selected_years` is one list for
         the batch, or a list with one entry (list or None) per question."""
+        # tens of thousands of acyclic record dictionaries are born in a batch: pausing the cyclic collector for the
+        # call saves its young-generation passes (and full passes over a process holding millions of chunk dicts)
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            return self._retrieve_batch(company_name, queries, top_n, return_parent_pages, selected_years)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+
+    def _retrieve_batch(self, company_name, queries, top_n, return_parent_pages, selected_years):
         per_question_years = (isinstance(selected_years, (list, tuple)) and len(selected_years) == len(queries)
                               and all(y is None or isinstance(y, (list, tuple)) for y in selected_years))
         all_documents = self._documents()
@@ -423,15 +442,26 @@ def _raise_reference_unbound_local(name):
 
 
 class _RawHits:
-    """Result rows of one (query, report) basic search, not yet turned into hit tuples (reference :1142-1157)."""
-    __slots__ = ("sha1", "chunks", "pages", "scores", "ids", "parent_pages", "report_name")
+    """Result rows of one (query, report) basic search, not yet turned into hit tuples (reference :1142-1157):
+    row `row` of the float32 [nq, k] scores / int64 [nq, k] ids a batched search returned."""
+    __slots__ = ("sha1", "chunks", "pages", "D", "I", "row", "parent_pages", "report_name", "ids_ok")
 
-    def __init__(self, sha1, chunks, pages, scores, ids, parent_pages, report_name):
+    def __init__(self, sha1, chunks, pages, D, I, row, parent_pages, report_name, ids_ok=None):
         self.sha1, self.chunks, self.pages = sha1, chunks, pages
-        self.scores, self.ids, self.parent_pages, self.report_name = scores, ids, parent_pages, report_name
+        self.D, self.I, self.row = D, I, row
+        self.parent_pages, self.report_name, self.ids_ok = parent_pages, report_name, ids_ok
 
     def __bool__(self):
-        return bool(self.ids)
+        return self.I.shape[1] > 0
+
+    # .tolist() yields the same Python floats / ints as float(d) / int(i) per element
+    @property
+    def scores(self):
+        return self.D[self.row].tolist()
+
+    @property
+    def ids(self):
+        return self.I[self.row].tolist()
 
     def hits(self, query_text, log):
         """The reference's hit tuples, in rank order; a failing hit ends the list, the hits before it are kept
@@ -445,44 +475,56 @@ class _RawHits:
             log(f"[ERROR] Vector search failed for query '{query_text[:60]}' in report {self.report_name}: {e}")
         return out
 
-    def records(self, query_text, log):
+    def records(self, query_text, log, helper=True):
         """Final records of a question that has ONE query text and only basic hits: every aggregation key then
         holds one query and one method, so both bonuses are exactly 1.0 and a record is its best hit
         (fuse_similarity / _final_record with count == 1).  Chunk mode needs distinct, valid ids (anything else
-        goes through hits()); page mode merges the chunks of a page in first-hit order, as the aggregation does."""
-        sha1, chunks, pages = self.sha1, self.chunks, self.pages
+        goes through hits()); page mode merges the chunks of a page in first-hit order, as the aggregation does.
+        The loops run in the C helper when it is built (`helper=False`: the Python statement of the same)."""
         out = []
         try:
-            if not self.parent_pages:
-                for distance, index in zip(self.scores, self.ids):
-                    chunk = chunks[index]
-                    if chunk["page"] not in pages:  # a missing parent page fails the hit, as in the reference (:1145)
-                        raise KeyError(chunk["page"])
-                    r = round(distance * 1.0, 4)
-                    out.append({"vector_similarity": r, "max_original_similarity": r, "page": chunk["page"],
-                                "text": chunk["text"], "hit_count": 1, "retrieval_sources": ["basic"],
-                                "source_sha1": sha1, "query_sources": [query_text]})
+            if helper and _b2r_records is not None:
+                build = _b2r_records.append_page_records if self.parent_pages else _b2r_records.append_chunk_records
+                build(out, self.D, self.I, self.row, self.chunks, self.pages, self.sha1, query_text)
             else:
-                by_page = {}
-                for distance, index in zip(self.scores, self.ids):
-                    parent = pages[chunks[index]["page"]]
-                    r = round(distance * 1.0, 4)
-                    rec = by_page.get(parent["page"])
-                    if rec is None:
-                        rec = by_page[parent["page"]] = {
-                            "vector_similarity": r, "max_original_similarity": r, "page": parent["page"],
-                            "text": parent["text"], "hit_count": 1, "retrieval_sources": ["basic"],
-                            "source_sha1": sha1, "query_sources": [query_text]}
-                        out.append(rec)
-                    elif r > rec["vector_similarity"]:
-                        rec["vector_similarity"] = rec["max_original_similarity"] = r
+                self._records_py(out, query_text)
         except Exception as e:  # noqa: BLE001
             log(f"[ERROR] Vector search failed for query '{query_text[:60]}' in report {self.report_name}: {e}")
         return out
 
+    def _records_py(self, out, query_text):
+        sha1, chunks, pages = self.sha1, self.chunks, self.pages
+        if not self.parent_pages:
+            for distance, index in zip(self.scores, self.ids):
+                chunk = chunks[index]
+                if chunk["page"] not in pages:  # a missing parent page fails the hit, as in the reference (:1145)
+                    raise KeyError(chunk["page"])
+                r = round(distance * 1.0, 4)
+                out.append({"vector_similarity": r, "max_original_similarity": r, "page": chunk["page"],
+                            "text": chunk["text"], "hit_count": 1, "retrieval_sources": ["basic"],
+                            "source_sha1": sha1, "query_sources": [query_text]})
+        else:
+            by_page = {}
+            for distance, index in zip(self.scores, self.ids):
+                parent = pages[chunks[index]["page"]]
+                r = round(distance * 1.0, 4)
+                rec = by_page.get(parent["page"])
+                if rec is None:
+                    rec = by_page[parent["page"]] = {
+                        "vector_similarity": r, "max_original_similarity": r, "page": parent["page"],
+                        "text": parent["text"], "hit_count": 1, "retrieval_sources": ["basic"],
+                        "source_sha1": sha1, "query_sources": [query_text]}
+                    out.append(rec)
+                elif r > rec["vector_similarity"]:
+                    rec["vector_similarity"] = rec["max_original_similarity"] = r
+
     def direct_ok(self):
+        if self.parent_pages:
+            return True
+        if self.ids_ok is not None:
+            return bool(self.ids_ok)
         ids = self.ids
-        return self.parent_pages or (len(set(ids)) == len(ids) and (not ids or min(ids) >= 0))
+        return len(set(ids)) == len(ids) and (not ids or min(ids) >= 0)
 
 
 class VectorRetriever:
@@ -874,12 +916,17 @@ class VectorRetriever:
             except Exception as e:  # noqa: BLE001
                 self._safe_print(f"[ERROR] Vector search failed in report {report.get('name')}: {e}")
                 return [(q, []) for q in texts]
-            # .tolist() yields the same Python floats / ints as float(d) / int(i) per element, without the numpy
-            # scalar round trips (23k hits for a 127-question batch over six databases).  The rows stay raw here:
-            # _finalize turns them into records directly when it can, into hit tuples otherwise (_RawHits).
-            D_rows, I_rows = np.asarray(D).tolist(), np.asarray(I).tolist()
+            # The rows stay raw here (23k hits for a 127-question batch over six databases): _finalize turns
+            # them into records directly when it can, into hit tuples otherwise (_RawHits).
+            D = np.ascontiguousarray(D, dtype=np.float32)
+            I = np.ascontiguousarray(I, dtype=np.int64)
+            ids_ok = None
+            if I.shape[1] > 1:  # distinct, non-negative ids per row, for the whole batch at once
+                S = np.sort(I, axis=1)
+                ids_ok = ((S[:, 0] >= 0) & (S[:, 1:] != S[:, :-1]).all(axis=1)).tolist()
             name = report.get("name")
-            return [(q, _RawHits(sha1, chunks, pages, D_rows[qi], I_rows[qi], return_parent_pages, name))
+            return [(q, _RawHits(sha1, chunks, pages, D, I, qi, return_parent_pages, name,
+                                 None if ids_ok is None else ids_ok[qi]))
                     for qi, q in enumerate(texts)]
 
         if getattr(self, "batched_expansion", True):
@@ -1152,6 +1199,17 @@ class VectorRetriever:
         but every report is searched ONCE with the embeddings of all the questions routed to it (one
         tensor-core batch per year-DB, the year-DBs on their own GPUs in parallel).  `selected_years` is one
         list for the batch, or a list with one entry (list or None) per question."""
+        gc_was_enabled = gc.isenabled()   # see BM25Retriever.retrieve_batch
+        gc.disable()
+        try:
+            return self._retrieve_batch(company_name, queries, top_n, return_parent_pages, use_hyde, use_multi_query,
+                                        selected_years, multi_query_config, retrieval_method, max_hops, neighbor_k)
+        finally:
+            if gc_was_enabled:
+                gc.enable()
+
+    def _retrieve_batch(self, company_name, queries, top_n, return_parent_pages, use_hyde, use_multi_query,
+                        selected_years, multi_query_config, retrieval_method, max_hops, neighbor_k):
         per_question_years = (isinstance(selected_years, (list, tuple)) and len(selected_years) == len(queries)
                               and all(y is None or isinstance(y, (list, tuple)) for y in selected_years))
         plans = []
@@ -1301,7 +1359,7 @@ class VectorRetriever:
                 self._aggregate(aggregated, hits, query_text)
 
         final_results = direct if direct is not None else [self._final_record(info) for info in aggregated.values()]
-        final_results = sorted(final_results, key=lambda x: x["vector_similarity"], reverse=True)
+        final_results = sorted(final_results, key=_BY_SIMILARITY, reverse=True)
         all_initial_results = final_results.copy()
         final_results = final_results[:top_n]
         if progress_callback:

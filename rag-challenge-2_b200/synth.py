@@ -203,9 +203,11 @@ class _LazyPages(dict):
             return False
 
 
-def synthetic_year_report(name, company, n_chunks, vector_db, chunks_per_page=8):
+def synthetic_year_report(name, company, n_chunks, vector_db, chunks_per_page=8, materialise=False):
     """A report dict {"name", "vector_db", "document"} in the chunked-report schema whose
-    chunk / page records are generated on demand: chunk i sits on page i // chunks_per_page + 1."""
+    chunk / page records are generated on demand: chunk i sits on page i // chunks_per_page + 1.
+    `materialise=True` builds the real lists a report loaded from JSON holds (~0.4 KB of host RAM per chunk) —
+    what a host-path timing should run on: the on-demand records cost a Python call + an f-string per hit."""
     n_pages = (n_chunks + chunks_per_page - 1) // chunks_per_page
 
     def chunk(i):
@@ -215,6 +217,18 @@ def synthetic_year_report(name, company, n_chunks, vector_db, chunks_per_page=8)
     def page(p):
         return {"page": p, "text": f"{name} page {p}"}
 
+    if materialise:
+        import gc
+        was = gc.isenabled()
+        gc.disable()   # millions of acyclic dicts: the collector's generation passes would dominate the build
+        try:
+            document = {"metainfo": {"sha1_name": name, "company_name": company, "pages_amount": n_pages},
+                        "content": {"pages": [page(j + 1) for j in range(n_pages)],
+                                    "chunks": [chunk(i) for i in range(n_chunks)]}}
+        finally:
+            if was:
+                gc.enable()
+        return {"name": name, "vector_db": vector_db, "document": document}
     document = {"metainfo": {"sha1_name": name, "company_name": company, "pages_amount": n_pages},
                 "content": {"pages": _LazySeq(n_pages, lambda j: page(j + 1)), "chunks": _LazySeq(n_chunks, chunk)}}
     return {"name": name, "vector_db": vector_db, "document": document,

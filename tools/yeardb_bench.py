@@ -31,6 +31,8 @@ ap.add_argument("--questions", type=int, default=127)
 ap.add_argument("--top-n", type=int, default=30)
 ap.add_argument("--dim", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--lazy-records", action="store_true", help="chunk / page records generated on demand (r01 behaviour)")
+ap.add_argument("--python-records", action="store_true", help="build the records with the Python loops (no C helper)")
 args = ap.parse_args()
 
 COMPANY = "金盘科技"
@@ -44,7 +46,9 @@ for i, (year, n) in enumerate(zip(YEARS, sizes)):
     lo = i * ((args.rows_max + block - 1) // block + 1) * block     # disjoint seeded blocks per year
     rows = synth.dense_rows_torch(lo, lo + int(n), args.dim, dev)
     index = pkg.FlatIPIndex.from_device_tensor(rows)
-    reports.append(synth.synthetic_year_report(f"J{year}", COMPANY, int(n), index))
+    reports.append(synth.synthetic_year_report(f"J{year}", COMPANY, int(n), index, materialise=not args.lazy_records))
+if args.python_records:
+    retrieval._b2r_records = None
 retriever = retrieval.VectorRetriever.from_reports(reports, qwen=retrieval.HashEmbedder(args.dim), parallel_workers=8)
 
 questions = [f"{YEARS[i % 6]}年{COMPANY}的第{i}个财务指标是多少？" for i in range(args.questions)]
@@ -57,13 +61,16 @@ def strip(res):
 
 
 out = {"config": "6 year-DBs J2020-J2025, one per GPU (i % G)", "n_gpus": G, "rows_per_db": [int(n) for n in sizes],
-       "questions": args.questions, "top_n": args.top_n, "dim": args.dim, "mixes": {}}
+       "questions": args.questions, "top_n": args.top_n, "dim": args.dim,
+       "chunk_records": "on demand" if args.lazy_records else "materialised lists",
+       "record_helper": "C (_b2r_records)" if retrieval._b2r_records is not None else "python loops", "mixes": {}}
 for name, years in mixes.items():
     n_dbs = len(years) if years else len(YEARS)
     rows_scanned = int(sum(int(n) for y, n in zip(YEARS, sizes) if years is None or y in years))
     retriever.retrieve_batch(COMPANY, questions, selected_years=years, **kw)  # warm-up (workspaces, row norms)
-    t_batch = []
+    t_batch, got = [], None
     for _ in range(args.reps):
+        got = None   # the previous batch's records are released before the clock starts, not inside the call
         t0 = time.perf_counter()
         got = retriever.retrieve_batch(COMPANY, questions, selected_years=years, **kw)
         t_batch.append(time.perf_counter() - t0)
