@@ -42,9 +42,12 @@ def main():
     qall = torch.randn((8, d), generator=gq, device="cuda")
     qall /= qall.norm(dim=1, keepdim=True)
     gbytes = n * d * 4 / 1e9
+    for kv in sys.argv[4:]:   # key=value tunables for the "defaults" pass
+        key, v = kv.split("=")
+        _lib.tunable_set(key, int(v))
     for nq in (1, 2, 3, 4, 8):
         ms = time_search(index, qall[:nq].contiguous(), 30)
-        print(json.dumps({"defaults": 1, "nq": nq, "ms": round(ms, 4), "gbps": round(gbytes / ms * 1e3, 1)}), flush=True)
+        print(json.dumps({"defaults": 1, "tunables": sys.argv[4:], "nq": nq, "ms": round(ms, 4), "gbps": round(gbytes / ms * 1e3, 1)}), flush=True)
     if len(sys.argv) > 3 and sys.argv[3] == "defaults":
         return
     results = []

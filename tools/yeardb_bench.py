@@ -33,6 +33,7 @@ ap.add_argument("--dim", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--lazy-records", action="store_true", help="chunk / page records generated on demand (r01 behaviour)")
 ap.add_argument("--python-records", action="store_true", help="build the records with the Python loops (no C helper)")
+ap.add_argument("--phases", action="store_true", help="also report where the host time of one batch goes")
 args = ap.parse_args()
 
 COMPANY = "金盘科技"
@@ -103,8 +104,33 @@ for name, years in mixes.items():
     for d, e0, e1 in evs:
         torch.cuda.synchronize(d)
         dev_ms = max(dev_ms, e0.elapsed_time(e1))
+    phases = None
+    if args.phases:   # wall time inside the retriever's own phases for one more batch (wrappers add ~1 us per call)
+        spent = {}
+
+        def timed(fn, key):
+            def run(*a, **k):
+                t = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    spent[key] = spent.get(key, 0.0) + time.perf_counter() - t
+            return run
+
+        originals = {}
+        for key in ("_prepare", "_embed_queries", "_search_reports", "_finalize", "_direct_records"):
+            originals[key] = getattr(retriever, key)
+            setattr(retriever, key, timed(originals[key], key))
+        got = None
+        t0 = time.perf_counter()
+        got = retriever.retrieve_batch(COMPANY, questions, selected_years=years, **kw)
+        spent["total"] = time.perf_counter() - t0
+        for key, fn in originals.items():
+            setattr(retriever, key, fn)
+        phases = {key: round(v * 1e3, 2) for key, v in spent.items()}
     best = min(t_batch)
     out["mixes"][name] = {
+        "host_phases_ms": phases,
         "dbs_searched": n_dbs, "rows_scanned_per_question": rows_scanned,
         "batch_s": round(best, 4), "batch_questions_per_s": round(args.questions / best, 1),
         "loop_s": round(t_loop, 4), "loop_questions_per_s": round(args.questions / t_loop, 1),
