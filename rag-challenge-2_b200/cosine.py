@@ -28,6 +28,10 @@ def cosine_stats(rows, col_begin=0, col_end=None, n_bins=N_BINS, finalize=True):
         raise ValueError("cosine_stats needs a contiguous float32 CUDA tensor [n, d]")
     n, d = int(rows.shape[0]), int(rows.shape[1])
     col_end = n if col_end is None else int(col_end)
+    source = rows
+    if d % 32:  # the kernels take widths that are multiples of 32: zero columns change neither norms nor products
+        rows = torch.nn.functional.pad(rows, (0, 32 - d % 32)).contiguous()
+        d = int(rows.shape[1])
     stats = torch.zeros(6, dtype=torch.float64, device=rows.device)
     hist = torch.zeros(n_bins, dtype=torch.int64, device=rows.device)
     stream = torch.cuda.current_stream(rows.device).cuda_stream
@@ -39,7 +43,7 @@ def cosine_stats(rows, col_begin=0, col_end=None, n_bins=N_BINS, finalize=True):
         return stats, hist
     out = finalize_stats(stats.cpu().numpy(), hist.cpu().numpy())
     if 2 <= n <= EXACT_MEDIAN_MAX_ROWS and int(col_begin) == 0 and col_end == n:
-        out["median_similarity"] = exact_median_small(rows)
+        out["median_similarity"] = exact_median_small(source)
     return out
 
 
