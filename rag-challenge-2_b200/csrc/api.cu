@@ -55,6 +55,8 @@ static std::map<std::string, int>& tunables() {
       {"bm25.debug_skip", 0},      // perf experiments (wrong results): 1 no select, 2 no accumulate, 4 no merge
       {"bm25.no_skip", 0},         // 1: streaming kernel ignores the block index (binary searches in the producer)
       {"exchange.timeout_ms", 0},  // bound on the exchange kernel's wait for its peers (default 10000 ms)
+      {"bm25.no_slots", 0},        // 1: streaming kernel without the per-query threshold slots (r02 A/B)
+      {"bm25.pilot_blocks", 0},    // blocks per query in the pilot launch (0: about three waves in all, -1: no pilot launch)
       {"bm25.cfg", 0},             // ring geometry of the streaming kernel (A/B runs; see bm25_stream_launch)
       {"bm25.ctas_per_sm", 0},     // cap on resident streaming-kernel CTAs per SM
       {"hybrid.no_copy_stream", 0},// 1: the host step's H2D copy goes on the step's own stream (experiment)

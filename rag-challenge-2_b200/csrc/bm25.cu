@@ -376,12 +376,14 @@ struct Bm25StreamArgs {
   const u32* skip;          // [V][n_blocks + 1] first posting (relative to indptr[t]) with doc >= b * kStreamBlk; may be NULL
   long long n_docs;
   int n_blocks;
+  int b_begin, b_count;     // this launch covers blocks [b_begin, b_begin + b_count) of every query (pilot / main launch)
   const int* term_ids;
   const int* term_offsets;
   int q_base, nq_launch;
   int k;
   u128* partial;            // [nq_launch][n_blocks][k]
   u64* tau_g;               // [nq_launch]
+  u64* slots;               // [nq_launch][k] best score seen among the documents with id % k == slot (0: none); may be NULL
   double* dense;            // non-NULL: write the scores of query q_base densely, skip the select
   int debug_skip;           // perf experiments only (wrong results): 1 no select, 2 no accumulate
 };
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
     mbar_fence_init();
   }
   __syncthreads();
-  const long long n_items = static_cast<long long>(a.nq_launch) * a.n_blocks;
+  const long long n_items = static_cast<long long>(a.nq_launch) * a.b_count;
   // CTA c takes items c, c + grid, ...: at any time the whole grid works on one or two queries, so a query's
   // threshold tau_g saturates within its first wave of blocks and the remaining blocks select next to nothing
   const long long item_lo = blockIdx.x, item_hi = n_items, item_step = gridDim.x;
@@ -436,8 +438,8 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
     u32 nx0 = 0, nx1 = 0;  // prefetched block-index entries of the next item (lane-held)
     bool have_next = false;
     for (long long item = item_lo; item < item_hi; item += item_step) {
-      const int ql = static_cast<int>(item / a.n_blocks);
-      const int b = static_cast<int>(item - static_cast<long long>(ql) * a.n_blocks);
+      const int ql = static_cast<int>(item / a.b_count);
+      const int b = a.b_begin + static_cast<int>(item - static_cast<long long>(ql) * a.b_count);
       const long long lo = static_cast<long long>(b) * kStreamBlk;
       const long long hi = min(a.n_docs, lo + kStreamBlk);
       if (ql != cur_q) {
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
         }
         if (tb == t0) {  // prefetch the next item's entries when it belongs to the same query
           have_next = false;
-          if (a.skip && item + item_step < item_hi && b + item_step < a.n_blocks) {
+          if (a.skip && item + item_step < item_hi && b + item_step < a.b_begin + a.b_count) {
             if (t0 + lane < t1) {
               const u32* row = a.skip + static_cast<size_t>(term) * (a.n_blocks + 1) + (b + item_step);
               nx0 = row[0];
@@ -563,10 +565,10 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
   u64* s_mn = ctl + 2;
   u64* s_mx = ctl + 3;
   // item -> (query, block) without a 64-bit division per item: the coordinates advance with the stride
-  int ql = static_cast<int>(item_lo / a.n_blocks);
-  int b = static_cast<int>(item_lo - static_cast<long long>(ql) * a.n_blocks);
-  const int step_q = static_cast<int>(item_step / a.n_blocks);
-  const int step_b = static_cast<int>(item_step - static_cast<long long>(step_q) * a.n_blocks);
+  int ql = static_cast<int>(item_lo / a.b_count);
+  int b = a.b_begin + static_cast<int>(item_lo - static_cast<long long>(ql) * a.b_count);
+  const int step_q = static_cast<int>(item_step / a.b_count);
+  const int step_b = static_cast<int>(item_step - static_cast<long long>(step_q) * a.b_count);
   const bool no_acc = (a.debug_skip & 2) != 0;
   for (long long item = item_lo; item < item_hi; item += item_step) {
     const int lo_i = b * kStreamBlk;
@@ -599,8 +601,8 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
     const int ql_now = ql, b_now = b;  // advance the coordinates for the next item (every path below may `continue`)
     b += step_b;
     ql += step_q;
-    if (b >= a.n_blocks) {
-      b -= a.n_blocks;
+    if (b >= a.b_begin + a.b_count) {
+      b -= a.b_count;
       ++ql;
     }
     if (a.dense) {
@@ -793,7 +795,38 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
       // k documents of this block score >= sel[k - 1]: nothing below it can enter the query's top k
       atomicMax(a.tau_g + ql_now, static_cast<u64>(sel[k - 1] >> 64));
     }
-    named_bar_sync_256();  // the list area is reused by the next item
+    // A block's own k-th best is a weak bound (the 30th of 4096 documents is far below the 30th of ten million).  The
+    // query also keeps k slots, slot j = the best score seen among the documents with id % k == j: the slots hold k
+    // DISTINCT documents, so their minimum is a lower bound of the query's k-th best score — and since the best
+    // documents spread over the slots it settles near the (k ln k)-th best score seen so far.  With it, most blocks
+    // after a query's first wave have no document at or above the threshold and leave through the one-barrier path.
+    if (a.slots != nullptr) {
+      u64* sl = a.slots + static_cast<size_t>(ql_now) * k;
+      const int m = min(min(n_sel, p2), k);
+      for (int i = ct; i < m; i += 256) {
+        const u128 key = sel[i];
+        if (key != 0) {
+          u64* slot = sl + (0xFFFFFFFFu - static_cast<u32>(key)) % static_cast<u32>(k);
+          const u64 sc = static_cast<u64>(key >> 64);
+          if (sc > *reinterpret_cast<volatile u64*>(slot)) atomicMax(slot, sc);
+        }
+      }
+    }
+    named_bar_sync_256();  // the list area is reused by the next item; the slot updates of this block are done
+    if (a.slots != nullptr && warp == 0) {
+      const u64* sl = a.slots + static_cast<size_t>(ql_now) * k;
+      u64 mn = ~0ull;
+      for (int j = lane; j < k; j += 32) {
+        const u64 v = *reinterpret_cast<const volatile u64*>(sl + j);
+        mn = v < mn ? v : mn;
+      }
+#pragma unroll
+      for (int mm = 16; mm > 0; mm >>= 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, mn, mm);
+        mn = o < mn ? o : mn;
+      }
+      if (lane == 0 && mn != 0ull) atomicMax(a.tau_g + ql_now, mn);  // 0: some slot is still empty
+    }
   }
   pdl_wait_for_previous_grid();
 }
@@ -1057,7 +1090,7 @@ static int bm25_stream_launch_cfg(b2r_bm25* h, Bm25StreamArgs<W> a, cudaStream_t
                       static_cast<size_t>(kStreamSelCap) * 16;
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  const long long n_items = static_cast<long long>(a.nq_launch) * a.n_blocks;
+  const long long n_items = static_cast<long long>(a.nq_launch) * a.b_count;
   int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(MINB, (227 * 1024) / (smem + 1024))));
   if (tunable("bm25.ctas_per_sm") > 0) per_sm = std::min(per_sm, tunable("bm25.ctas_per_sm"));
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_items, static_cast<long long>(h->num_sms) * per_sm)));
@@ -1099,9 +1132,11 @@ static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term
   Bm25Ws ws;
   int rc = bm25_get_ws(h, stream, &ws);
   if (rc) return rc;
-  const size_t per_q = static_cast<size_t>(h->n_blocks) * k * 16;
+  // per query: the (block) lists + the k threshold slots
+  const bool use_slots = !dense_dev && !tunable("bm25.no_slots");
+  const size_t per_q = static_cast<size_t>(h->n_blocks) * k * 16 + (use_slots ? static_cast<size_t>(k) * 8 : 0);
   // the first half of the stream's workspace only: the second half carries the doc-block kernel's alternate control words
-  long long max_q = static_cast<long long>(((ws.bytes / 2 & ~static_cast<size_t>(255)) - kBm25CtlBytes) / per_q);
+  long long max_q = static_cast<long long>(((ws.bytes / 2 & ~static_cast<size_t>(255)) - kBm25CtlBytes - 256) / per_q);
   max_q = std::min<long long>(max_q, kBm25MaxQPerLaunch);
   if (max_q < 1) return fail(B2R_ERR_UNSUPPORTED, "bm25: workspace too small for one query (corpus x k too large)");
   for (int q0 = 0; q0 < nq; q0 += static_cast<int>(max_q)) {
@@ -1118,19 +1153,38 @@ static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term
     a.q_base = q0;
     a.nq_launch = static_cast<int>(std::min<long long>(max_q, nq - q0));
     a.k = k;
-    a.partial = reinterpret_cast<u128*>(ws.base + kBm25CtlBytes);
     a.tau_g = reinterpret_cast<u64*>(ws.base + kBm25CtlBytes / 2);
+    // [slots: nq_launch x k, cleared below — the doc-block kernel keeps its own lists in this workspace][lists]
+    const size_t slot_bytes = use_slots ? ((static_cast<size_t>(a.nq_launch) * k * 8 + 255) & ~static_cast<size_t>(255)) : 0;
+    a.slots = use_slots ? reinterpret_cast<u64*>(ws.base + kBm25CtlBytes) : nullptr;
+    a.partial = reinterpret_cast<u128*>(ws.base + kBm25CtlBytes + slot_bytes);
     a.dense = dense_dev;
     a.debug_skip = tunable("bm25.debug_skip");
-    if (h->weight_bits == 64) {
-      Bm25StreamArgs<double> ad;
-      memcpy(&ad, &a, sizeof(a));  // identical layout: only the weight pointer type differs
-      rc = bm25_stream_launch(h, ad, stream, overlap_prev && q0 == 0);
-    } else {
-      rc = bm25_stream_launch(h, a, stream, overlap_prev && q0 == 0);
+    if (use_slots) B2R_CUDA(cudaMemsetAsync(a.slots, 0, static_cast<size_t>(a.nq_launch) * k * 8, stream));
+    // Pilot launch.  Every query's first wave of blocks meets no threshold and pays the full histogram select; with
+    // many queries in a launch that is the whole grid once per query.  So the first few blocks of EVERY query go first
+    // (about one wave in all): when the main launch reaches a query, its slots already hold a threshold from those
+    // blocks and its first wave selects among a handful of documents instead of 4096.  One query alone gains nothing
+    // (its first wave is a fifth of its blocks either way), so small batches keep the single launch.
+    int pilot = 0;
+    if (use_slots && a.nq_launch >= 4) {
+      pilot = tunable("bm25.pilot_blocks");
+      if (pilot == 0) pilot = std::max(1, 3 * h->num_sms / a.nq_launch);
+      if (pilot < 0 || pilot * 4 > a.n_blocks) pilot = 0;
     }
-    if (rc) return rc;
-    ++launch_counter();
+    for (int part = pilot > 0 ? 0 : 1; part < 2; ++part) {
+      a.b_begin = part == 0 ? 0 : pilot;
+      a.b_count = part == 0 ? pilot : a.n_blocks - pilot;
+      if (h->weight_bits == 64) {
+        Bm25StreamArgs<double> ad;
+        memcpy(&ad, &a, sizeof(a));  // identical layout: only the weight pointer type differs
+        rc = bm25_stream_launch(h, ad, stream, overlap_prev && q0 == 0 && part == (pilot > 0 ? 0 : 1));
+      } else {
+        rc = bm25_stream_launch(h, a, stream, overlap_prev && q0 == 0 && part == (pilot > 0 ? 0 : 1));
+      }
+      if (rc) return rc;
+      ++launch_counter();
+    }
     if (!dense_dev) {
       const int msmem = kMergeCap * 16 + 1024 * 16 + (kSelBins + 4) * 4;
       auto mk = bm25_merge_kernel;

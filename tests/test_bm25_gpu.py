@@ -263,13 +263,49 @@ def test_streaming_kernel_variants_agree(b2r):
             top = oracle.bm25_topn_ref(want, k)
             assert np.array_equal(base[1][qi], top), f"k={k} q{qi}"
             assert np.array_equal(base[0][qi], want[top])
-        for key in ("bm25.no_skip", "bm25.v1"):
-            _lib.tunable_set(key, 1)
+        # ... and so must the streaming kernel without its threshold slots, with a pilot launch over the first two
+        # blocks of every query (the default takes one only on corpora of many blocks), and without one
+        for key, value in (("bm25.no_skip", 1), ("bm25.v1", 1), ("bm25.no_slots", 1), ("bm25.pilot_blocks", 2),
+                           ("bm25.pilot_blocks", -1)):
+            _lib.tunable_set(key, value)
             try:
                 S, I = idx.topk(queries, k)
             finally:
                 _lib.tunable_set(key, 0)
-            assert np.array_equal(I, base[1]) and np.array_equal(S, base[0]), f"{key} k={k}"
+            assert np.array_equal(I, base[1]) and np.array_equal(S, base[0]), f"{key}={value} k={k}"
+
+
+def test_streaming_kernel_threshold_slots_many_blocks(b2r):
+    """A corpus of ~100 blocks and a batch large enough for the default pilot launch: the sharper threshold (k slots
+    per query, minimum over the slots) prunes most blocks, the answers must not move — including k = 1 (one slot),
+    a k that does not divide the block size, heavy ties at the k-th place and an all-zero query."""
+    from rag_challenge_2_b200 import _lib
+    from rag_challenge_2_b200.bm25 import BM25Okapi
+
+    s = synth(b2r)
+    docs = s.token_corpus_np(400_000, vocab=5000, seed=31)
+    for i in range(1000, 400_000, 997):          # identical documents spread over the blocks: exact ties
+        docs[i] = docs[1000]
+    idx = BM25Okapi(docs, weight_bits=64)
+    queries = [as_tokens(q) for q in s.token_queries_np(70, vocab=5000, seed=32)]
+    queries[3] = []
+    queries[5] = list(docs[1000][:6])            # its best documents are the ~400 copies
+    for k in (1, 7, 30, 200):
+        base = None
+        for key, value in (("bm25.no_slots", 1), ("bm25.no_slots", 0), ("bm25.pilot_blocks", -1), ("bm25.pilot_blocks", 9)):
+            _lib.tunable_set(key, value)
+            try:
+                got = idx.topk(queries, k)
+            finally:
+                _lib.tunable_set(key, 0)
+            if base is None:
+                base = got
+                for qi in (0, 3, 5, 69):         # the slot-free kernel against the formula
+                    want = idx.get_scores(queries[qi])
+                    top = oracle.bm25_topn_ref(want, k)
+                    assert np.array_equal(base[1][qi], top) and np.array_equal(base[0][qi], want[top]), (k, qi)
+            else:
+                assert np.array_equal(got[1], base[1]) and np.array_equal(got[0], base[0]), f"{key}={value} k={k}"
 
 
 def test_streaming_kernel_heavy_ties(b2r):
