@@ -429,8 +429,7 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
     // the two block-index entries per token change, and those of the NEXT item are loaded while this item's
     // copies are being issued.
     const u64 policy = l2_policy_evict_first();
-    int s = 0;
-    u32 ph = 0;
+    u32 gs = 0;  // stages issued so far by this CTA: stage n lives in slot n % STAGES, round parity (n / STAGES) & 1
     int cur_q = -1, t0 = 0, t1 = 0;
     int term = 0;          // lane-held token table (first 32 tokens of the query)
     long long ib = 0, ie = 0;
@@ -457,16 +456,14 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
       }
       if (t1 == t0) {  // a query without known tokens: one empty stage closes the item
         if (lane == 0) {
-          mbar_wait_wd(&empty[s], ph ^ 1u);
-          meta[s].fv = meta[s].lv = 0;
-          meta[s].idf = 0.0;
-          meta[s].flags = 3;
-          mbar_arrive(&full[s]);
+          const int slot = static_cast<int>(gs % STAGES);
+          mbar_wait_wd(&empty[slot], ((gs / STAGES) & 1u) ^ 1u);
+          meta[slot].fv = meta[slot].lv = 0;
+          meta[slot].idf = 0.0;
+          meta[slot].flags = 3;
+          mbar_arrive(&full[slot]);
         }
-        if (++s == STAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
+        ++gs;
         continue;
       }
       for (int tb = t0; tb < t1; tb += 32) {
@@ -512,42 +509,81 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
           }
         }
         const int nt = min(32, t1 - tb);
-        for (int u = 0; u < nt; ++u) {
+        // One lane issuing every stage (wait for the slot, four stores, expect-tx, two bulk copies: several hundred
+        // cycles of dependent instructions) was the critical path of the whole kernel — its time scaled with the
+        // number of producers per SM, not with the postings.  So the stages of a token group are flattened in token
+        // order (lane u owns token u's aligned window [a0, a1) and its chunk count; an exclusive scan numbers them)
+        // and issued STAGES at a time, one per lane, in parallel: the slots of a round are distinct, and each lane
+        // waits only for its own slot's previous use, which every earlier round has already issued.
+        const long long wa0 = p0 & ~3LL, wa1 = (p1 + 3) & ~3LL;  // 16-byte aligned copy window; consumers mask by index
+        // a token without postings in this block issues nothing (rare terms miss most blocks; every stage is a visit
+        // and a token barrier for the eight consumer warps)
+        const int nch = (lane < nt && p1 > p0) ? static_cast<int>((wa1 - wa0 + CHUNK - 1) / CHUNK) : 0;
+        int incl = nch;
+#pragma unroll
+        for (int mm = 1; mm < 32; mm <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, mm);
+          if (lane >= mm) incl += v;
+        }
+        const int pre = incl - nch;
+        const int n_stages = __shfl_sync(0xffffffffu, incl, 31);
+        const bool last_group = tb + 32 >= t1;
+        if (n_stages == 0) {
+          if (last_group) {  // nothing of the last tokens in this block: a bare marker closes the item
+            if (lane == 0) {
+              const int slot = static_cast<int>(gs % STAGES);
+              mbar_wait_wd(&empty[slot], ((gs / STAGES) & 1u) ^ 1u);
+              meta[slot].fv = meta[slot].lv = 0;
+              meta[slot].idf = 0.0;
+              meta[slot].flags = 3;
+              mbar_arrive(&full[slot]);
+            }
+            ++gs;
+          }
+          continue;
+        }
+        for (int base = 0; base < n_stages; base += STAGES) {
+          const int g = base + lane;
+          const bool on = lane < STAGES && g < n_stages;
+          int u = 0;  // the token of stage g: the largest u < nt with pre_u <= g (tokens after the owner start above g)
+#pragma unroll
+          for (int bit = 16; bit > 0; bit >>= 1) {
+            const int cand = u + bit;
+            const int pc = __shfl_sync(0xffffffffu, pre, cand & 31);
+            if (cand < nt && pc <= g) u = cand;
+          }
           const long long q0 = __shfl_sync(0xffffffffu, p0, u), q1 = __shfl_sync(0xffffffffu, p1, u);
           const double qidf = __shfl_sync(0xffffffffu, tidf, u);
-          const bool last_token = (tb + u == t1 - 1);
-          // 16-byte aligned copy window [a0, a1) around [q0, q1); consumers mask by posting index
-          const long long a0 = q0 & ~3LL;
-          const long long a1 = (q1 + 3) & ~3LL;
-          long long c0 = a0;
-          do {
+          const int pu = __shfl_sync(0xffffffffu, pre, u), nu = __shfl_sync(0xffffffffu, nch, u);
+          if (on) {
+            const long long a0 = q0 & ~3LL, a1 = (q1 + 3) & ~3LL;
+            const int c = g - pu;
+            const long long c0 = a0 + static_cast<long long>(c) * CHUNK;
             const long long c1 = min(a1, c0 + CHUNK);
             const int cnt = static_cast<int>(c1 - c0);
-            const bool last_chunk = c1 >= a1;
-            if (lane == 0) {
-              mbar_wait_wd(&empty[s], ph ^ 1u);
-              StreamMeta& m = meta[s];
-              m.idf = qidf;
-              m.fv = static_cast<int>(max(q0 - c0, 0LL));
-              m.lv = static_cast<int>(min(q1 - c0, static_cast<long long>(cnt)));
-              m.flags = (last_chunk ? 1 : 0) | ((last_chunk && last_token) ? 2 : 0);
-              unsigned char* st = ring + static_cast<size_t>(s) * kStageBytes;
-              if (cnt > 0) {
-                mbar_arrive_expect_tx(&full[s], static_cast<u32>(cnt) * (4u + static_cast<u32>(sizeof(W))));
-                bulk_g2s(st, a.doc_ids + c0, static_cast<u32>(cnt) * 4u, &full[s], policy);
-                bulk_g2s(st + CHUNK * 4, a.weight + c0, static_cast<u32>(cnt) * static_cast<u32>(sizeof(W)), &full[s],
-                         policy);
-              } else {
-                mbar_arrive(&full[s]);
-              }
+            const bool last_chunk = c == nu - 1;
+            const bool last_token = last_group && g == n_stages - 1;  // the item's last stage (later tokens are absent here)
+            const u32 n = gs + static_cast<u32>(g);
+            const int slot = static_cast<int>(n % STAGES);
+            mbar_wait_wd(&empty[slot], ((n / STAGES) & 1u) ^ 1u);
+            StreamMeta& m = meta[slot];
+            m.idf = qidf;
+            m.fv = static_cast<int>(max(q0 - c0, 0LL));
+            m.lv = static_cast<int>(min(q1 - c0, static_cast<long long>(cnt)));
+            m.flags = (last_chunk ? 1 : 0) | ((last_chunk && last_token) ? 2 : 0);
+            unsigned char* st = ring + static_cast<size_t>(slot) * kStageBytes;
+            if (cnt > 0) {
+              mbar_arrive_expect_tx(&full[slot], static_cast<u32>(cnt) * (4u + static_cast<u32>(sizeof(W))));
+              bulk_g2s(st, a.doc_ids + c0, static_cast<u32>(cnt) * 4u, &full[slot], policy);
+              bulk_g2s(st + CHUNK * 4, a.weight + c0, static_cast<u32>(cnt) * static_cast<u32>(sizeof(W)), &full[slot],
+                       policy);
+            } else {
+              mbar_arrive(&full[slot]);
             }
-            if (++s == STAGES) {
-              s = 0;
-              ph ^= 1u;
-            }
-            c0 = c1;
-          } while (c0 < a1);
+          }
+          __syncwarp();
         }
+        gs += static_cast<u32>(n_stages);
       }
     }
     pdl_wait_for_previous_grid();
@@ -1118,6 +1154,8 @@ static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<float> a, cudaStream_t
   switch (tunable("bm25.cfg")) {
     case 1: return bm25_stream_launch_cfg<float, 1024, 6, 2>(h, a, stream, overlap_prev);
     case 2: return bm25_stream_launch_cfg<float, 512, 8, 2>(h, a, stream, overlap_prev);
+    case 3: return bm25_stream_launch_cfg<float, 256, 12, 3>(h, a, stream, overlap_prev);
+    case 4: return bm25_stream_launch_cfg<float, 128, 24, 3>(h, a, stream, overlap_prev);
     default: return bm25_stream_launch_cfg<float, 512, 6, 3>(h, a, stream, overlap_prev);
   }
 }
