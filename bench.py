@@ -224,6 +224,18 @@ def cpu_baseline(args, n_queries, rows_host=None, bm25_docs=None, budget_s=60.0,
     except Exception:  # noqa: BLE001 - not installed (or unusable): the port is the baseline
         real = {}
     dense = (lambda x: real["flat"].search(x, args.k)) if real else (lambda x: oracle.flat_ip_search_ref(rows_host, x, args.k))
+    # "all the host threads it can use": torchrun exports OMP_NUM_THREADS=1 to its ranks, which would silently make the
+    # all-cores leg a one-thread leg at N > 1 — the BLAS pool is set explicitly, and what it really has is reported
+    cores = os.cpu_count()
+    blas_threads = None
+    if threadpool_limits is not None:
+        try:
+            from threadpoolctl import threadpool_info
+
+            threadpool_limits(limits=cores)   # stays in force for the process (the one-thread leg below narrows it again)
+            blas_threads = max([int(i.get("num_threads", 0)) for i in threadpool_info()] or [0]) or None
+        except Exception:  # noqa: BLE001
+            blas_threads = None
     dense(xq[:1])   # one untimed pass (BLAS thread pool, page faults)
     t_dense = t_bm = t_fuse = 0.0
     done = 0
@@ -257,10 +269,9 @@ def cpu_baseline(args, n_queries, rows_host=None, bm25_docs=None, budget_s=60.0,
     f_dense, f_bm = N / n_dense, N / n_docs
     dense_at_n, bm_at_n = t_dense * f_dense, t_bm * f_bm
     per_query = dense_at_n + bm_at_n + t_fuse
-    cores = os.cpu_count()
     return {
-        "value": 1.0 / per_query, "unit": UNIT, "cores": cores, "kind": kind, "port_vs_packages": deviation,
-        "threads": {"dense_scan_openblas": cores, "bm25_python_loops": 1},
+        "value": 1.0 / per_query, "unit": UNIT, "cores": blas_threads or cores, "kind": kind, "port_vs_packages": deviation,
+        "threads": {"dense_scan_openblas": blas_threads or cores, "bm25_python_loops": 1, "host_cpus": cores},
         "sample": (("faiss-cpu IndexFlatIP.search + rank_bm25.BM25Okapi.get_scores (the packages themselves, installed on this "
                     "machine) + Python stable sort" if real else
                     "oracle port (numpy/OpenBLAS fp32 scan on all cores + partial sort; rank_bm25's per-document dict loops + "
