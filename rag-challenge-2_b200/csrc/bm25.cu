@@ -357,8 +357,9 @@ __device__ __forceinline__ void consumer_sort_desc(K* a, int n, int ct) {
 //              global threshold tau_g (k-th best score any finished block has published), reduced to the best k
 //              by a histogram select on the ordered score bits (equal scores: ascending id), sorted, written to
 //              the per-(query, block) list; bm25_merge_kernel (one CTA per query) merges the lists.
-// Shared memory: 32 KiB accumulators + ring + 8 KiB histogram + 8 KiB list; float32 weights: 6 stages x 512 postings x
-// 8 B = 24 KiB -> 73 KiB, three CTAs per SM; float64 weights: 6 x 512 x 12 B = 36 KiB -> 85 KiB, two (see bm25_stream_launch).
+// Shared memory: 32 KiB accumulators (the select's 8 KiB histogram + 8 KiB list borrow their first 16 KiB) + the ring;
+// float32 weights: 5 stages x 1024 postings x 8 B = 40 KiB -> 73 KiB; float64 weights: 3 x 1024 x 12 B = 36 KiB -> 69 KiB;
+// three CTAs per SM either way (see bm25_stream_launch).
 // Algorithmic bytes per query: sum_t df_t * (4 + sizeof(weight)); the block index adds 8 B per (token, block).
 // ----------------------------------------------------------------------------------------------
 static const int kStreamBlk = 4096;       // documents per work item (block index granularity)
@@ -406,9 +407,14 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
   u64* full = reinterpret_cast<u64*>(meta + STAGES);
   u64* empty = full + STAGES;
   u64* ctl = empty + STAGES;                                                    // [8] select control words
-  u32* hist = reinterpret_cast<u32*>(ctl + 8);                                         // [kSelBins]
-  u128* sel = reinterpret_cast<u128*>(
-      (reinterpret_cast<uintptr_t>(hist + kSelBins) + 15) & ~static_cast<uintptr_t>(15));  // [kStreamSelCap]
+  // The select's histogram and candidate list live IN the accumulator area (its first 16 KiB): when a block has a
+  // candidate at all, every thread has moved its accumulators to registers and cleared them, and nothing touches the
+  // area until the next item's first stage.  A block that used them hands the area back zeroed.  The 16 KiB saved are
+  // ring: 1024-posting stages (fewer hand-overs per item, which is what the kernel's time follows) at three CTAs per SM.
+  static_assert(kSelBins * 4 + kStreamSelCap * 16 <= kStreamBlk * 8, "select scratch must fit the accumulator area");
+  u32* hist = reinterpret_cast<u32*>(acc);                                             // [kSelBins]
+  u128* sel = reinterpret_cast<u128*>(stream_smem + kSelBins * 4);                     // [kStreamSelCap]
+  constexpr int kScratchRows = (kSelBins * 4 + kStreamSelCap * 16) / 8 / 256;          // accumulator rows under them
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -848,7 +854,10 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
         }
       }
     }
-    named_bar_sync_256();  // the list area is reused by the next item; the slot updates of this block are done
+    named_bar_sync_256();  // every read of the list is done (and the slot updates of this block)
+#pragma unroll
+    for (int i = 0; i < kScratchRows; ++i) acc[i * 256 + ct] = 0.0;  // the scratch was accumulator space: zero it again
+    named_bar_sync_256();  // ... before any warp starts the next item
     if (a.slots != nullptr && warp == 0) {
       const u64* sl = a.slots + static_cast<size_t>(ql_now) * k;
       u64 mn = ~0ull;
@@ -1122,8 +1131,7 @@ static int bm25_stream_launch_cfg(b2r_bm25* h, Bm25StreamArgs<W> a, cudaStream_t
   a.weight = static_cast<const W*>(h->weight);
   auto kern = bm25_stream_kernel<W, CHUNK, STAGES, MINB>;
   const size_t smem = kStreamBlk * sizeof(double) + static_cast<size_t>(STAGES) * CHUNK * (4 + sizeof(W)) +
-                      STAGES * sizeof(StreamMeta) + 2 * STAGES * 8 + 8 * 8 + kSelBins * 4 + 16 +
-                      static_cast<size_t>(kStreamSelCap) * 16;
+                      STAGES * sizeof(StreamMeta) + 2 * STAGES * 8 + 8 * 8;  // select scratch: inside the accumulators
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   B2R_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const long long n_items = static_cast<long long>(a.nq_launch) * a.b_count;
@@ -1145,23 +1153,25 @@ static int bm25_stream_launch_cfg(b2r_bm25* h, Bm25StreamArgs<W> a, cudaStream_t
   return B2R_OK;
 }
 
-// Ring geometry (postings per stage, stages) and resident CTAs per SM.  The kernel waits more than it issues
-// (profiles/r02_bm25.md), so a third CTA per SM pays even though 72 registers per thread spill a little in the rare
-// select path: float32 weights 4.59 -> 4.22 ms for 64 queries over 10M documents with 512-posting stages x 6 (73 KiB).
-// float64 weights (12 B / posting): 512 x 6 = 85 KiB, two CTAs (the 1024-posting stages of r01 left room for one).
-// bm25.cfg = 1 / 2 select the alternatives.
+// Ring geometry (postings per stage, stages) and resident CTAs per SM.  Two things set the kernel's time: resident CTAs
+// (it waits more than it issues: 1 / 2 / 3 CTAs per SM = 8.8 / 5.0 / 4.2 ms for 64 queries over 10M documents, r01-r02)
+// and the number of stage hand-overs per item (256-posting stages x 12: +35 %, 128 x 24: +140 %).  With the select's
+// scratch inside the accumulator area the ring has 40 KiB at three CTAs per SM: 1024-posting stages x 5 for float32
+// weights (64 queries 2.65 -> 2.38 ms), x 3 for float64 weights (12 B / posting; three CTAs instead of two: 3.42 -> 2.63 ms).
+// bm25.cfg = 1 / 2 select the earlier geometries for A/B runs.
 static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<float> a, cudaStream_t stream, bool overlap_prev) {
   switch (tunable("bm25.cfg")) {
     case 1: return bm25_stream_launch_cfg<float, 1024, 6, 2>(h, a, stream, overlap_prev);
-    case 2: return bm25_stream_launch_cfg<float, 512, 8, 2>(h, a, stream, overlap_prev);
-    case 3: return bm25_stream_launch_cfg<float, 256, 12, 3>(h, a, stream, overlap_prev);
-    case 4: return bm25_stream_launch_cfg<float, 128, 24, 3>(h, a, stream, overlap_prev);
-    default: return bm25_stream_launch_cfg<float, 512, 6, 3>(h, a, stream, overlap_prev);
+    case 2: return bm25_stream_launch_cfg<float, 512, 6, 3>(h, a, stream, overlap_prev);
+    default: return bm25_stream_launch_cfg<float, 1024, 5, 3>(h, a, stream, overlap_prev);
   }
 }
 static int bm25_stream_launch(b2r_bm25* h, Bm25StreamArgs<double> a, cudaStream_t stream, bool overlap_prev) {
-  if (tunable("bm25.cfg") == 1) return bm25_stream_launch_cfg<double, 1024, 6, 2>(h, a, stream, overlap_prev);
-  return bm25_stream_launch_cfg<double, 512, 6, 2>(h, a, stream, overlap_prev);
+  switch (tunable("bm25.cfg")) {
+    case 1: return bm25_stream_launch_cfg<double, 1024, 5, 2>(h, a, stream, overlap_prev);
+    case 2: return bm25_stream_launch_cfg<double, 512, 6, 2>(h, a, stream, overlap_prev);
+    default: return bm25_stream_launch_cfg<double, 1024, 3, 3>(h, a, stream, overlap_prev);
+  }
 }
 
 static int bm25_run_stream(b2r_bm25* h, const int* term_ids_dev, const int* term_offsets_dev, int nq, int k, double* S_dev,

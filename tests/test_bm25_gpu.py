@@ -265,8 +265,9 @@ def test_streaming_kernel_variants_agree(b2r):
             assert np.array_equal(base[0][qi], want[top])
         # ... and so must the streaming kernel without its threshold slots, with a pilot launch over the first two
         # blocks of every query (the default takes one only on corpora of many blocks), and without one
+        # ... and the other ring geometries (bm25.cfg)
         for key, value in (("bm25.no_skip", 1), ("bm25.v1", 1), ("bm25.no_slots", 1), ("bm25.pilot_blocks", 2),
-                           ("bm25.pilot_blocks", -1)):
+                           ("bm25.pilot_blocks", -1), ("bm25.cfg", 1), ("bm25.cfg", 2)):
             _lib.tunable_set(key, value)
             try:
                 S, I = idx.topk(queries, k)
@@ -292,7 +293,8 @@ def test_streaming_kernel_threshold_slots_many_blocks(b2r):
     queries[5] = list(docs[1000][:6])            # its best documents are the ~400 copies
     for k in (1, 7, 30, 200):
         base = None
-        for key, value in (("bm25.no_slots", 1), ("bm25.no_slots", 0), ("bm25.pilot_blocks", -1), ("bm25.pilot_blocks", 9)):
+        for key, value in (("bm25.no_slots", 1), ("bm25.no_slots", 0), ("bm25.pilot_blocks", -1), ("bm25.pilot_blocks", 9),
+                           ("bm25.cfg", 2)):
             _lib.tunable_set(key, value)
             try:
                 got = idx.topk(queries, k)
