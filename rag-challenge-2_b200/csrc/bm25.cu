@@ -349,14 +349,19 @@ __device__ __forceinline__ void consumer_sort_desc(K* a, int n, int ct) {
 //   work item = (query, block of kStreamBlk = 4096 documents); CTA c takes items c, c + grid, ...
 //   producer   per item and token: segment bounds from the block index skip[term][block] (built once per
 //              index; no binary search on the query path), then 16-byte aligned bulk copies of the segment's
-//              (doc id, weight) arrays into a ring of 1024-posting stages.  It runs ahead of the consumers
-//              across item boundaries, so the index / term-table latency is hidden behind their work.
+//              (doc id, weight) arrays into a ring of 1024-posting stages — the stages of a token group are
+//              numbered by a warp scan and issued a ring round at a time, one per lane; a token without postings
+//              in the block issues nothing.  It runs ahead of the consumers across item boundaries, so the
+//              index / term-table latency is hidden behind their work.
 //   consumers  acc[doc] += idf * w for the postings of a stage (documents are unique within a token, tokens are
 //              separated by a named barrier: float64 sums in the reference's order, no atomics), then the
 //              fused select over the 4096 accumulators: candidates are the documents with score >= the query's
-//              global threshold tau_g (k-th best score any finished block has published), reduced to the best k
-//              by a histogram select on the ordered score bits (equal scores: ascending id), sorted, written to
-//              the per-(query, block) list; bm25_merge_kernel (one CTA per query) merges the lists.
+//              global threshold tau_g, reduced to the best k by a histogram select on the ordered score bits
+//              (equal scores: ascending id), sorted, written to the per-(query, block) list; bm25_merge_kernel
+//              (one CTA per query) merges the lists.  tau_g = the minimum over the query's k threshold slots
+//              (slot j: best score seen among documents with id % k == j — k distinct documents, hence a lower
+//              bound of the k-th best score); batches run a pilot launch over every query's first blocks so that
+//              the main launch starts with a threshold (bm25_run_stream).
 // Shared memory: 32 KiB accumulators (the select's 8 KiB histogram + 8 KiB list borrow their first 16 KiB) + the ring;
 // float32 weights: 5 stages x 1024 postings x 8 B = 40 KiB -> 73 KiB; float64 weights: 3 x 1024 x 12 B = 36 KiB -> 69 KiB;
 // three CTAs per SM either way (see bm25_stream_launch).
