@@ -1,16 +1,12 @@
 #!/usr/bin/env bash
 set -uo pipefail
 mkdir -p gpurun_out/r02_bm25
-timeout 600 python -m pytest tests/test_bm25_gpu.py tests/test_published_vectors_gpu.py tests/test_random_shapes_gpu.py -x -q -k "bm25 or hybrid or published" 2>&1 | tail -6
 {
 timeout 200 python tools/bm25_profile.py 10000000 64
-timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=5
-timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=7
-timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=8
-timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=9
-timeout 200 python tools/bm25_profile.py 10000000 1 bm25.cfg=7
-timeout 200 python tools/bm25_profile.py 10000000 8 bm25.cfg=7
+timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=3
+timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=4
+timeout 200 python tools/bm25_profile.py 10000000 64 bm25.pilot_blocks=14
 B2R_BM25_BITS=64 timeout 200 python tools/bm25_profile.py 10000000 64
-B2R_BM25_BITS=64 timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=7
-B2R_BM25_BITS=64 timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=8
-} 2>&1 | grep '^{' | tee gpurun_out/r02_bm25/alias_$(date +%H%M%S).jsonl
+B2R_BM25_BITS=64 timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=3
+B2R_BM25_BITS=64 timeout 200 python tools/bm25_profile.py 10000000 64 bm25.cfg=4
+} 2>&1 | grep '^{' | tee gpurun_out/r02_bm25/geom2_$(date +%H%M%S).jsonl
