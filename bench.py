@@ -303,7 +303,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.nq / cb["value"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        # the config of the arm this line is compared with (same workload at N GPUs); the CPU arm itself does not shard
+        "config": workload_config(args, max(1, args.gpus)),
+        "cpu_sharding": "none: one host process over the whole corpus",
         "cpu_baseline": {k: cb[k] for k in CB_KEYS},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "timed_steps": cb["queries_timed"],
