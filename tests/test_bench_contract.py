@@ -34,6 +34,29 @@ def test_reference_arm_json_line():
     assert abs(d["ms_per_step"] - 1e3 / d["value"]) < 1e-6 * d["ms_per_step"]
 
 
+def test_reference_arm_prints_the_config_of_the_arm_it_is_compared_with():
+    """At N GPUs the driver compares the two arms' `config` objects: the CPU arm names the same workload (sharding
+    rows/N of the GPU arm), says separately that it does not shard itself, and uses every host CPU for its dense leg
+    even under torchrun's OMP_NUM_THREADS=1."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="4", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "4", "--steps", "1",
+                          "--warmup", "0", "--rows", "50000", "--cpu-rows", "10000", "--ref-docs", "5000"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["n_gpus"] == 4 and d["config"]["sharding"] == "rows/4" and d["cpu_sharding"].startswith("none")
+    sys.path.insert(0, ROOT)
+    import argparse
+
+    import bench
+
+    ns = argparse.Namespace(k=d["config"]["k"], rows=d["config"]["rows"], dim=d["config"]["dim"], vocab=d["config"]["vocab"],
+                            nq=d["config"]["queries_per_step"], no_overlap=False, overlap=d["config"]["bm25_overlapped_with_scan"])
+    assert d["config"] == bench.workload_config(ns, 4)
+    threads = d["cpu_baseline"]["threads"]
+    assert threads["dense_scan_openblas"] == threads["host_cpus"] or threads["host_cpus"] == 1
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
