@@ -483,7 +483,9 @@ class _RawHits:
         The loops run in the C helper when it is built (`helper=False`: the Python statement of the same)."""
         out = []
         try:
-            if helper and _b2r_records is not None:
+            # the helper reads faiss's result types (float32 scores, int64 ids); any other index object keeps the
+            # Python loops, whose floats are the index's own
+            if helper and _b2r_records is not None and self.D.dtype == np.float32 and self.I.dtype == np.int64:
                 build = _b2r_records.append_page_records if self.parent_pages else _b2r_records.append_chunk_records
                 build(out, self.D, self.I, self.row, self.chunks, self.pages, self.sha1, query_text)
             else:
@@ -918,8 +920,7 @@ class VectorRetriever:
                 return [(q, []) for q in texts]
             # The rows stay raw here (23k hits for a 127-question batch over six databases): _finalize turns
             # them into records directly when it can, into hit tuples otherwise (_RawHits).
-            D = np.ascontiguousarray(D, dtype=np.float32)
-            I = np.ascontiguousarray(I, dtype=np.int64)
+            D, I = np.ascontiguousarray(D), np.ascontiguousarray(I)   # dtypes as the index returned them
             ids_ok = None
             if I.shape[1] > 1:  # distinct, non-negative ids per row, for the whole batch at once
                 S = np.sort(I, axis=1)

@@ -114,3 +114,16 @@ def test_direct_ok_uses_the_precomputed_flag_or_the_ids():
     assert not retrieval._RawHits("s", [], {}, D, I, 2, False, "r").direct_ok()
     assert retrieval._RawHits("s", [], {}, D, I, 1, True, "r").direct_ok()
     assert not retrieval._RawHits("s", [], {}, D, I, 0, False, "r", ids_ok=False).direct_ok()
+
+
+def test_other_result_dtypes_keep_the_python_loops():
+    """An index object that returns float64 scores (not faiss's float32) must keep its own precision: round() of the
+    float64 value, not of its float32 rounding."""
+    chunks = [{"page": 1, "text": "t"}]
+    pages = {1: {"page": 1, "text": "p"}}
+    D = np.array([[0.123449999]], np.float64)            # float32(0.123449999) = 0.12345 -> would round to 0.1235
+    I = np.array([[0]], np.int64)
+    rec = retrieval._RawHits("s", chunks, pages, D, I, 0, False, "r").records("q", print)
+    assert rec[0]["vector_similarity"] == round(0.123449999, 4) == 0.1234
+    rec = retrieval._RawHits("s", chunks, pages, D.astype(np.float32), I.astype(np.int32), 0, False, "r").records("q", print)
+    assert rec[0]["vector_similarity"] == round(float(np.float32(0.123449999)), 4)
