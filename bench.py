@@ -785,6 +785,13 @@ def run_b200(args):
 
     if rank == 0:
         value = args.nq * args.steps / (ms_total / 1e3)
+        # Both call patterns of the public API were timed over the same K steps (max over ranks each): one blocking call
+        # per question, and two questions in flight (submit the next, collect the previous).  The line's e2e is the
+        # pattern that served this configuration better — on several GPUs keeping two in flight hides the host's part
+        # of a 0.74 ms step; on one GPU the two are within a percent and the blocking call is the steadier one.
+        ms_e2e_two = ms_e2e
+        two_better = can_submit and ms_e2e_two <= ms_e2e_sync
+        ms_e2e = ms_e2e_two if two_better else ms_e2e_sync
         e2e_value = args.nq * args.steps / (ms_e2e / 1e3)
         peak, peak_src = measured_peak_gbs()
         alg_bytes = 4.0 * (hi - lo) * args.dim
@@ -795,10 +802,14 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps,
-                    "in_flight": (2 if can_submit else 1),
+                    "in_flight": (2 if two_better else 1),
                     "how": ("HybridIndex.search_hybrid_submit / _collect: numpy in, numpy out, the next question submitted while the "
                             "previous one is on the GPU; every step's H2D copy and result delivery inside the timed region"
-                            if can_submit else "HybridIndex.search_hybrid, one blocking call per step"),
+                            if two_better else
+                            "HybridIndex.search_hybrid: numpy in, numpy out, one blocking call per step; every step's H2D copy and "
+                            "result delivery inside the timed region"),
+                    "two_in_flight": ({"value": args.nq * args.steps / (ms_e2e_two / 1e3), "ms_per_step": ms_e2e_two / args.steps}
+                                      if can_submit else None),
                     "one_call_at_a_time": {"value": args.nq * args.steps / (ms_e2e_sync / 1e3), "ms_per_step": ms_e2e_sync / args.steps}},
             "gpu_launches": int(launches), "collectives": int(collectives), "exchange": exchange,
             "roofline": {"bound": "hbm", "kernel": "flat_scan_tma_kernel", "achieved": achieved, "peak": peak,
