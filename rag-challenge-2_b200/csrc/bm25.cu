@@ -307,6 +307,22 @@ __device__ __forceinline__ void mbar_wait_wd(u64* bar, u32 parity) {
   }
 }
 
+// one NON-BLOCKING probe of an mbarrier phase (test_wait; try_wait may suspend the thread for a while): true when the
+// phase with this parity has completed
+__device__ __forceinline__ bool mbar_probe(u64* bar, u32 parity) {
+  u32 done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0u;
+}
+
 // barrier over the 256 consumer threads of the streaming kernel (the producer warp never joins)
 __device__ __forceinline__ void named_bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -566,17 +582,25 @@ __global__ void __launch_bounds__(kStreamThreads, MINB) bm25_stream_kernel(const
           const long long q0 = __shfl_sync(0xffffffffu, p0, u), q1 = __shfl_sync(0xffffffffu, p1, u);
           const double qidf = __shfl_sync(0xffffffffu, tidf, u);
           const int pu = __shfl_sync(0xffffffffu, pre, u), nu = __shfl_sync(0xffffffffu, nch, u);
-          if (on) {
-            const long long a0 = q0 & ~3LL, a1 = (q1 + 3) & ~3LL;
-            const int c = g - pu;
-            const long long c0 = a0 + static_cast<long long>(c) * CHUNK;
-            const long long c1 = min(a1, c0 + CHUNK);
-            const int cnt = static_cast<int>(c1 - c0);
-            const bool last_chunk = c == nu - 1;
-            const bool last_token = last_group && g == n_stages - 1;  // the item's last stage (later tokens are absent here)
-            const u32 n = gs + static_cast<u32>(g);
-            const int slot = static_cast<int>(n % STAGES);
-            mbar_wait_wd(&empty[slot], ((n / STAGES) & 1u) ^ 1u);
+          const long long a0 = q0 & ~3LL, a1 = (q1 + 3) & ~3LL;
+          const int c = g - pu;
+          const long long c0 = a0 + static_cast<long long>(c) * CHUNK;
+          const long long c1 = min(a1, c0 + CHUNK);
+          const int cnt = static_cast<int>(c1 - c0);
+          const bool last_chunk = c == nu - 1;
+          const bool last_token = last_group && g == n_stages - 1;  // the item's last stage (later tokens are absent here)
+          const u32 n = gs + static_cast<u32>(g);
+          const int slot = static_cast<int>(n % STAGES);
+          const u32 free_parity = ((n / STAGES) & 1u) ^ 1u;
+          // A lane must not WAIT for its slot inside the branch: the warp would reconverge behind the slowest lane, i.e.
+          // issue nothing of a round until every slot of the ring is free — the ring would drain between rounds.  Every
+          // lane probes its slot once per turn instead; slots come free in order, so the round's stages go out one by
+          // one as the consumers release them, and the lanes still issue in parallel whenever several are free.
+          bool todo = on;
+          for (u32 spins = 0; __any_sync(0xffffffffu, todo); ++spins) {
+            if (spins == (1u << 27)) __trap();
+            if (!(todo && mbar_probe(&empty[slot], free_parity))) continue;
+            todo = false;
             StreamMeta& m = meta[slot];
             m.idf = qidf;
             m.fv = static_cast<int>(max(q0 - c0, 0LL));
