@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu under gpurun)")
 
 
+def pytest_sessionstart(session):
+    """The shared libraries are build artefacts (git-ignored): a fresh checkout builds them once before the first test
+    (nvcc cross-compiles sm_100a without a GPU).  B2R_NO_AUTOBUILD=1 skips this."""
+    import shutil
+    import subprocess
+
+    lib = os.path.join(ROOT, "rag-challenge-2_b200", "libb2r.so")
+    if os.path.exists(lib) or os.environ.get("B2R_NO_AUTOBUILD") or shutil.which("nvcc") is None:
+        return
+    subprocess.run(["bash", os.path.join(ROOT, "build.sh")], cwd=ROOT, check=False)
+
+
 @pytest.fixture(scope="session")
 def b2r():
     import rag_challenge_2_b200 as pkg
